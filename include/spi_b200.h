@@ -1,0 +1,119 @@
+/* spi_b200.h -- C ABI of libspi_b200.so (sm_100a kernels for the SPI inversion hot path).
+ *
+ * Conventions (restating the reference plugin conventions of SURVEY.md §8b.1 as a plain C ABI):
+ *   - every pointer is a DEVICE pointer unless named `*_strides` / `*_out` (host); shapes are plain ints;
+ *   - inputs are borrowed, outputs are caller-allocated (the Python shim allocates them with torch);
+ *   - work is enqueued on `stream`; no host synchronisation, no internal threads;
+ *   - return value: 0 = ok, -1 = invalid argument (Python raises RuntimeError with spi_last_error(), as
+ *     TORCH_CHECK does in the reference), -2 = no specialised kernel (soft error: the reference's
+ *     `return_code = -1` of filtered_lrelu.cpp:53-56), -3 = CUDA launch failure;
+ *   - dtype codes: 0 = float32, 1 = float16, 2 = float64; index math is 64-bit where tensors can exceed INT_MAX.
+ *   - a NULL pointer means "operand absent" (the reference passes empty tensors, bias_act.py:138).
+ */
+#ifndef SPI_B200_H
+#define SPI_B200_H
+
+#include <cuda_runtime.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library state ---------------------------------------------------------------------------------- */
+const char* spi_last_error(void);
+unsigned long long spi_launch_count(void);   /* kernels launched by this library since the last reset */
+void spi_reset_launch_count(void);
+int spi_abi_version(void);
+
+/* ---- L1 operators: replace the pybind plugins built by eg3d/torch_utils/custom_ops.py:61 ------------- */
+
+/* bias_act plugin op: eg3d/torch_utils/ops/bias_act.cpp:36-93 (kernel bias_act.cu:28-147).
+ * grad = 0/1/2; act = 1..9 (linear, relu, lrelu, tanh, sigmoid, elu, selu, softplus, swish; bias_act.py:23-33);
+ * clamp < 0 disables clamping; step_b = x.stride(dim), size_b = b.numel(); x must be dense. */
+int spi_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                 long long numel, int size_b, int step_b, int dtype, int grad, int act, float alpha, float gain,
+                 float clamp, cudaStream_t stream);
+
+/* upfirdn2d plugin op: eg3d/torch_utils/ops/upfirdn2d.cpp:20-105 (kernels upfirdn2d.cu:33-204).
+ * f: fp32 [fh, fw]; strides in elements, order (n, c, h, w); y is [n, c, out_h, out_w] with
+ * out = (in*up + pad0 + pad1 - f + down) / down (upfirdn2d.cpp:49-50). */
+int spi_upfirdn2d(const void* x, const float* f, void* y, int dtype, int n, int c, int in_h, int in_w,
+                  const long long* x_strides, const long long* y_strides, int fh, int fw, int upx, int upy, int downx,
+                  int downy, int padx0, int padx1, int pady0, int pady1, int flip, float gain, cudaStream_t stream);
+
+/* filtered_lrelu plugin op: eg3d/torch_utils/ops/filtered_lrelu.cpp:20-213 (kernel filtered_lrelu.cu:144).
+ * fu/fd: fp32 rank-2 filters (separable 1-D filters are expanded by the caller); s: uint8 sign tensor
+ * [n, c, s_h, s_w_bytes] (4 elements per byte) or NULL; sign_mode 0 none / 1 write / 2 read (+ offsets sx, sy). */
+int spi_filtered_lrelu_sign_shape(int yh, int yw, int down, int fdh, int fdw, int* sh_out, int* sw_bytes_out);
+int spi_filtered_lrelu(const void* x, void* y, const void* b, unsigned char* s, const float* fu, const float* fd, int dtype,
+                       int n, int c, int xh, int xw, const long long* x_strides, const long long* y_strides, int fuh, int fuw,
+                       int fdh, int fdw, int up, int down, int px0, int px1, int py0, int py1, int s_h, int s_w_bytes, int sx,
+                       int sy, float gain, float slope, float clamp, int flip, int sign_mode, cudaStream_t stream);
+/* filtered_lrelu_act_ plugin op: filtered_lrelu.cpp:217-293 (kernel filtered_lrelu.cu:1110); in place on x. */
+int spi_filtered_lrelu_act(void* x, unsigned char* s, int dtype, int n, int c, int h, int w, const long long* x_strides,
+                           int s_h, int s_w_bytes, int sx, int sy, float gain, float slope, float clamp, int sign_mode,
+                           cudaStream_t stream);
+
+/* ---- fused volume renderer: replaces eg3d/training/volumetric_rendering/{renderer,ray_marcher,ray_sampler}.py
+ *      and OSGDecoder (eg3d/training/triplane.py:112-135) ---------------------------------------------- */
+
+/* ImportanceRenderer.forward (renderer.py:88-140) fused with RaySampler.forward (ray_sampler.py:24-61).
+ * planes: channels-last [n, plane_h, plane_w, 96]; origins/dirs [n, R, 3]; jitter [n, R, dc]; u [n*R, df];
+ * decoder tensors as stored in the state dict (decoder.net.0/2.{weight,bias}), lr_mul = decoder_lr_mul; outputs feat [n, R, 32],
+ * depth [n, R] (clamped to the global sample-depth range, ray_marcher.py:49-50), wsum [n, R];
+ * depths_all [n, R, dc+df] is the sorted merged depth list the backward pass needs; sigma_all optional (NULL);
+ * minmax: 2 ints of scratch that the backward pass re-reads. */
+int spi_render_forward(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
+                       const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
+                       float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n, int rays_per_image,
+                       int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end, float box_warp, int disparity,
+                       cudaStream_t stream);
+/* Backward of the above w.r.t. planes (accumulated into g_planes, may be NULL) and, when the sc_* buffers are
+ * given, the per-sample rows [S,32] [S,64] [S,64] [S,36] from which the decoder weight gradients are formed
+ * (dW1 = dpre^T f, dW2 = dout^T hid; S = n*R*(dc+df)). */
+int spi_render_backward(const float* planes, const float* origins, const float* dirs, const float* depths_all, const int* minmax,
+                        const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, const float* g_feat,
+                        const float* g_depth, float* g_planes, float* sc_f, float* sc_hid, float* sc_dpre, float* sc_dout, int n,
+                        int rays_per_image, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream);
+/* ImportanceRenderer.run_model (renderer.py:142-149) on arbitrary points: coords [n, m, 3] -> rgb [n, m, 32],
+ * sigma [n, m]; used by TriPlaneGenerator.sample / sample_mixed (triplane.py:91-102). */
+int spi_points_forward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,
+                       const float* b2, float lr_mul, float* rgb, float* sigma, int n, int m, int plane_h, int plane_w, float box_warp,
+                       cudaStream_t stream);
+int spi_points_backward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,
+                        const float* b2, float lr_mul, const float* g_rgb, const float* g_sigma, float* g_planes, float* sc_f, float* sc_hid,
+                        float* sc_dpre, float* sc_dout, int n, int m, int plane_h, int plane_w, float box_warp,
+                        cudaStream_t stream);
+/* Stand-alone stages (bit-exact index parity). */
+int spi_ray_sampler(const float* cam, int n, int res, float* origins, float* dirs, cudaStream_t stream);      /* ray_sampler.py:24 */
+int spi_ray_march(const float* colors, const float* sigma, const float* depths, int rays, int d, int c, float* rgb,
+                  float* depth, float* weights, int* minmax, cudaStream_t stream);                            /* ray_marcher.py:25 */
+int spi_sample_importance(const float* depths, const float* weights, const float* u, int rays, int dc, int df, float* fine,
+                          int* inds, float* cdf, cudaStream_t stream);                                        /* renderer.py:194-253 */
+int spi_inverse_cdf(const float* bins, const float* cdf, const float* u, int rays, int ncdf, int nbins, int df, float* fine,
+                    int* inds, cudaStream_t stream);                                                          /* renderer.py:241-253 */
+int spi_unify_samples(const float* depths_coarse, const float* depths_fine, int rays, int dc, int df, int* perm,
+                      float* sorted, cudaStream_t stream);                                                    /* renderer.py:157-167 */
+
+/* ---- depth-guided 3-D warp: replaces rotate() (spi/utils/rotate.py:92-116) --------------------------- */
+/* cameras [n, 25]; depths [n, 1, depth_res, depth_res]; image [n, 3, res, res]; mask [n, 1, res, res] or NULL;
+ * *_bs = batch strides in elements of the source tensors (0 broadcasts one source over n views, replacing the
+ * `.repeat(rot_bs, ...)` copies of rot_bbox_cx_coach.py:93-99). */
+int spi_rotate(const float* target_camera, const float* target_depth, const float* src_image, const float* src_camera,
+               const float* src_depth, const float* src_mask, float* out_rgb, float* out_mask, int n, int res, int depth_res,
+               long long src_camera_bs, long long src_depth_bs, long long src_image_bs, long long src_mask_bs, float eps,
+               cudaStream_t stream);
+
+/* ---- optimiser / streaming helpers -------------------------------------------------------------------- */
+/* torch.optim.Adam step (base_coach.py:134, *_projector.py:58) over flat fp32 arenas; hyper (device, optional)
+ * = {lr, 1-beta1^t, 1-beta2^t}; zero_grad != 0 clears the gradient arena in the same pass. */
+int spi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                  float beta2, float eps, int step, const float* hyper, int zero_grad, cudaStream_t stream);
+/* F.interpolate(..., (H/2, W/2), mode='bilinear'|'area') at exactly half size (lpips.py:38-39, bbox_cx_loss.py:161-163,
+ * w_projector.py:50,83); contiguous [planes, 2*out_h, 2*out_w] -> [planes, out_h, out_w]; backward != 0 runs the adjoint. */
+int spi_downsample2x(const float* x, float* y, long long planes, int out_h, int out_w, int backward, cudaStream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPI_B200_H */

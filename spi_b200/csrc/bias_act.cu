@@ -1,0 +1,176 @@
+// bias_act for sm_100a: y = clamp(act(x + b) * gain), plus first/second-order gradient modes.
+//
+// Replaces the reference plugin op `bias_act` (eg3d/torch_utils/ops/bias_act.cpp:36-93,
+// kernel bias_act.cu:28-147) with the same argument meaning:
+//   grad=0: x is the activation input;            y = clamp(act(x+b)*gain)
+//   grad=1: x is the incoming gradient dy;        y = x * act'(.) * gain, masked where the fwd clamp saturated
+//   grad=2: x is the gradient of grad=1's output; second-order term (uses `dy`)
+// `xref` / `yref` are the saved forward input / output; empty (NULL) means absent.
+//
+// B200 design: pure HBM streaming.  Each thread moves 16 bytes per tensor per iteration (LDG.128 / STG.128,
+// L1 no-allocate), 2 independent iterations in flight, grid sized to a multiple of the SM count.  The bias index is
+// resolved per vector: stepB % VEC == 0 (NCHW) -> one scalar bias per vector; stepB == 1 (channels_last) -> a
+// vector of consecutive biases.  Anything else takes the scalar tail path.
+#include "common.cuh"
+
+namespace {
+
+struct BiasActParams {
+    const void* x; const void* b; const void* xref; const void* yref; const void* dy; void* y;
+    int grad, act;
+    float alpha, gain, clamp;
+    long long n;
+    int sizeB, stepB, force_scalar;
+};
+
+template <class S, int A>
+__device__ __forceinline__ S act_eval(S x, S b, S xref, S yref, S dy, int G, S alpha, S gain, S clamp) {
+    const S one = (S)1, two = (S)2, expRange = (S)80, halfExpRange = (S)40;
+    const S seluScale = (S)1.0507009873554804934193349852946;
+    const S seluAlpha = (S)1.6732632423543772848170429916717;
+    S yy = (gain != 0) ? yref / gain : (S)0;
+    S y = 0;
+    if (G == 0) x += b; else xref += b;
+    if (A == 1) { y = x; }
+    if (A == 2) { y = (G == 0) ? ((x > 0) ? x : (S)0) : (G == 1 ? ((yy > 0) ? x : (S)0) : (S)0); }
+    if (A == 3) { y = (G == 0) ? ((x > 0) ? x : x * alpha) : (G == 1 ? ((yy > 0) ? x : x * alpha) : (S)0); }
+    if (A == 4) {
+        if (G == 0) { S c = exp(x), d = one / c; y = (x < -expRange) ? -one : (x > expRange) ? one : (c - d) / (c + d); }
+        if (G == 1) y = x * (one - yy * yy);
+        if (G == 2) y = x * (one - yy * yy) * (-two * yy);
+    }
+    if (A == 5) {
+        if (G == 0) y = (x < -expRange) ? (S)0 : one / (exp(-x) + one);
+        if (G == 1) y = x * yy * (one - yy);
+        if (G == 2) y = x * yy * (one - yy) * (one - two * yy);
+    }
+    if (A == 6) {
+        if (G == 0) y = (x >= 0) ? x : exp(x) - one;
+        if (G == 1) y = (yy >= 0) ? x : x * (yy + one);
+        if (G == 2) y = (yy >= 0) ? (S)0 : x * (yy + one);
+    }
+    if (A == 7) {
+        if (G == 0) y = (x >= 0) ? seluScale * x : (seluScale * seluAlpha) * (exp(x) - one);
+        if (G == 1) y = (yy >= 0) ? x * seluScale : x * (yy + seluScale * seluAlpha);
+        if (G == 2) y = (yy >= 0) ? (S)0 : x * (yy + seluScale * seluAlpha);
+    }
+    if (A == 8) {
+        if (G == 0) y = (x > expRange) ? x : log(exp(x) + one);
+        if (G == 1) y = x * (one - exp(-yy));
+        if (G == 2) { S c = exp(-yy); y = x * c * (one - c); }
+    }
+    if (A == 9) {
+        if (G == 0) y = (x < -expRange) ? (S)0 : x / (exp(-x) + one);
+        else {
+            S c = exp(xref), d = c + one;
+            if (G == 1) y = (xref > halfExpRange) ? x : x * c * (xref + d) / (d * d);
+            else y = (xref > halfExpRange) ? (S)0 : x * c * (xref * (two - d) + two * d) / (d * d * d);
+            yref = (xref < -expRange) ? (S)0 : xref / (exp(-xref) + one) * gain;
+        }
+    }
+    y *= gain * dy;
+    if (clamp >= 0) {
+        if (G == 0) y = (y > -clamp && y < clamp) ? y : ((y >= 0) ? clamp : -clamp);
+        else y = (yref > -clamp && yref < clamp) ? y : (S)0;
+    }
+    return y;
+}
+
+template <class T> struct Vec;       // 16-byte vectors
+template <> struct Vec<float>  { static constexpr int N = 4; };
+template <> struct Vec<__half> { static constexpr int N = 8; };
+template <> struct Vec<double> { static constexpr int N = 2; };
+
+template <class T, int N> struct alignas(16) Pack { T v[N]; };
+
+template <class T, int A>
+__global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p) {
+    typedef typename Acc<T>::t S;
+    constexpr int V = Vec<T>::N;
+    typedef Pack<T, V> P;
+    const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const int G = p.grad;
+    const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* xr = (const T*)p.xref;
+    const T* yr = (const T*)p.yref; const T* dyp = (const T*)p.dy; T* y = (T*)p.y;
+    const long long nvec = p.n / V;
+    const bool vec_ok = !p.force_scalar && ((b == nullptr) || (p.stepB % V == 0) || (p.stepB == 1 && p.sizeB % V == 0));
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (vec_ok) {
+        for (; i < nvec; i += stride) {
+            P vx = ((const P*)x)[i], vxr, vyr, vdy, vb, out;
+            if (xr) vxr = ((const P*)xr)[i];
+            if (yr) vyr = ((const P*)yr)[i];
+            if (dyp) vdy = ((const P*)dyp)[i];
+            long long e0 = i * V;
+            S bs = 0;
+            bool bvec = false;
+            if (b) {
+                if (p.stepB == 1) { vb = *(const P*)(b + (e0 % p.sizeB)); bvec = true; }
+                else bs = (S)b[(e0 / p.stepB) % p.sizeB];
+            }
+#pragma unroll
+            for (int k = 0; k < V; k++) {
+                S bb = bvec ? (S)vb.v[k] : bs;
+                out.v[k] = (T)act_eval<S, A>((S)vx.v[k], bb, xr ? (S)vxr.v[k] : (S)0, yr ? (S)vyr.v[k] : (S)0,
+                                             dyp ? (S)vdy.v[k] : (S)1, G, alpha, gain, clamp);
+            }
+            ((P*)y)[i] = out;
+        }
+    }
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long e = (vec_ok ? nvec * V : 0) + tid; e < p.n; e += stride) {
+        S bb = b ? (S)b[(e / p.stepB) % p.sizeB] : (S)0;
+        y[e] = (T)act_eval<S, A>((S)x[e], bb, xr ? (S)xr[e] : (S)0, yr ? (S)yr[e] : (S)0, dyp ? (S)dyp[e] : (S)1, G,
+                                 alpha, gain, clamp);
+    }
+}
+
+template <class T>
+void* pick_kernel(int act) {
+    switch (act) {
+        case 1: return (void*)bias_act_kernel<T, 1>;
+        case 2: return (void*)bias_act_kernel<T, 2>;
+        case 3: return (void*)bias_act_kernel<T, 3>;
+        case 4: return (void*)bias_act_kernel<T, 4>;
+        case 5: return (void*)bias_act_kernel<T, 5>;
+        case 6: return (void*)bias_act_kernel<T, 6>;
+        case 7: return (void*)bias_act_kernel<T, 7>;
+        case 8: return (void*)bias_act_kernel<T, 8>;
+        case 9: return (void*)bias_act_kernel<T, 9>;
+    }
+    return nullptr;
+}
+
+}  // namespace
+
+extern "C" int spi_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                            long long numel, int size_b, int step_b, int dtype, int grad, int act, float alpha,
+                            float gain, float clamp, cudaStream_t stream) {
+    SPI_CHECK_ARG(x && y, "bias_act: x and y must be non-null");
+    SPI_CHECK_ARG(numel >= 0 && numel <= 2147483647LL, "bias_act: x is too large");
+    SPI_CHECK_ARG(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2");
+    SPI_CHECK_ARG(act >= 1 && act <= 9, "bias_act: no CUDA kernel found for the specified activation func");
+    SPI_CHECK_ARG(!b || (size_b > 0 && step_b > 0), "bias_act: b has wrong number of elements");
+    if (numel == 0) return SPI_OK;
+    void* k = nullptr;
+    int vec = 4;
+    if (dtype == SPI_DT_F32) { k = pick_kernel<float>(act); vec = 4; }
+    else if (dtype == SPI_DT_F16) { k = pick_kernel<__half>(act); vec = 8; }
+    else if (dtype == SPI_DT_F64) { k = pick_kernel<double>(act); vec = 2; }
+    SPI_CHECK_ARG(k, "bias_act: unsupported dtype %d", dtype);
+    // The vector path needs 16-byte aligned pointers (torch allocations are; offset views may not be).
+    uintptr_t al = (uintptr_t)x | (uintptr_t)y | (uintptr_t)xref | (uintptr_t)yref | (uintptr_t)dy | (uintptr_t)b;
+    BiasActParams p{x, b, xref, yref, dy, y, grad, act, alpha, gain, clamp, numel, b ? size_b : 1, b ? step_b : 1,
+                    (al & 15) ? 1 : 0};
+    const int block = 256;
+    long long work = p.force_scalar ? numel : (numel + vec - 1) / vec;
+    long long blocks = (work + block * 2 - 1) / (block * 2);
+    long long cap = (long long)spi_num_sms() * 16;
+    int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+    void* args[] = {&p};
+    cudaError_t e = cudaLaunchKernel(k, dim3(grid), dim3(block), args, 0, stream);
+    SPI_COUNT_LAUNCH(1);
+    if (e != cudaSuccess) { spi_set_error("bias_act: %s", cudaGetErrorString(e)); return SPI_ERR_CUDA; }
+    return SPI_OK;
+}

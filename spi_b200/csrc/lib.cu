@@ -1,0 +1,18 @@
+// libspi_b200: library-wide state (error string, launch counter, version).
+#include "common.cuh"
+#include <stdarg.h>
+
+static thread_local char g_err[512] = "";
+unsigned long long g_spi_launches = 0;
+
+void spi_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* spi_last_error() { return g_err; }
+extern "C" unsigned long long spi_launch_count() { return g_spi_launches; }
+extern "C" void spi_reset_launch_count() { g_spi_launches = 0; }
+extern "C" int spi_abi_version() { return 1; }

@@ -1,0 +1,103 @@
+// Fused Adam and small streaming helpers for sm_100a.
+//
+// Adam replaces `torch.optim.Adam(...).step()` as used at spi/training/coaches/base_coach.py:132-135 (all
+// G.parameters(), lr 3e-4) and spi/training/projectors/*_projector.py:55-58 ([w_opt] + noise buffers): defaults
+// betas=(0.9, 0.999), eps=1e-8, no weight decay, no amsgrad.  Same arithmetic as torch's single-tensor path:
+//   m = m + (g - m)*(1-b1);  v = v*b2 + g*g*(1-b2);  p -= (lr/bc1) * m / (sqrt(v)/sqrt(bc2) + eps)
+// The host keeps every parameter of an optimiser as a view into one flat fp32 arena (params, grads, m, v), so one
+// launch streams 28 B/param (836 MB per G-step) with 128-bit loads/stores instead of ~400 foreach launches.
+// `hyper` (device, optional) = {lr, bc1, bc2} lets a captured CUDA graph be replayed with a new learning rate.
+#include "common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
+                                                   float bc1, float bc2, const float* __restrict__ hyper, int zero_grad, float* gz) {
+    if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }
+    const float step_size = lr / bc1;
+    const float rsbc2 = 1.f / sqrtf(bc2);
+    const long long nv = n / 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 pp = ((float4*)p)[i], gg = ldg_stream((const float4*)g + i), mm = ((float4*)m)[i], vv = ((float4*)v)[i];
+        float* P = (float*)&pp; float* G = (float*)&gg; float* M = (float*)&mm; float* V = (float*)&vv;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            M[k] = M[k] + (G[k] - M[k]) * (1.f - b1);
+            V[k] = V[k] * b2 + G[k] * G[k] * (1.f - b2);
+            float denom = sqrtf(V[k]) * rsbc2 + eps;
+            P[k] = P[k] - step_size * (M[k] / denom);
+        }
+        ((float4*)p)[i] = pp; ((float4*)m)[i] = mm; ((float4*)v)[i] = vv;
+        if (zero_grad) ((float4*)gz)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gk = g[i];
+        float mk = m[i] + (gk - m[i]) * (1.f - b1);
+        float vk = v[i] * b2 + gk * gk * (1.f - b2);
+        m[i] = mk; v[i] = vk;
+        p[i] = p[i] - step_size * (mk / (sqrtf(vk) * rsbc2 + eps));
+        if (zero_grad) gz[i] = 0.f;
+    }
+}
+
+// y[i] = mean of the 2x2 block (== F.interpolate bilinear/area at exactly 1/2 scale, align_corners=False), NCHW planes
+__global__ void __launch_bounds__(256) half_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long planes, int oh, int ow) {
+    const long long total = planes * oh * ow;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % ow); long long r = i / ow; int oy = (int)(r % oh); long long pl = r / oh;
+        const float2* r0 = (const float2*)(x + (pl * 2 * oh + 2 * oy) * (2LL * ow)) + ox;
+        const float2* r1 = (const float2*)(x + (pl * 2 * oh + 2 * oy + 1) * (2LL * ow)) + ox;
+        float2 a = __ldg(r0), b = __ldg(r1);
+        // torch's bilinear: (1-l)*((1-l)*a.x + l*a.y) + l*(...) with l = 0.5
+        y[i] = 0.5f * (0.5f * a.x + 0.5f * a.y) + 0.5f * (0.5f * b.x + 0.5f * b.y);
+    }
+}
+
+__global__ void __launch_bounds__(256) half_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, long long planes, int oh, int ow) {
+    const long long total = planes * oh * ow;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ox = (int)(i % ow); long long r = i / ow; int oy = (int)(r % oh); long long pl = r / oh;
+        float g = 0.25f * gy[i];
+        float2* r0 = (float2*)(gx + (pl * 2 * oh + 2 * oy) * (2LL * ow)) + ox;
+        float2* r1 = (float2*)(gx + (pl * 2 * oh + 2 * oy + 1) * (2LL * ow)) + ox;
+        *r0 = make_float2(g, g); *r1 = make_float2(g, g);
+    }
+}
+
+}  // namespace
+
+extern "C" int spi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                             float beta2, float eps, int step, const float* hyper, int zero_grad, cudaStream_t stream) {
+    SPI_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
+    SPI_CHECK_ARG(step >= 1 || hyper, "adam_step: step must be >= 1");
+    SPI_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "adam_step: arenas must be 16-byte aligned");
+    if (n == 0) return SPI_OK;
+    float bc1 = 1.f, bc2 = 1.f;
+    if (!hyper) {
+        bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+        bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+    }
+    long long blocks = (n / 4 + 255) / 256;
+    long long cap = (long long)spi_num_sms() * 8;
+    int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+    adam_kernel<<<grid, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, hyper, zero_grad, (float*)grad);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("adam_step");
+    return SPI_OK;
+}
+
+extern "C" int spi_downsample2x(const float* x, float* y, long long planes, int out_h, int out_w, int backward, cudaStream_t stream) {
+    SPI_CHECK_ARG(x && y && out_h >= 1 && out_w >= 1, "downsample2x: bad argument");
+    SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 7) == 0, "downsample2x: tensors must be 8-byte aligned");
+    long long total = planes * out_h * out_w;
+    if (total == 0) return SPI_OK;
+    long long cap = (long long)spi_num_sms() * 8, blocks = (total + 255) / 256;
+    int grid = (int)(blocks > cap ? cap : blocks);
+    if (!backward) half_fwd_kernel<<<grid, 256, 0, stream>>>(x, y, planes, out_h, out_w);
+    else half_bwd_kernel<<<grid, 256, 0, stream>>>(x, y, planes, out_h, out_w);   // x = grad_out [planes,oh,ow], y = grad_in
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("downsample2x");
+    return SPI_OK;
+}

@@ -1,0 +1,126 @@
+"""Fused bias + activation (drop-in for `torch_utils.ops.bias_act`, eg3d/torch_utils/ops/bias_act.py).
+
+Same Python surface: `activation_funcs` table, `bias_act(x, b, dim, act, alpha, gain, clamp, impl)`.
+The arithmetic runs in `spi_bias_act` (spi_b200/csrc/bias_act.cu) -- forward, first- and second-order gradient modes,
+exactly the plugin's `grad` = 0/1/2 protocol (bias_act.cpp:36).  CUDA only: a CPU tensor raises.
+"""
+import math
+from types import SimpleNamespace
+
+import torch
+
+from ... import _lib
+
+# eg3d/torch_utils/ops/bias_act.py:23-33 (cuda_idx = kernel id, ref = which tensor the backward needs)
+activation_funcs = {
+    'linear':   SimpleNamespace(def_alpha=0,   def_gain=1,            cuda_idx=1, ref='',  has_2nd_grad=False),
+    'relu':     SimpleNamespace(def_alpha=0,   def_gain=math.sqrt(2), cuda_idx=2, ref='y', has_2nd_grad=False),
+    'lrelu':    SimpleNamespace(def_alpha=0.2, def_gain=math.sqrt(2), cuda_idx=3, ref='y', has_2nd_grad=False),
+    'tanh':     SimpleNamespace(def_alpha=0,   def_gain=1,            cuda_idx=4, ref='y', has_2nd_grad=True),
+    'sigmoid':  SimpleNamespace(def_alpha=0,   def_gain=1,            cuda_idx=5, ref='y', has_2nd_grad=True),
+    'elu':      SimpleNamespace(def_alpha=0,   def_gain=1,            cuda_idx=6, ref='y', has_2nd_grad=True),
+    'selu':     SimpleNamespace(def_alpha=0,   def_gain=1,            cuda_idx=7, ref='y', has_2nd_grad=True),
+    'softplus': SimpleNamespace(def_alpha=0,   def_gain=1,            cuda_idx=8, ref='y', has_2nd_grad=True),
+    'swish':    SimpleNamespace(def_alpha=0,   def_gain=math.sqrt(2), cuda_idx=9, ref='x', has_2nd_grad=True),
+}
+
+
+def _dense_like(x):
+    """Memory format the op works in: channels_last if x already is, else contiguous (bias_act.py:137-138)."""
+    if x.ndim == 4 and x.stride(1) == 1 and x.shape[1] > 1:
+        return torch.channels_last
+    return torch.contiguous_format
+
+
+def _plugin_bias_act(x, b, xref, yref, dy, grad, dim, act_idx, alpha, gain, clamp):
+    """The plugin entry point `bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)` (bias_act.cpp:36)."""
+    if not x.is_cuda:
+        raise RuntimeError('x must reside on CUDA device')
+    if b is not None and b.numel():
+        if b.ndim != 1:
+            raise RuntimeError('b must have rank 1')
+        if not (0 <= dim < x.ndim):
+            raise RuntimeError('dim is out of bounds')
+        if b.numel() != x.shape[dim]:
+            raise RuntimeError('b has wrong number of elements')
+        if b.dtype != x.dtype:
+            raise RuntimeError('b must have the same dtype and device as x')
+    y = torch.empty_like(x)        # preserves a dense layout
+    if x.numel() == 0:
+        return y
+    for t in (xref, yref, dy):
+        if t is not None and t.numel() and (t.shape != x.shape or t.stride() != x.stride()):
+            raise RuntimeError('xref/yref/dy must have the same shape and layout as x')
+    has_b = b is not None and b.numel() > 0
+    _lib.check(_lib.load().spi_bias_act(
+        _lib.ptr(x), _lib.ptr(b), _lib.ptr(xref), _lib.ptr(yref), _lib.ptr(dy), _lib.ptr(y), x.numel(),
+        b.numel() if has_b else 1, x.stride(dim) if has_b else 1, _lib.dtype_code(x), grad, act_idx,
+        alpha, gain, clamp, _lib.stream()))
+    return y
+
+
+class _BiasActGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dy, x, b, y, cfg):
+        dim, spec, alpha, gain, clamp = cfg
+        dx = _plugin_bias_act(dy, b, x, y, None, 1, dim, spec.cuda_idx, alpha, gain, clamp)
+        ctx.cfg = cfg
+        ctx.save_for_backward(dy if spec.has_2nd_grad else None, x, b, y)
+        return dx
+
+    @staticmethod
+    def backward(ctx, d_dx):
+        dim, spec, alpha, gain, clamp = ctx.cfg
+        dy, x, b, y = ctx.saved_tensors
+        d_dx = d_dx.contiguous(memory_format=_dense_like(d_dx))
+        d_dy = d_x = d_b = None
+        if ctx.needs_input_grad[0]:
+            d_dy = _BiasActGrad.apply(d_dx, x, b, y, ctx.cfg)
+        if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            d_x = _plugin_bias_act(d_dx, b, x, y, dy, 2, dim, spec.cuda_idx, alpha, gain, clamp)
+            if ctx.needs_input_grad[2]:
+                d_b = d_x.sum([i for i in range(d_x.ndim) if i != dim])
+        return d_dy, d_x, d_b, None, None
+
+
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, b, cfg):
+        dim, spec, alpha, gain, clamp = cfg
+        fmt = _dense_like(x)
+        x = x.contiguous(memory_format=fmt)
+        b = b.contiguous() if b is not None else None
+        y = x
+        if spec.cuda_idx != 1 or gain != 1 or clamp >= 0 or b is not None:
+            y = _plugin_bias_act(x, b, None, None, None, 0, dim, spec.cuda_idx, alpha, gain, clamp)
+        keep_x = 'x' in spec.ref or spec.has_2nd_grad
+        ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if 'y' in spec.ref else None)
+        ctx.cfg, ctx.fmt = cfg, fmt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dim, spec, alpha, gain, clamp = ctx.cfg
+        x, b, y = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=ctx.fmt)
+        dx = db = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dx = dy
+            if spec.cuda_idx != 1 or gain != 1 or clamp >= 0:
+                dx = _BiasActGrad.apply(dy, x, b, y, ctx.cfg)
+        if ctx.needs_input_grad[1]:
+            db = dx.sum([i for i in range(dx.ndim) if i != dim])
+        return dx, db, None
+
+
+def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
+    """y = clamp(act(x + b) * gain); see eg3d/torch_utils/ops/bias_act.py:54-88 for the argument contract."""
+    assert isinstance(x, torch.Tensor)
+    assert impl in ['ref', 'cuda']
+    assert clamp is None or clamp >= 0
+    spec = activation_funcs[act]
+    cfg = (dim, spec, float(alpha if alpha is not None else spec.def_alpha),
+           float(gain if gain is not None else spec.def_gain), float(clamp if clamp is not None else -1))
+    if not x.is_cuda:
+        raise RuntimeError('spi_b200.bias_act: x must reside on a CUDA device (no CPU path in this build)')
+    return _BiasAct.apply(x, b, cfg)

@@ -1,0 +1,240 @@
+"""Importance-sampled tri-plane volume renderer (drop-in for `training.volumetric_rendering.renderer`,
+renderer.py:84-253).
+
+`ImportanceRenderer.forward(planes, decoder, ray_origins, ray_directions, rendering_options)` keeps the reference
+signature and return value; the whole chain (stratified sampling, tri-plane gather, OSG decoder, coarse march,
+importance sampling, merge, final march) runs in `spi_render_forward` / `spi_render_backward`
+(spi_b200/csrc/raymarch.cu).  Randomness: the two uniform draws of renderer.py:190,237 are taken from torch's CUDA
+generator with the reference's shapes and order; tests inject them through `ImportanceRenderer.inject_noise`.
+"""
+import torch
+
+from ... import _lib
+from .ray_marcher import MipRayMarcher2
+
+SCRATCH_COLS = (32, 64, 64, 36)
+
+
+def generate_planes():
+    """renderer.py:22-37 (kept for API parity; the kernel hard-wires these three projections)."""
+    return torch.tensor([[[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+                         [[1, 0, 0], [0, 0, 1], [0, 1, 0]],
+                         [[0, 0, 1], [1, 0, 0], [0, 1, 0]]], dtype=torch.float32)
+
+
+def _planes_nhwc(planes):
+    """[N,3,32,H,W] (any strides) -> channels-last storage [N,H,W,96] as an [N,96,H,W] tensor."""
+    n, p, c, h, w = planes.shape
+    assert p == 3 and c == 32, 'tri-plane features must be [N, 3, 32, H, W]'
+    return planes.reshape(n, p * c, h, w).contiguous(memory_format=torch.channels_last)
+
+
+def _decoder_tensors(decoder):
+    fc1, fc2 = decoder.net[0], decoder.net[2]
+    lr_mul = float(fc1.bias_gain)
+    assert fc1.weight.shape == (64, 32) and fc2.weight.shape == (33, 64), 'OSGDecoder must be 32 -> 64 -> 33'
+    return fc1.weight, fc1.bias, fc2.weight, fc2.bias, lr_mul
+
+
+def _decoder_grads(sc, n_rows, lr_mul):
+    """dW1 = dpre^T f, db1 = sum dpre, dW2 = dout^T hid, db2 = sum dout (gains of FullyConnectedLayer folded back)."""
+    f, hid, dpre, dout = sc
+    g1 = lr_mul / (32 ** 0.5)
+    g2 = lr_mul / (64 ** 0.5)
+    dw1 = (dpre[:n_rows].t() @ f[:n_rows]) * g1
+    db1 = dpre[:n_rows].sum(0) * lr_mul
+    dw2 = (dout[:n_rows, :33].t() @ hid[:n_rows]) * g2
+    db2 = dout[:n_rows, :33].sum(0) * lr_mul
+    return dw1, db1, dw2, db2
+
+
+class _RenderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, planes, w1, b1, w2, b2, origins, dirs, jitter, u, opts):
+        lib = _lib.load()
+        n, _, h, w = planes.shape
+        r = origins.shape[1]
+        dc, df = opts['dc'], opts['df']
+        dev = planes.device
+        feat = torch.empty(n, r, 32, device=dev)
+        depth = torch.empty(n, r, 1, device=dev)
+        wsum = torch.empty(n, r, 1, device=dev)
+        depths_all = torch.empty(n, r, dc + df, device=dev)
+        minmax = torch.empty(2, dtype=torch.int32, device=dev)
+        _lib.check(lib.spi_render_forward(
+            _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(jitter), _lib.ptr(u), _lib.ptr(w1), _lib.ptr(b1),
+            _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(feat), _lib.ptr(depth), _lib.ptr(wsum), _lib.ptr(depths_all),
+            None, _lib.ptr(minmax), n, r, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
+            int(opts['disparity']), _lib.stream()))
+        ctx.save_for_backward(planes, w1, b1, w2, b2, origins, dirs, depths_all, minmax)
+        ctx.opts = opts
+        ctx.mark_non_differentiable(wsum)
+        return feat, depth, wsum
+
+    @staticmethod
+    def backward(ctx, g_feat, g_depth, _g_wsum):
+        planes, w1, b1, w2, b2, origins, dirs, depths_all, minmax = ctx.saved_tensors
+        opts = ctx.opts
+        lib = _lib.load()
+        n, _, h, w = planes.shape
+        r = origins.shape[1]
+        dc, df = opts['dc'], opts['df']
+        need_planes = ctx.needs_input_grad[0]
+        need_dec = any(ctx.needs_input_grad[1:5])
+        g_feat = g_feat.contiguous()
+        g_depth = g_depth.contiguous() if g_depth is not None else None
+        g_planes = torch.zeros_like(planes) if need_planes else None       # channels-last arena, accumulated with RED
+        gw = None
+        if need_dec:
+            rows = r * (dc + df)
+            sc = [torch.empty(rows, c, device=planes.device) for c in SCRATCH_COLS]
+            for k in range(n):       # per image: bounds the scratch to rows*784 B and keeps it L2/HBM friendly
+                _lib.check(lib.spi_render_backward(
+                    _lib.ptr(planes[k:k + 1]), _lib.ptr(origins[k:k + 1]), _lib.ptr(dirs[k:k + 1]), _lib.ptr(depths_all[k:k + 1]),
+                    _lib.ptr(minmax), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'],
+                    _lib.ptr(g_feat[k:k + 1]), _lib.ptr(g_depth[k:k + 1]) if g_depth is not None else None,
+                    _lib.ptr(g_planes[k:k + 1]) if need_planes else None, _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]),
+                    _lib.ptr(sc[3]), 1, r, h, w, dc, df, opts['box_warp'], _lib.stream()))
+                g = _decoder_grads(sc, rows, opts['lr_mul'])
+                gw = g if gw is None else tuple(a + b for a, b in zip(gw, g))
+        else:
+            _lib.check(lib.spi_render_backward(
+                _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
+                _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
+                _lib.ptr(g_planes), None, None, None, None, n, r, h, w, dc, df, opts['box_warp'], _lib.stream()))
+            gw = (None, None, None, None)
+        return (g_planes, *gw, None, None, None, None, None)
+
+
+class _PointsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, planes, w1, b1, w2, b2, coords, opts):
+        n, _, h, w = planes.shape
+        m = coords.shape[1]
+        rgb = torch.empty(n, m, 32, device=planes.device)
+        sigma = torch.empty(n, m, 1, device=planes.device)
+        _lib.check(_lib.load().spi_points_forward(
+            _lib.ptr(planes), _lib.ptr(coords), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'],
+            _lib.ptr(rgb), _lib.ptr(sigma), n, m, h, w, opts['box_warp'], _lib.stream()))
+        ctx.save_for_backward(planes, w1, b1, w2, b2, coords)
+        ctx.opts = opts
+        return rgb, sigma
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_sigma):
+        planes, w1, b1, w2, b2, coords = ctx.saved_tensors
+        opts = ctx.opts
+        n, _, h, w = planes.shape
+        m = coords.shape[1]
+        need_planes = ctx.needs_input_grad[0]
+        need_dec = any(ctx.needs_input_grad[1:5])
+        g_planes = torch.zeros_like(planes) if need_planes else None
+        sc = [torch.empty(n * m, c, device=planes.device) for c in SCRATCH_COLS] if need_dec else [None] * 4
+        _lib.check(_lib.load().spi_points_backward(
+            _lib.ptr(planes), _lib.ptr(coords), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'],
+            _lib.ptr(g_rgb.contiguous()) if g_rgb is not None else None,
+            _lib.ptr(g_sigma.contiguous()) if g_sigma is not None else None, _lib.ptr(g_planes),
+            _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]), _lib.ptr(sc[3]), n, m, h, w, opts['box_warp'], _lib.stream()))
+        gw = _decoder_grads(sc, n * m, opts['lr_mul']) if need_dec else (None,) * 4
+        return (g_planes, *gw, None, None)
+
+
+class ImportanceRenderer(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.ray_marcher = MipRayMarcher2()
+        self.plane_axes = generate_planes()
+        self._noise_queue = []
+
+    def inject_noise(self, jitter, u):
+        """Queue the (jitter [N,R,Dc,1], u [N*R,Df]) pair the next forward() consumes instead of drawing from the RNG."""
+        self._noise_queue.append((jitter, u))
+
+    @staticmethod
+    def _check_options(o):
+        if isinstance(o['ray_start'], str) or isinstance(o['ray_end'], str):
+            raise NotImplementedError("ray_start/ray_end='auto' (per-ray box limits, renderer.py:91-97) is not built: the "
+                                      'FFHQ generator of the inversion path uses scalar limits')
+        if o.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 (renderer.py:146-147) is a GAN-training feature, not built')
+        if o.get('white_back', False):
+            raise NotImplementedError('white_back=True is not used by the FFHQ generator, not built')
+        assert o.get('clamp_mode', 'softplus') == 'softplus', "MipRayMarcher only supports `clamp_mode`=`softplus`!"
+
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options):
+        o = rendering_options
+        self._check_options(o)
+        if not planes.is_cuda:
+            raise RuntimeError('spi_b200.ImportanceRenderer: tensors must reside on a CUDA device (no CPU path in this build)')
+        n, r, _ = ray_origins.shape
+        dc, df = int(o['depth_resolution']), int(o['depth_resolution_importance'])
+        if self._noise_queue:
+            jitter, u = self._noise_queue.pop(0)
+        else:   # same shapes and order as renderer.py:190 (rand_like of [N,R,Dc,1]) and :237 (rand [N*R, Df])
+            jitter = torch.rand(n, r, dc, 1, device=planes.device)
+            u = torch.rand(n * r, max(df, 1), device=planes.device)
+        w1, b1, w2, b2, lr_mul = _decoder_tensors(decoder)
+        opts = dict(dc=dc, df=df, lr_mul=lr_mul, ray_start=float(o['ray_start']), ray_end=float(o['ray_end']),
+                    box_warp=float(o['box_warp']), disparity=bool(o.get('disparity_space_sampling', False)))
+        feat, depth, wsum = _RenderFn.apply(_planes_nhwc(planes), w1, b1, w2, b2, ray_origins.detach().float().contiguous(),
+                                            ray_directions.detach().float().contiguous(), jitter.float().contiguous(),
+                                            u.float().contiguous(), opts)
+        return feat, depth, wsum
+
+    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
+        """renderer.py:142-149: {'rgb': [N,M,32], 'sigma': [N,M,1]} at arbitrary points."""
+        if options.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 is not built')
+        w1, b1, w2, b2, lr_mul = _decoder_tensors(decoder)
+        opts = dict(lr_mul=lr_mul, box_warp=float(options['box_warp']))
+        rgb, sigma = _PointsFn.apply(_planes_nhwc(planes), w1, b1, w2, b2, sample_coordinates.detach().float().contiguous(), opts)
+        return {'rgb': rgb, 'sigma': sigma}
+
+    # ---- stand-alone stages, same names as the reference methods (forward only; index outputs are int64) ----
+    def sample_importance(self, z_vals, weights, N_importance, u=None):
+        """renderer.py:194-212; `u` optionally injects the uniform draw of sample_pdf (:237)."""
+        n, r, dc, _ = z_vals.shape
+        z = z_vals.detach().reshape(n * r, dc).float().contiguous()
+        w = weights.detach().reshape(n * r, -1).float().contiguous()
+        if u is None:
+            u = torch.rand(n * r, N_importance, device=z.device)
+        fine = torch.empty(n * r, N_importance, device=z.device)
+        inds = torch.empty(n * r, N_importance, dtype=torch.int32, device=z.device)
+        _lib.check(_lib.load().spi_sample_importance(_lib.ptr(z), _lib.ptr(w), _lib.ptr(u.contiguous()), n * r, dc, N_importance,
+                                                     _lib.ptr(fine), _lib.ptr(inds), None, _lib.stream()))
+        return fine.reshape(n, r, N_importance, 1)
+
+    def sample_pdf_from_cdf(self, bins, cdf, u):
+        """Inverse-CDF half of sample_pdf (renderer.py:241-253): returns (samples, inds int64)."""
+        rays, ncdf = cdf.shape
+        df = u.shape[1]
+        fine = torch.empty(rays, df, device=cdf.device)
+        inds = torch.empty(rays, df, dtype=torch.int32, device=cdf.device)
+        _lib.check(_lib.load().spi_inverse_cdf(_lib.ptr(bins.float().contiguous()), _lib.ptr(cdf.float().contiguous()),
+                                               _lib.ptr(u.float().contiguous()), rays, ncdf, bins.shape[1], df, _lib.ptr(fine),
+                                               _lib.ptr(inds), _lib.stream()))
+        return fine, inds.long()
+
+    def unify_samples(self, depths1, colors1, densities1, depths2, colors2, densities2):
+        """renderer.py:157-167 (forward only): merge by depth."""
+        n, r, dc, _ = depths1.shape
+        df = depths2.shape[2]
+        perm = torch.empty(n * r, dc + df, dtype=torch.int32, device=depths1.device)
+        srt = torch.empty(n * r, dc + df, device=depths1.device)
+        _lib.check(_lib.load().spi_unify_samples(_lib.ptr(depths1.detach().float().reshape(n * r, dc).contiguous()),
+                                                 _lib.ptr(depths2.detach().float().reshape(n * r, df).contiguous()), n * r, dc, df,
+                                                 _lib.ptr(perm), _lib.ptr(srt), _lib.stream()))
+        idx = perm.long().reshape(n, r, dc + df, 1)
+        all_colors = torch.gather(torch.cat([colors1, colors2], -2), -2, idx.expand(-1, -1, -1, colors1.shape[-1]))
+        all_dens = torch.gather(torch.cat([densities1, densities2], -2), -2, idx)
+        return srt.reshape(n, r, dc + df, 1), all_colors, all_dens
+
+    def sort_permutation(self, depths1, depths2):
+        n, r, dc, _ = depths1.shape
+        df = depths2.shape[2]
+        perm = torch.empty(n * r, dc + df, dtype=torch.int32, device=depths1.device)
+        srt = torch.empty(n * r, dc + df, device=depths1.device)
+        _lib.check(_lib.load().spi_unify_samples(_lib.ptr(depths1.detach().float().reshape(n * r, dc).contiguous()),
+                                                 _lib.ptr(depths2.detach().float().reshape(n * r, df).contiguous()), n * r, dc, df,
+                                                 _lib.ptr(perm), _lib.ptr(srt), _lib.stream()))
+        return perm.long().reshape(n, r, dc + df, 1), srt.reshape(n, r, dc + df, 1)
