@@ -1,0 +1,63 @@
+"""Fused Adam over flat arenas (replaces `torch.optim.Adam` at spi/training/coaches/base_coach.py:132-135 and
+spi/training/projectors/*_projector.py:55-58; defaults betas=(0.9,0.999), eps=1e-8).
+
+Every parameter is re-seated as a view into one contiguous fp32 arena and its `.grad` as a view into a matching
+gradient arena, so `zero_grad()` is one memset and `step()` one `spi_adam_step` launch streaming 28 B/param.
+`param_groups[0]['lr']` is honoured at step time (the projectors rewrite it every step, mirror_projector.py:88-91).
+Parameters that never receive a gradient keep a zero gradient and therefore never move (m = v = 0 -> update 0), which
+matches torch skipping `grad is None` parameters.
+"""
+import torch
+
+from . import _lib
+
+
+class FlatAdam:
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        assert self.params, 'FlatAdam: empty parameter list'
+        dev = self.params[0].device
+        if dev.type != 'cuda':
+            raise RuntimeError('spi_b200.FlatAdam: parameters must reside on a CUDA device (no CPU path in this build)')
+        sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]       # keep every view 16-byte aligned
+        total = sum(sizes)
+        self.arena = torch.zeros(total, device=dev)
+        self.grads = torch.zeros(total, device=dev)
+        self.exp_avg = torch.zeros(total, device=dev)
+        self.exp_avg_sq = torch.zeros(total, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p, sz in zip(self.params, sizes):
+                view = self.arena[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grads[off:off + p.numel()].view(p.shape)
+                off += sz
+        self.param_groups = [dict(params=self.params, lr=lr, betas=betas, eps=eps)]
+        self.steps = 0
+
+    def zero_grad(self, set_to_none=False):
+        self.grads.zero_()
+        for p in self.params:           # autograd may have replaced .grad (e.g. after set_to_none elsewhere): re-seat
+            if p.grad is None or p.grad.data_ptr() < self.grads.data_ptr() or p.grad.data_ptr() >= self.grads.data_ptr() + self.grads.numel() * 4:
+                self._reseat()
+                break
+
+    def _reseat(self):
+        off = 0
+        for p in self.params:
+            sz = (p.numel() + 3) // 4 * 4
+            view = self.grads[off:off + p.numel()].view(p.shape)
+            if p.grad is not None and p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+            p.grad = view
+            off += sz
+
+    @torch.no_grad()
+    def step(self):
+        self._reseat()
+        self.steps += 1
+        g = self.param_groups[0]
+        _lib.check(_lib.load().spi_adam_step(_lib.ptr(self.arena), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                             self.arena.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+                                             self.steps, None, 0, _lib.stream()))

@@ -1,0 +1,181 @@
+"""GPU parity: the L1 operators through the C ABI vs the CPU oracle (and the reference goldens)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_l2
+from oracle import ops as O
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-6     # fp32 elementwise / short FIR sums
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.fixture(scope='module')
+def P():
+    from spi_b200.torch_utils.ops import bias_act, filtered_lrelu, upfirdn2d
+    import types
+    return types.SimpleNamespace(bias_act=bias_act, upfirdn2d=upfirdn2d, filtered_lrelu=filtered_lrelu)
+
+
+def test_bias_act_forward_golden(P, golden, lib):
+    g = golden('ops')
+    x, b = T(g['ba_x']).cuda(), T(g['ba_b']).cuda()
+    for act in O.ACTS:
+        assert rel_l2(P.bias_act.bias_act(x, b, act=act), g[f'ba_{act}_d']) < TOL, act
+        assert rel_l2(P.bias_act.bias_act(x, b, act=act, gain=0.7, clamp=0.9, alpha=0.3), g[f'ba_{act}_g']) < TOL, act
+        xc = x.contiguous(memory_format=torch.channels_last)
+        y = P.bias_act.bias_act(xc, b, act=act)
+        assert y.is_contiguous(memory_format=torch.channels_last)
+        assert rel_l2(y, g[f'ba_{act}_d']) < TOL, act
+
+
+def test_bias_act_gradients_golden(P, golden):
+    g = golden('ops')
+    for act, kw in (('lrelu', dict(gain=math.sqrt(2), clamp=256.)), ('linear', dict(clamp=1.0)), ('lrelu', dict(clamp=0.5))):
+        key = f"ba_grad_{act}_{kw.get('clamp')}"
+        x = T(g['ba_x']).cuda().requires_grad_(True)
+        b = T(g['ba_b']).cuda().requires_grad_(True)
+        P.bias_act.bias_act(x, b, act=act, **kw).backward(T(g[key + '_dy']).cuda())
+        assert rel_l2(x.grad, g[key + '_dx']) < TOL and rel_l2(b.grad, g[key + '_db']) < 1e-5
+
+
+@pytest.mark.parametrize('act', list(O.ACTS))
+@pytest.mark.parametrize('shape,dim', [((3, 5, 7, 9), 1), ((4, 33), 1), ((2, 8, 16, 16), 1), ((1000003,), 0), ((0, 4), 1)])
+def test_bias_act_vs_oracle_with_autograd(P, act, shape, dim):
+    gen = torch.Generator().manual_seed(hash((act, shape)) % 1000)
+    x = torch.randn(*shape, generator=gen) * 2
+    b = torch.randn(shape[dim], generator=gen) if len(shape) > 1 else None
+    xo = x.clone().requires_grad_(True)
+    yo = O.bias_act(xo, b, dim=dim, act=act, clamp=1.5)
+    xg = x.cuda().requires_grad_(True)
+    yg = P.bias_act.bias_act(xg, b.cuda() if b is not None else None, dim=dim, act=act, clamp=1.5)
+    assert yg.shape == yo.shape
+    if x.numel() == 0:
+        return
+    assert rel_l2(yg, yo) < 1e-5
+    dy = torch.randn(*shape, generator=gen)
+    yo.backward(dy)
+    yg.backward(dy.cuda())
+    assert rel_l2(xg.grad, xo.grad) < 1e-5
+
+
+def test_bias_act_second_order(P):
+    x = torch.randn(2, 4, 5, 5, dtype=torch.float32)
+    for act in ('tanh', 'sigmoid', 'softplus', 'swish', 'elu', 'selu'):
+        xo = x.clone().requires_grad_(True)
+        go, = torch.autograd.grad(O.bias_act(xo, act=act).sum(), xo, create_graph=True)
+        (go ** 2).sum().backward()
+        xg = x.cuda().requires_grad_(True)
+        gg, = torch.autograd.grad(P.bias_act.bias_act(xg, act=act).sum(), xg, create_graph=True)
+        (gg ** 2).sum().backward()
+        assert rel_l2(xg.grad, xo.grad) < 1e-4, act
+
+
+def test_bias_act_dtypes_and_errors(P):
+    x = torch.randn(2, 6, 4, 4)
+    b = torch.randn(6)
+    ref = O.bias_act(x.double(), b.double(), act='lrelu')
+    assert rel_l2(P.bias_act.bias_act(x.double().cuda(), b.double().cuda(), act='lrelu'), ref) < 1e-12
+    assert rel_l2(P.bias_act.bias_act(x.half().cuda(), b.half().cuda(), act='lrelu').float(), O.bias_act(x.half().float(), b.half().float(), act='lrelu')) < 2e-3
+    with pytest.raises(RuntimeError):
+        P.bias_act.bias_act(x.cuda(), torch.randn(5).cuda())
+
+
+UP_CASES = {
+    'blur_after_convT': dict(up=1, down=1, padding=[1, 1, 1, 1], gain=4.0, flip_filter=False),
+    'upsample2d': dict(up=2, down=1, padding=[2, 1, 2, 1], gain=4.0, flip_filter=False),
+    'upsample2d_bwd': dict(up=1, down=2, padding=[1, 2, 1, 2], gain=4.0, flip_filter=True),
+    'generic_a': dict(up=[2, 1], down=[1, 2], padding=[3, 0, 1, 2], gain=1.3, flip_filter=True),
+    'crop': dict(up=1, down=1, padding=[-1, 2, 0, -2], gain=1.0, flip_filter=False),
+    'down3': dict(up=1, down=3, padding=[2, 2, 2, 2], gain=1.0, flip_filter=False),
+}
+
+
+def test_upfirdn2d_golden(P, golden):
+    g = golden('ops')
+    x, f = T(g['up_x']).cuda(), T(g['f4']).cuda()
+    for name, kw in UP_CASES.items():
+        assert rel_l2(P.upfirdn2d.upfirdn2d(x, f, **kw), g['up_' + name]) < TOL, name
+        xc = x.contiguous(memory_format=torch.channels_last)
+        assert rel_l2(P.upfirdn2d.upfirdn2d(xc, f, **kw), g['up_' + name]) < TOL, name + '/cl'
+    xs, f12 = T(g['up_xs']).cuda(), T(g['f12']).cuda()
+    assert rel_l2(P.upfirdn2d.upfirdn2d(xs, f12, up=2, padding=[5, 6, 5, 6], gain=4.0), g['up_separable12']) < 1e-5
+
+
+@pytest.mark.parametrize('case', list(UP_CASES))
+@pytest.mark.parametrize('cl', [False, True])
+def test_upfirdn2d_vs_oracle_with_autograd(P, case, cl):
+    kw = UP_CASES[case]
+    gen = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 8, 21, 19, generator=gen)
+    f = O.setup_filter([1, 3, 3, 1])
+    xo = x.clone().requires_grad_(True)
+    yo = O.upfirdn2d(xo, f, **kw)
+    xg = x.cuda()
+    if cl:
+        xg = xg.contiguous(memory_format=torch.channels_last)
+    xg.requires_grad_(True)
+    yg = P.upfirdn2d.upfirdn2d(xg, f.cuda(), **kw)
+    assert yg.shape == yo.shape and rel_l2(yg, yo) < TOL
+    dy = torch.randn(*yo.shape, generator=gen)
+    yo.backward(dy)
+    yg.backward(dy.cuda())
+    assert rel_l2(xg.grad, xo.grad) < TOL
+
+
+def test_upsample2d_full_size_property(P):
+    """512^2-scale property check: upsample2d of a constant image is constant (DC gain 1), and linearity."""
+    f = O.setup_filter([1, 3, 3, 1]).cuda()
+    x = torch.full((1, 96, 128, 128), 0.37, device='cuda').contiguous(memory_format=torch.channels_last)
+    y = P.upfirdn2d.upsample2d(x, f)
+    assert y.shape == (1, 96, 256, 256)
+    assert (y[:, :, 4:-4, 4:-4] - 0.37).abs().max() < 1e-6
+    a, b = torch.randn(1, 96, 128, 128, device='cuda'), torch.randn(1, 96, 128, 128, device='cuda')
+    lhs = P.upfirdn2d.upsample2d(a + 2 * b, f)
+    rhs = P.upfirdn2d.upsample2d(a, f) + 2 * P.upfirdn2d.upsample2d(b, f)
+    assert rel_l2(lhs, rhs) < 1e-6
+
+
+FL_CASES = {
+    'u2d2': dict(up=2, down=2, padding=[9, 10, 9, 10], gain=math.sqrt(2), slope=0.2, clamp=256., flip_filter=False),
+    'u2d1': dict(up=2, down=1, padding=[5, 6, 5, 6], gain=math.sqrt(2), slope=0.2, clamp=None, flip_filter=False),
+    'u1d2': dict(up=1, down=2, padding=[5, 5, 5, 5], gain=1.1, slope=0.1, clamp=0.8, flip_filter=True),
+    'u1d1': dict(up=1, down=1, padding=[0, 0, 0, 0], gain=math.sqrt(2), slope=0.2, clamp=None, flip_filter=False),
+}
+
+
+@pytest.mark.parametrize('name', list(FL_CASES))
+def test_filtered_lrelu_golden_and_grad(P, golden, name):
+    g = golden('ops')
+    kw = FL_CASES[name]
+    xs, f12, fd12, b = T(g['up_xs']), T(g['f12']), T(g['fd12']), T(g['fl_b'])
+    fu = f12 if kw['up'] > 1 else (None if name == 'u1d1' else f12)
+    fd = fd12 if kw['down'] > 1 else None
+    xg = xs.cuda().requires_grad_(True)
+    bg = b.cuda().requires_grad_(True)
+    yg = P.filtered_lrelu.filtered_lrelu(xg, fu=fu.cuda() if fu is not None else None, fd=fd.cuda() if fd is not None else None, b=bg, **kw)
+    assert rel_l2(yg, g['fl_' + name]) < 1e-5
+    xo = xs.clone().requires_grad_(True)
+    bo = b.clone().requires_grad_(True)
+    yo = O.filtered_lrelu(xo, fu=fu, fd=fd, b=bo, **kw)
+    dy = torch.randn(*yo.shape, generator=torch.Generator().manual_seed(5))
+    yo.backward(dy)
+    yg.backward(dy.cuda())
+    assert rel_l2(xg.grad, xo.grad) < 1e-5 and rel_l2(bg.grad, bo.grad) < 1e-5
+
+
+def test_filtered_lrelu_larger_and_channels_last(P):
+    gen = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 5, 37, 41, generator=gen)
+    b = torch.randn(5, generator=gen)
+    fu = O.setup_filter([1, 3, 3, 1]) * 1.0
+    for cl in (False, True):
+        xg = x.cuda().contiguous(memory_format=torch.channels_last) if cl else x.cuda()
+        y = P.filtered_lrelu.filtered_lrelu(xg, fu=fu.cuda(), fd=fu.cuda(), b=b.cuda(), up=2, down=2, padding=[3, 3, 3, 3], clamp=1.0)
+        assert rel_l2(y, O.filtered_lrelu(x, fu=fu, fd=fu, b=b, up=2, down=2, padding=[3, 3, 3, 3], clamp=1.0)) < 1e-5
