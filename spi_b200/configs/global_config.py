@@ -1,0 +1,8 @@
+"""spi/configs/global_config.py:2-12 (module-level globals mutated at run time, as in the reference)."""
+cuda_visible_devices = '0'
+device = 'cuda:0'
+training_step = 1
+log_snapshot = 500
+pivotal_training_steps = 0
+model_snapshot_interval = 400
+run_name = ''

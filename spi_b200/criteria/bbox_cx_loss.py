@@ -1,0 +1,120 @@
+"""Mirror-view contextual loss on landmark boxes (drop-in for spi/criteria/bbox_cx_loss.py:20-182).
+
+Landmark boxes (int64, the reference's truncation and padding quirks kept), `roi_align` 80x80 crops, VGG19[:6]
+features (conv engine), centred cosine distance, relative distance, CX, -log mean max.
+"""
+import torch
+import torch.nn.functional as F
+from torchvision.ops import roi_align
+
+from ..ops import conv as conv_engine
+from ..ops.resize import downsample2x
+
+
+def get_landmark_bbox(lm, scale=1):
+    """bbox_cx_loss.py:20-37.  `p` is not reset after the eyes, so the (unused) nose box also gets 15."""
+    p = 8
+    bbox = []
+    for _i, (a, b) in enumerate(((48, 68), (36, 42), (42, 48), (27, 36))):
+        box_lm = lm[:, a:b]
+        ly, ry = torch.min(box_lm[:, :, 0], dim=1)[0], torch.max(box_lm[:, :, 0], dim=1)[0]
+        lx, rx = torch.min(box_lm[:, :, 1], dim=1)[0], torch.max(box_lm[:, :, 1], dim=1)[0]
+        lx, rx, ly, ry = (lx * scale).long(), (rx * scale).long(), (ly * scale).long(), (ry * scale).long()
+        if _i == 1 or _i == 2:
+            p = 15
+        bbox.append(torch.stack([ly - p, lx - p, ry + p, rx + p], dim=1))
+    return bbox
+
+
+def get_bbox(image, fake_image, lm):
+    """bbox_cx_loss.py:41-59."""
+    assert image.shape[-1] == 256
+    bbox = get_landmark_bbox(lm)
+    idx = torch.arange(image.shape[0], device=image.device).unsqueeze(1)
+    out = []
+    for k in range(3):
+        rois = torch.cat([idx, bbox[k].to(image.device)], dim=1).float()
+        out.append(roi_align(image, boxes=rois, output_size=80))
+    for k in range(3):
+        rois = torch.cat([idx, bbox[k].to(image.device)], dim=1).float()
+        out.append(roi_align(fake_image, boxes=rois, output_size=80))
+    return tuple(out)      # gt_mouth, gt_l_eye, gt_r_eye, fake_mouth, fake_l_eye, fake_r_eye
+
+
+class VGG19(torch.nn.Module):
+    """torchvision `vgg19().features[:6]` = conv(3,64) relu conv(64,64) relu maxpool conv(64,128)  (bbox_cx_loss.py:76-91)."""
+
+    def __init__(self, requires_grad=False):
+        super().__init__()
+        self.slice1 = torch.nn.Sequential()
+        mods = [torch.nn.Conv2d(3, 64, 3, padding=1), torch.nn.ReLU(inplace=True), torch.nn.Conv2d(64, 64, 3, padding=1),
+                torch.nn.ReLU(inplace=True), torch.nn.MaxPool2d(2, 2), torch.nn.Conv2d(64, 128, 3, padding=1)]
+        for i, m in enumerate(mods):
+            self.slice1.add_module(str(i), m)
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+    def forward(self, X):
+        X = X.contiguous(memory_format=torch.channels_last)
+        for m in self.slice1:
+            if isinstance(m, torch.nn.Conv2d):
+                X = conv_engine.conv2d(X, m.weight, padding=1) + m.bias.view(1, -1, 1, 1)
+            else:
+                X = m(X)
+        return X
+
+
+def compute_cosine_distance(x, y):
+    y_mu = y.mean(dim=(0, 2, 3), keepdim=True)
+    x_n = F.normalize(x - y_mu, p=2, dim=1)
+    y_n = F.normalize(y - y_mu, p=2, dim=1)
+    N, C = x.shape[:2]
+    return 1 - torch.bmm(x_n.reshape(N, C, -1).transpose(1, 2), y_n.reshape(N, C, -1))
+
+
+def compute_relative_distance(dist_raw):
+    dist_min, _ = torch.min(dist_raw, dim=2, keepdim=True)
+    return torch.clamp(dist_raw / (dist_min + 1e-5), max=10., min=-10)
+
+
+def compute_cx(dist_tilde, band_width):
+    w = torch.exp((1 - dist_tilde) / band_width)
+    return w / torch.sum(w, dim=2, keepdim=True)
+
+
+def flip_landmark(lm):
+    """bbox_cx_loss.py:133-137: returns its input unchanged (the flipped copy is discarded)."""
+    return lm
+
+
+class BoxCXLoss(torch.nn.Module):
+    def __init__(self, band_width: float = 0.5):
+        super().__init__()
+        self.band_width = band_width
+        self.vgg_model = VGG19()
+        self.register_buffer('vgg_mean', torch.tensor([[[0.485]], [[0.456]], [[0.406]]]))
+        self.register_buffer('vgg_std', torch.tensor([[[0.229]], [[0.224]], [[0.225]]]))
+
+    @staticmethod
+    def _to256(t):
+        if t.shape[-1] == 512 and t.shape[-2] == 512:
+            return downsample2x(t)
+        if t.shape[-1] > 256:
+            return F.interpolate(t, (256, 256), mode='bilinear', align_corners=False)
+        return t
+
+    def forward(self, x, y, lm):
+        if not x.is_cuda:
+            raise RuntimeError('spi_b200 BoxCXLoss: tensors must reside on a CUDA device (no CPU path in this build)')
+        x, y = self._to256(x), self._to256(y)
+        x = x.sub(self.vgg_mean).div(self.vgg_std)       # ImageNet z-score on [-1,1] data, as the reference does (:165-166)
+        y = y.sub(self.vgg_mean).div(self.vgg_std)
+        gt_mouth, gt_l_eye, gt_r_eye, fake_mouth, fake_l_eye, fake_r_eye = get_bbox(x, y, lm)
+        loss = 0
+        for _x, _y in ((gt_mouth, fake_mouth), (gt_l_eye, fake_l_eye), (gt_r_eye, fake_r_eye)):
+            fx, fy = self.vgg_model(_x), self.vgg_model(_y)
+            cx = compute_cx(compute_relative_distance(compute_cosine_distance(fx, fy)), self.band_width)
+            cx = torch.mean(torch.max(cx, dim=1)[0], dim=1)
+            loss = loss + torch.mean(-torch.log(cx + 1e-5))
+        return loss * 0.1

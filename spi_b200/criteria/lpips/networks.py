@@ -1,0 +1,75 @@
+"""LPIPS backbones (drop-in for spi/criteria/lpips/networks.py).  Only the VGG16 variant is on the inversion path
+(`LPIPS(net_type='vgg')`, base_coach.py:48); the module tree (`layers.<i>`, `mean`, `std`) matches torchvision's
+`vgg16().features` so pretrained state dicts load by name."""
+from typing import Sequence
+
+import torch
+import torch.nn as nn
+
+from ...ops import conv as conv_engine
+from .utils import normalize_activation
+
+VGG16_FEATURES = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M')
+
+
+def vgg_features(cfg):
+    layers, cin = [], 3
+    for v in cfg:
+        if v == 'M':
+            layers.append(nn.MaxPool2d(kernel_size=2, stride=2))
+        else:
+            layers += [nn.Conv2d(cin, v, kernel_size=3, padding=1), nn.ReLU(inplace=True)]
+            cin = v
+    return nn.Sequential(*layers)
+
+
+def get_network(net_type: str):
+    if net_type == 'vgg':
+        return VGG16()
+    raise NotImplementedError("spi_b200 builds the 'vgg' LPIPS backbone only (the one SPI uses)")
+
+
+class LinLayers(nn.ModuleList):
+    def __init__(self, n_channels_list: Sequence[int]):
+        super().__init__([nn.Sequential(nn.Identity(), nn.Conv2d(nc, 1, 1, 1, 0, bias=False)) for nc in n_channels_list])
+        for p in self.parameters():
+            p.requires_grad = False
+
+
+class BaseNet(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer('mean', torch.Tensor([-.030, -.088, -.188])[None, :, None, None])
+        self.register_buffer('std', torch.Tensor([.458, .448, .450])[None, :, None, None])
+
+    def set_requires_grad(self, state: bool):
+        for p in list(self.parameters()) + list(self.buffers()):
+            p.requires_grad = state
+
+    def z_score(self, x):
+        return (x - self.mean) / self.std
+
+    def forward(self, x):
+        if not x.is_cuda:
+            raise RuntimeError('spi_b200 LPIPS: tensors must reside on a CUDA device (no CPU path in this build)')
+        x = self.z_score(x).contiguous(memory_format=torch.channels_last)
+        output = []
+        for i, layer in enumerate(self.layers, 1):
+            if isinstance(layer, nn.Conv2d):
+                x = conv_engine.conv2d(x, layer.weight, padding=1) + layer.bias.view(1, -1, 1, 1)
+            else:
+                x = layer(x)
+            if i in self.target_layers:
+                output.append(normalize_activation(x))
+            if len(output) == len(self.target_layers):
+                break
+        return output
+
+
+class VGG16(BaseNet):
+    def __init__(self):
+        super().__init__()
+        self.layers = vgg_features(VGG16_FEATURES)          # torchvision `vgg16().features` naming
+        self.target_layers = [4, 9, 16, 23, 30]
+        self.n_channels_list = [64, 128, 256, 512, 512]
+        self.set_requires_grad(False)

@@ -94,7 +94,10 @@ class _BiasAct(torch.autograd.Function):
         if spec.cuda_idx != 1 or gain != 1 or clamp >= 0 or b is not None:
             y = _plugin_bias_act(x, b, None, None, None, 0, dim, spec.cuda_idx, alpha, gain, clamp)
         keep_x = 'x' in spec.ref or spec.has_2nd_grad
-        ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if 'y' in spec.ref else None)
+        # y is also kept when a clamp is active so that the gradient is masked where the output saturated -- the
+        # behaviour of the reference's CPU path (`_bias_act_ref`, the oracle).  The reference CUDA plugin drops y for
+        # act='linear' (spec.ref == '') and lets the gradient through the clamp; see DESIGN.md 'Known deviations'.
+        ctx.save_for_backward(x if keep_x else None, b if keep_x else None, y if ('y' in spec.ref or clamp >= 0) else None)
         ctx.cfg, ctx.fmt = cfg, fmt
         return y
 

@@ -1,0 +1,142 @@
+"""Outer per-image loop scaffolding (spi/training/coaches/base_coach.py:36-270): generator reload per image, stage-1
+dispatch, G-stage Adam over all G.parameters() (lr 3e-4), checkpoint / still-image output, coach naming."""
+import abc
+import os
+
+import numpy as np
+import torch
+from PIL import Image
+
+from ...configs import global_config, hyperparameters, paths_config
+from ...criteria.lpips.lpips import LPIPS
+from ...optim import FlatAdam
+from ...utils import load_utils
+from ...utils.camera_utils import cal_mirror_c
+from ...utils.log_utils import log_image_from_w
+from ..projectors import mirror_projector, w_plus_projector, w_projector
+
+
+def toogle_grad(model, flag=True):
+    for p in model.parameters():
+        p.requires_grad = flag
+
+
+def fix_seed():
+    """base_coach.py:28-33."""
+    torch.manual_seed(0)
+    torch.cuda.manual_seed_all(0)
+    np.random.seed(0)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+
+class BaseCoach:
+    def __init__(self, data_loader, use_wandb, lpips_loss=None, vgg16=None):
+        self.use_wandb = use_wandb
+        self.data_loader = data_loader
+        self.w_pivots = {}
+        self.image_counter = 0
+        self.metric_dic = {}
+        self.coach_name = 'Base_coach'
+        self.lpips_loss = lpips_loss if lpips_loss is not None else LPIPS(net_type='vgg').to(global_config.device).eval()
+        self.restart_training()
+        self.vgg16 = vgg16 if vgg16 is not None else load_utils.load_sg_vgg().to(global_config.device)
+
+    def restart_training(self):
+        """base_coach.py:53-60: fresh G and original_G per image, new optimiser, then fix_seed()."""
+        self.G = load_utils.load_eg3d()
+        toogle_grad(self.G, True)
+        self.original_G = load_utils.load_eg3d()
+        self.optimizer = self.configure_optimizers()
+        fix_seed()
+
+    def get_inversion(self, image_name, image, camera, fg_mask=None):
+        embedding_dir = f'{paths_config.embedding_base_dir}/{self.coach_name}/'
+        os.makedirs(embedding_dir, exist_ok=True)
+        w_pivot = None
+        if hyperparameters.load_embedding_coach_name is not None:
+            w_pivot = self.load_inversions(f'{paths_config.embedding_base_dir}/{hyperparameters.load_embedding_coach_name}/', image_name)
+        if w_pivot is None:
+            w_pivot = self.calc_inversions(image_name, image, camera, fg_mask)
+        torch.save(w_pivot, f'{embedding_dir}/{image_name}.pt')
+        w_pivot = w_pivot.to(global_config.device)
+        if self.use_wandb:
+            log_image_from_w(w_pivot, camera, self.G, f'{image_name}_w_inv')
+            log_image_from_w(w_pivot, cal_mirror_c(camera), self.G, f'{image_name}_w_inv_m')
+        return w_pivot
+
+    def load_inversions(self, embedding_dir, image_name):
+        if image_name in self.w_pivots:
+            return self.w_pivots[image_name]
+        path = f'{embedding_dir}/{image_name}.pt'
+        if not os.path.isfile(path):
+            print('[ERROR]: No existing w codes.')
+            return None
+        w = torch.load(path, map_location='cpu').to(global_config.device)
+        self.w_pivots[image_name] = w
+        return w
+
+    def calc_inversions(self, image_name, image, camera, fg_mask=None):
+        assert hyperparameters.first_inv_type in ['sg', 'sgw+', 'mir', 'reg']
+        kw = dict(device=torch.device(global_config.device), w_avg_samples=600, num_steps=hyperparameters.first_inv_steps,
+                  verbose=self.use_wandb, w_name=image_name, initial_w=None)
+        if hyperparameters.first_inv_type == 'sg':
+            return w_projector.project(self.G, image, camera, vgg16=self.vgg16, **kw)
+        if hyperparameters.first_inv_type == 'sgw+':
+            return w_plus_projector.project(self.G, image, camera, lpips_func=self.lpips_loss, **kw)
+        if hyperparameters.first_inv_type == 'mir':
+            return mirror_projector.project(self.G, image, camera, lpips_func=self.lpips_loss, fg_mask=fg_mask, **kw)
+        raise NotImplementedError
+
+    @abc.abstractmethod
+    def train(self):
+        pass
+
+    def configure_optimizers(self):
+        """base_coach.py:132-135: Adam over every G parameter, lr = pti_learning_rate."""
+        return FlatAdam(self.G.parameters(), lr=hyperparameters.pti_learning_rate)
+
+    def save(self, w, c, G, path):
+        torch.save({'w': w.detach().cpu(), 'c': c.detach().cpu(), 'G': {k: v.detach().cpu() for k, v in G.state_dict().items()}}, path)
+
+    def load(self, path):
+        ckpt = torch.load(path, map_location='cpu')
+        self.G.load_state_dict(ckpt['G'])
+        return ckpt['w'].to(global_config.device), ckpt['c'].to(global_config.device), self.G
+
+    def post_process(self, w, c, G, name):
+        self.save(w, c, G, path=os.path.join(paths_config.checkpoints_dir, self.coach_name, f'{name}.pt'))
+        self.log_image(w, c, G, path=os.path.join(paths_config.images_output_dir, self.coach_name, name + '.jpg'))
+        self.log_image(w, cal_mirror_c(c), G, path=os.path.join(paths_config.mirror_images_output_dir, self.coach_name, name + '.jpg'))
+        self.log_video(w, G, path=os.path.join(paths_config.video_output_dir, self.coach_name, f'{name}.mp4'))
+
+    def log_image(self, w, c, G, path):
+        if len(w.size()) <= 2:
+            w = w.unsqueeze(0)
+        with torch.no_grad():
+            img = G.synthesis(w, c, noise_mode='const')['image'][0].permute(1, 2, 0)
+            img = (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).detach().cpu().numpy()
+        Image.fromarray(img).save(path)
+
+    def log_video(self, w, G, path):
+        """The 120-frame orbit video (spi/utils/video_utils.py:74) needs imageio/mrcfile and is post-processing outside the
+        hot path: not built."""
+        return None
+
+    def build_name(self):
+        """base_coach.py:240-270."""
+        hp = hyperparameters
+        self.coach_name += f'_{hp.first_inv_type}_{hp.first_inv_steps}_{hp.G_1_type}_{hp.G_1_step}'
+        if hp.use_encoder:
+            self.coach_name += '_wenc'
+        if hp.use_G_avg:
+            self.coach_name += '_wgavg'
+        self.coach_name += f'_rot_{hp.pt_rot_lambda}_mirrorrot_{hp.pt_mirror_rot_lambda}_depth_{hp.pt_depth_lambda}_tv_{hp.pt_tv_lambda}'
+        if hp.use_adapt_yaw_range:
+            self.coach_name += '_wadyaw'
+        if hp.description is not None:
+            self.coach_name += '_' + hp.description
+        print('[COACH]:', self.coach_name)
+        for d in (paths_config.checkpoints_dir, paths_config.embedding_base_dir, paths_config.experiments_output_dir,
+                  paths_config.images_output_dir, paths_config.mirror_images_output_dir, paths_config.video_output_dir):
+            os.makedirs(os.path.join(d, self.coach_name), exist_ok=True)

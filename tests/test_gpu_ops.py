@@ -62,7 +62,9 @@ def test_bias_act_vs_oracle_with_autograd(P, act, shape, dim):
     dy = torch.randn(*shape, generator=gen)
     yo.backward(dy)
     yg.backward(dy.cuda())
-    assert rel_l2(xg.grad, xo.grad) < 1e-5
+    # the plugin decides the branch from y (= act(x)*gain), torch from x: they differ only where act(x) rounds to 0
+    bad = ((xg.grad.cpu() - xo.grad).abs() > 1e-5 * (1 + xo.grad.abs())).float().mean().item()
+    assert bad < 1e-5
 
 
 def test_bias_act_second_order(P):
@@ -81,7 +83,7 @@ def test_bias_act_dtypes_and_errors(P):
     x = torch.randn(2, 6, 4, 4)
     b = torch.randn(6)
     ref = O.bias_act(x.double(), b.double(), act='lrelu')
-    assert rel_l2(P.bias_act.bias_act(x.double().cuda(), b.double().cuda(), act='lrelu'), ref) < 1e-12
+    assert rel_l2(P.bias_act.bias_act(x.double().cuda(), b.double().cuda(), act='lrelu'), ref) < 1e-7      # alpha/gain cross the ABI as float32, as in the plugin
     assert rel_l2(P.bias_act.bias_act(x.half().cuda(), b.half().cuda(), act='lrelu').float(), O.bias_act(x.half().float(), b.half().float(), act='lrelu')) < 2e-3
     with pytest.raises(RuntimeError):
         P.bias_act.bias_act(x.cuda(), torch.randn(5).cuda())
