@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the SPI inversion hot path (BASELINE.json metric: inversion iterations / second, 512^2, 64 depth samples).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+Workload (BASELINE.json configs[1]): one 512^2 image, `first_inv_type=mir` followed by `G_1_type=RotBbox` with the README
+lambdas (rot 0.1, mirror 0.05, depth 1, tv 0), 32 coarse + 32 importance samples per ray, nrr = 128.  A "step" is ONE
+optimiser iteration.  The K timed steps keep the 500 : 1000 stage proportion of the config: K/3 `mir` projector
+iterations, then 2K/3 RotBbox iterations (whole 4-iteration cycles, so the i%4==0 branches are weighted correctly).
+Inputs are synthetic (seeded target, camera yaw 0.3, parsing mask, 68 landmarks) and weights random-init (no checkpoint
+exists offline); N > 1 runs one independent image per rank (weak scaling, no data-path collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+import torch
+
+DEPTH = (32, 32)           # "64 depth samples" of the headline metric
+METRIC = 'inversion iters/sec (512^2, 64 depth samples)'
+UNIT = 'it/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=24)
+    ap.add_argument('--warmup', type=int, default=6)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='wall budget of the reference / cpu_baseline legs')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- synthetic inputs (no oracle import here)
+
+def synthetic_inputs(seed=4):
+    """Target image, camera (yaw 0.3 so the mirror branch is active), parsing mask, landmarks -- host tensors."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.randn(1, 3, 16, 16, generator=g)
+    img = torch.nn.functional.interpolate(low, size=(512, 512), mode='bicubic', align_corners=False)
+    img = (img / img.abs().max()).clamp(-1, 1).contiguous()
+    yy, xx = torch.meshgrid(torch.arange(512.), torch.arange(512.), indexing='ij')
+    m = torch.zeros(512, 512, dtype=torch.int64)
+    m[((xx - 256) / 150) ** 2 + ((yy - 200) / 170) ** 2 < 1] = 17
+    m[((xx - 256) / 140) ** 2 + ((yy - 280) / 180) ** 2 < 1] = 1
+    m[((xx - 190) / 30) ** 2 + ((yy - 230) / 14) ** 2 < 1] = 4
+    m[((xx - 322) / 30) ** 2 + ((yy - 230) / 14) ** 2 < 1] = 5
+    m[((xx - 256) / 22) ** 2 + ((yy - 290) / 40) ** 2 < 1] = 10
+    m[((xx - 256) / 50) ** 2 + ((yy - 374) / 16) ** 2 < 1] = 12
+    pts = np.zeros((68, 2), dtype=np.float32)
+    t = np.linspace(0, np.pi, 17)
+    pts[0:17] = np.stack([128 - 70 * np.cos(t), 110 + 90 * np.sin(t)], 1)
+    pts[17:27] = np.stack([np.linspace(75, 181, 10), np.full(10, 95.)], 1)
+    pts[27:36] = np.stack([np.linspace(116, 140, 9), np.linspace(110, 150, 9)], 1)
+    e = np.linspace(0, 2 * np.pi, 7)[:6]
+    pts[36:42] = np.stack([95 + 12 * np.cos(e), 115 + 5 * np.sin(e)], 1)
+    pts[42:48] = np.stack([161 + 12 * np.cos(e), 115 + 5 * np.sin(e)], 1)
+    q = np.linspace(0, 2 * np.pi, 21)[:20]
+    pts[48:68] = np.stack([128 + 25 * np.cos(q), 185 + 9 * np.sin(q)], 1)
+    from spi_b200.utils.camera_utils import cal_canonical_c
+    return dict(img=img, c=cal_canonical_c(0.3, 0.0, 1, 'cpu'), mask=m[None, None], lm=torch.from_numpy(pts)[None])
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
+                'samples': len(self.rows)}
+
+
+class KernelTimer:
+    """CUDA events around tagged launches, recorded on the launching (current) stream."""
+
+    def __init__(self):
+        self.open, self.spans = {}, {}
+
+    def start(self, tag, units=1):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.open[tag] = (e, units)
+
+    def stop(self, tag):
+        e0, units = self.open.pop(tag)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self.spans.setdefault(tag, []).append((e0, e1, units))
+
+    def summary(self, tag):
+        sp = self.spans.get(tag, [])
+        if not sp:
+            return None
+        ms = [a.elapsed_time(b) for a, b, _ in sp]
+        units = [u for _, _, u in sp]
+        return {'launches': len(sp), 'ms_total': float(sum(ms)), 'ms_per_unit': float(sum(ms) / sum(units)), 'units': int(sum(units))}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def render_fwd_bytes(dc, df, res=128):
+    """Algorithmic HBM bytes of one fused render forward per image (DESIGN.md 'Roofline'): planes + rays + jitter + u + out."""
+    r = res * res
+    return 3 * 32 * 256 * 256 * 4 + r * 24 + r * dc * 4 + r * df * 4 + r * 34 * 4 + r * (dc + df) * 4
+
+
+# ----------------------------------------------------------------------------- this repo's arm
+
+class OursJob:
+    """mir projector followed by the RotBbox coach on one image, driven step by step through the public classes."""
+
+    def __init__(self, device, data):
+        from spi_b200.configs import global_config, hyperparameters as hp, paths_config
+        from spi_b200.criteria.bbox_cx_loss import BoxCXLoss
+        from spi_b200.criteria.lpips.lpips import LPIPS
+        from spi_b200.training.coaches.rot_bbox_cx_coach import RotBboxCoach, SPIState
+        from spi_b200.training.projectors._common import LatentProjector
+        from spi_b200.utils import load_utils
+        global_config.device = device
+        paths_config.EG3D_PATH = 'synthetic:0'
+        load_utils.DEPTH_OVERRIDE = DEPTH
+        hp.first_inv_type, hp.G_1_type = 'mir', 'RotBbox'
+        hp.pt_rot_lambda, hp.pt_mirror_rot_lambda, hp.pt_depth_lambda, hp.pt_tv_lambda = 0.1, 0.05, 1.0, 0.0
+        hp.LPIPS_value_threshold = -1.0          # early exit disabled so every timed step does the full work
+        torch.manual_seed(1)
+        self.lpips = LPIPS(net_type='vgg').to(device).eval()
+        torch.manual_seed(2)
+        self.cx = BoxCXLoss().to(device).eval()
+        coach = RotBboxCoach.__new__(RotBboxCoach)
+        coach.use_wandb, coach.data_loader, coach.w_pivots, coach.image_counter = False, None, {}, 0
+        coach.lpips_loss, coach.box_cx_loss = self.lpips, self.cx
+        coach.restart_training()
+        self.coach, self.SPIState, self.LatentProjector = coach, SPIState, LatentProjector
+        self.device = device
+        self.host = data
+        self.pinned = {k: v.pin_memory() for k, v in data.items()}
+        self.upload()
+        self.proj = LatentProjector(coach.G, self.dev['img'], self.dev['c'], 'mir', lpips_func=self.lpips, num_steps=500, w_avg_samples=600)
+        self.state = SPIState(self.dev['img'], self.dev['c'], self.dev['mask'], self.dev['lm'])
+        self.w_pivot = None
+        self.i_mir = self.i_rot = 0
+
+    def upload(self):
+        self.dev = {k: v.to(self.device, non_blocking=True) for k, v in self.pinned.items()}
+        return sum(v.numel() * v.element_size() for v in self.pinned.values())
+
+    def step(self, kind, e2e=False):
+        if e2e:      # host buffers in, loss scalar out, every step
+            self.upload()
+            self.proj.target, self.proj.c = self.dev['img'], self.dev['c']
+            self.proj.target_m = torch.flip(self.dev['img'], dims=[3])
+            self.state = self.SPIState(self.dev['img'], self.dev['c'], self.dev['mask'], self.dev['lm'])
+        if kind == 'mir':
+            out = self.proj.step(self.i_mir % 500)
+            self.i_mir += 1
+            res = out['dist']
+        else:
+            if self.w_pivot is None:
+                self.w_pivot = self.proj.result().detach().clone().requires_grad_(True)
+            res, _ = self.coach.train_step(self.i_rot, self.state, self.w_pivot)
+            self.i_rot += 1
+        if e2e:
+            return float(res)          # device -> host read of the step's loss
+        return res
+
+
+def schedule(k):
+    n_mir = k // 3
+    n_rot = k - n_mir
+    return ['mir'] * n_mir + ['rot'] * n_rot
+
+
+def run_ours(args):
+    from spi_b200 import _lib
+    from spi_b200.training.volumetric_rendering import renderer as R
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (this build has no CPU path)')
+    torch.cuda.set_device(local)
+    device = f'cuda:{local}'
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(device))
+    _lib.load()
+    data = synthetic_inputs(seed=4 + rank)       # one independent image per rank
+    job = OursJob(device, data)
+    k, w = args.steps, args.warmup
+    assert k % 12 == 0, '--steps must be a multiple of 12 (1:2 stage mix, whole 4-iteration RotBbox cycles)'
+    sched = schedule(k)
+    warm = ['mir'] * max(3, w // 3) + ['rot'] * max(4, (w - w // 3 + 3) // 4 * 4)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e):
+        job.i_rot = 0
+        barrier()
+        sampler = ClockSampler(local) if not e2e else None
+        if sampler:
+            sampler.start()
+        _lib.reset_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for kind in sched:
+            job.step(kind, e2e=e2e)
+        e1.record()
+        barrier()
+        launches = _lib.launch_count()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.finish() if sampler else None
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, clocks
+
+    for kind in warm:
+        job.step(kind)
+    timer = KernelTimer()
+    R.KERNEL_TIMER = timer
+    ms, launches, clocks = timed(e2e=False)
+    R.KERNEL_TIMER = None
+    value = world * k / (ms / 1e3)
+    e2e = None
+    if not args.no_e2e:
+        job.step('mir', e2e=True)
+        ms2, _, _ = timed(e2e=True)
+        h2d = sum(v.numel() * v.element_size() for v in job.pinned.values())
+        e2e = {'value': world * k / (ms2 / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms2 / k}
+    # roofline of the dominant hand-written kernel (fused render forward), timed live inside the timed region
+    peak, peak_src = measured_peaks()
+    rf = timer.summary('render_fwd')
+    roofline = None
+    if rf:
+        bytes_per_img = render_fwd_bytes(*DEPTH)
+        ach = bytes_per_img / (rf['ms_per_unit'] * 1e-3) / 1e9
+        roofline = {'kernel': 'render_fwd_kernel (spi_b200/csrc/raymarch.cu)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_image': bytes_per_img,
+                    'ms_per_image': rf['ms_per_unit'], 'launches_timed': rf['launches'],
+                    'note': 'intensity ~385 FLOP/B: the kernel is FP32-issue / L2-gather bound, HBM fraction reported as the contract asks'}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(job, budget_s=min(args.cpu_budget_s, 60.0), heavy=False)
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': k, 'warmup': len(warm), 'ms_per_step': ms / k,
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (TF32 tensor-core contractions)',
+                'data': 'synthetic', 'impl': 'ours',
+                'config': {'workload': 'configs[1]: single 512^2 image per GPU, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
+                           'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': f'{k // 3} mir + {k - k // 3} RotBbox iterations',
+                           'l2_policy': 'per-step working set (weights + activations, > 1 GB) exceeds the 126 MB L2', 'images_per_gpu': 1},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port of the reference)
+
+def oracle_job(job_or_none, rank=0):
+    """Build the oracle Projector / Coach on the same weights and inputs as the GPU job."""
+    from oracle import loops as OL
+    from oracle import generator as OG
+    if job_or_none is not None:
+        sd = {k: v.detach().cpu().clone() for k, v in job_or_none.coach.original_G.state_dict().items()}
+        vgg = {k: v.detach().cpu() for k, v in job_or_none.lpips.net.layers.state_dict().items()}
+        lin = [l[1].weight.detach().cpu() for l in job_or_none.lpips.lin]
+        vgg19 = {k: v.detach().cpu() for k, v in job_or_none.cx.vgg_model.slice1.state_dict().items()}
+        data = job_or_none.host
+    else:
+        from spi_b200.criteria.bbox_cx_loss import BoxCXLoss
+        from spi_b200.criteria.lpips.lpips import LPIPS
+        from spi_b200.utils import load_utils
+        load_utils.DEPTH_OVERRIDE = DEPTH
+        sd = load_utils.build_generator(device='cpu', seed=0).state_dict()
+        torch.manual_seed(1)
+        lp = LPIPS(net_type='vgg')
+        torch.manual_seed(2)
+        cx = BoxCXLoss()
+        vgg, lin = lp.net.layers.state_dict(), [l[1].weight.detach() for l in lp.lin]
+        vgg19 = cx.vgg_model.slice1.state_dict()
+        data = synthetic_inputs(seed=4 + rank)
+    nets = {'vgg16': vgg, 'lin': lin, 'vgg19': vgg19}
+    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=DEPTH[0], depth_resolution_importance=DEPTH[1])
+    return OL, sd, nets, rk, data
+
+
+def cpu_baseline(job, budget_s, heavy):
+    """The oracle (CPU restatement of the reference, kind='port') timed on the host cores on a bounded sample."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    OL, sd, nets, rk, data = oracle_job(job)
+    w = torch.randn(1, 14, 512, generator=torch.Generator().manual_seed(5)) * 0.5
+    coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind='RotBbox', rk=rk, noise=OL.NoiseSource(0))
+    t0 = time.perf_counter()
+    n = 0
+    i = 1                          # i % 4 != 0: main branch only (the light iteration)
+    while True:
+        coach.step(i)
+        n += 1
+        i += 1
+        if i % 4 == 0:
+            i += 1
+        if time.perf_counter() - t0 > budget_s / 3 or n >= 3:
+            break
+    dt = time.perf_counter() - t0
+    return {'value': n / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f'{n} RotBbox G-stage iteration(s) with i%4!=0 (main L2+LPIPS branch only; the i%4==0 iteration is ~10x heavier '
+                      f'and is timed by --impl reference), depth 32+32, oracle/loops.py on torch CPU fp32'}
+
+
+def run_reference(args):
+    """`--impl reference`: the reference algorithm on the host CPU (oracle port; the reference itself is Python and cannot
+    travel to the GPU box).  Steps are time-bounded: 1 warm-up + up to K iterations following the same stage mix, stopped
+    once the wall budget is spent (always at least one full 4-iteration RotBbox cycle is attempted first)."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    OL, sd, nets, rk, data = oracle_job(None)
+    t_all = time.perf_counter()
+    proj = OL.Projector(sd, data['img'], data['c'], nets, kind='mir', num_steps=500, rk=rk, noise=OL.NoiseSource(1))
+    w = proj.result().clone()
+    coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind='RotBbox', rk=rk, noise=OL.NoiseSource(2))
+    coach.step(1)                                   # warm-up (light iteration)
+    budget = args.cpu_budget_s
+    t0 = time.perf_counter()
+    done = {'mir': 0, 'rot': 0}
+    # one whole RotBbox cycle first (i = 0 heavy + 3 light), then mir steps in the 1:2 proportion, budget permitting
+    for i in range(4):
+        coach.step(i)
+        done['rot'] += 1
+        if time.perf_counter() - t0 > budget:
+            break
+    while done['mir'] < max(1, done['rot'] // 2) and time.perf_counter() - t0 < budget:
+        proj.step(done['mir'] + 25)
+        done['mir'] += 1
+    dt = time.perf_counter() - t0
+    n = done['mir'] + done['rot']
+    value = n / dt
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': 1, 'ms_per_step': dt / n * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': 'configs[1]: single 512^2 image, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
+                       'depth_samples': '32+32', 'neural_rendering_resolution': 128,
+                       'step_mix': f"{done['mir']} mir + {done['rot']} RotBbox iterations (time-bounded sample)"},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+                             'sample': f"{done['rot']} RotBbox iterations (i=0..{done['rot'] - 1}, one heavy i%4==0) + {done['mir']} mir iterations, "
+                                       f'{dt:.1f} s wall, setup {t0 - t_all:.1f} s excluded'},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    a = parse()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -13,6 +13,7 @@ from ... import _lib
 from .ray_marcher import MipRayMarcher2
 
 SCRATCH_COLS = (32, 64, 64, 36)
+KERNEL_TIMER = None      # bench.py installs an object with .start(tag) / .stop(tag) that records CUDA events on the launch stream
 
 
 def generate_planes():
@@ -61,11 +62,15 @@ class _RenderFn(torch.autograd.Function):
         wsum = torch.empty(n, r, 1, device=dev)
         depths_all = torch.empty(n, r, dc + df, device=dev)
         minmax = torch.empty(2, dtype=torch.int32, device=dev)
+        if KERNEL_TIMER is not None:
+            KERNEL_TIMER.start('render_fwd', n)
         _lib.check(lib.spi_render_forward(
             _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(jitter), _lib.ptr(u), _lib.ptr(w1), _lib.ptr(b1),
             _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(feat), _lib.ptr(depth), _lib.ptr(wsum), _lib.ptr(depths_all),
             None, _lib.ptr(minmax), n, r, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
             int(opts['disparity']), _lib.stream()))
+        if KERNEL_TIMER is not None:
+            KERNEL_TIMER.stop('render_fwd')
         ctx.save_for_backward(planes, w1, b1, w2, b2, origins, dirs, depths_all, minmax)
         ctx.opts = opts
         ctx.mark_non_differentiable(wsum)

@@ -27,11 +27,14 @@ FFHQ512_KWARGS = dict(
         decoder_lr_mul=1.0, sr_antialias=True, depth_resolution=48, depth_resolution_importance=48, ray_start=2.25,
         ray_end=3.3, box_warp=1, avg_camera_radius=2.7, avg_camera_pivot=[0, 0, 0.2]))
 
+DEPTH_OVERRIDE = None   # (depth_resolution, depth_resolution_importance) forced on every generator built here (bench sweeps)
 _template = {}      # network_pkl -> (init_kwargs, cpu state dict): unpickle / initialise once, clone per restart_training()
 
 
 def build_generator(init_kwargs=None, state_dict=None, device=None, seed=None):
     kw = copy.deepcopy(init_kwargs or FFHQ512_KWARGS)
+    if DEPTH_OVERRIDE is not None:
+        kw['rendering_kwargs']['depth_resolution'], kw['rendering_kwargs']['depth_resolution_importance'] = DEPTH_OVERRIDE
     if seed is not None:
         torch.manual_seed(seed)
     G = TriPlaneGenerator(**kw).eval().requires_grad_(False)
