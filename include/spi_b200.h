@@ -34,6 +34,12 @@ int spi_bias_act(const void* x, const void* b, const void* xref, const void* yre
                  long long numel, int size_b, int step_b, int dtype, int grad, int act, float alpha, float gain,
                  float clamp, cudaStream_t stream);
 
+/* SynthesisLayer epilogue (networks_stylegan2.py:320-329) in one pass: y = clamp(act(x + noise[h,w]*strength + b[c])*gain).
+ * noise: fp32 [hw]; noise_strength: device scalar; channels_last_c = C for channels-last x, 0 for NCHW. */
+int spi_bias_act_noise(const void* x, const void* b, void* y, const float* noise, const float* noise_strength, long long numel,
+                       int size_b, int step_b, int hw, int channels_last_c, int dtype, int act, float alpha, float gain,
+                       float clamp, cudaStream_t stream);
+
 /* upfirdn2d plugin op: eg3d/torch_utils/ops/upfirdn2d.cpp:20-105 (kernels upfirdn2d.cu:33-204).
  * f: fp32 [fh, fw]; strides in elements, order (n, c, h, w); y is [n, c, out_h, out_w] with
  * out = (in*up + pad0 + pad1 - f + down) / down (upfirdn2d.cpp:49-50). */
@@ -95,6 +101,15 @@ int spi_inverse_cdf(const float* bins, const float* cdf, const float* u, int ray
 int spi_unify_samples(const float* depths_coarse, const float* depths_fine, int rays, int dc, int df, int* perm,
                       float* sorted, cudaStream_t stream);                                                    /* renderer.py:157-167 */
 
+/* ---- modulated-convolution weight preparation: replaces the elementwise chain of modulated_conv2d
+ *      (eg3d/training/networks_stylegan2.py:58-68) -------------------------------------------------------- */
+/* out[n,o,i,k] = W[o,i,k]*s[n,i] (* rsqrt(sum_{i,k}(W s)^2 + 1e-8) when demodulate); dcoef [n,o] saved for backward. */
+int spi_modulate_weights(const float* weight, const float* styles, float* out, float* dcoef, int n, int o, int i, int kk,
+                         int demodulate, cudaStream_t stream);
+int spi_modulate_weights_backward(const float* weight, const float* styles, const float* dcoef, const float* grad_out,
+                                  float* grad_weight, float* grad_styles, int n, int o, int i, int kk, int demodulate,
+                                  cudaStream_t stream);
+
 /* ---- depth-guided 3-D warp: replaces rotate() (spi/utils/rotate.py:92-116) --------------------------- */
 /* cameras [n, 25]; depths [n, 1, depth_res, depth_res]; image [n, 3, res, res]; mask [n, 1, res, res] or NULL;
  * *_bs = batch strides in elements of the source tensors (0 broadcasts one source over n views, replacing the
@@ -106,9 +121,12 @@ int spi_rotate(const float* target_camera, const float* target_depth, const floa
 
 /* ---- optimiser / streaming helpers -------------------------------------------------------------------- */
 /* torch.optim.Adam step (base_coach.py:134, *_projector.py:58) over flat fp32 arenas; hyper (device, optional)
- * = {lr, 1-beta1^t, 1-beta2^t}; zero_grad != 0 clears the gradient arena in the same pass. */
+ * = {lr, 1-beta1^t, 1-beta2^t}; zero_grad != 0 clears the gradient arena in the same pass; skip_if_le (device scalar,
+ * optional): the step is a no-op when *skip_if_le <= skip_threshold -- the early exit of rot_bbox_cx_coach.py:148-151
+ * (`if loss_lpips <= threshold: break` BEFORE `optimizer.step()`) without a host synchronisation. */
 int spi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                  float beta2, float eps, int step, const float* hyper, int zero_grad, cudaStream_t stream);
+                  float beta2, float eps, int step, const float* hyper, int zero_grad, const float* skip_if_le,
+                  float skip_threshold, cudaStream_t stream);
 /* F.interpolate(..., (H/2, W/2), mode='bilinear'|'area') at exactly half size (lpips.py:38-39, bbox_cx_loss.py:161-163,
  * w_projector.py:50,83); contiguous [planes, 2*out_h, 2*out_w] -> [planes, out_h, out_w]; backward != 0 runs the adjoint. */
 int spi_downsample2x(const float* x, float* y, long long planes, int out_h, int out_w, int backward, cudaStream_t stream);

@@ -6,3 +6,6 @@ log_snapshot = 500
 pivotal_training_steps = 0
 model_snapshot_interval = 400
 run_name = ''
+
+## spi_b200: replay each optimisation iteration as a captured CUDA graph (eager when False or when tests inject noise)
+use_cuda_graphs = True

@@ -21,6 +21,8 @@ struct BiasActParams {
     float alpha, gain, clamp;
     long long n;
     int sizeB, stepB, force_scalar;
+    const float* noise; const float* noise_strength;   // optional per-pixel noise map [H*W] * device scalar, added with the bias
+    int hw, cl_c;                                       // pixels per image; channels if channels-last else 0
 };
 
 template <class S, int A>
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p) {
     const T* x = (const T*)p.x; const T* b = (const T*)p.b; const T* xr = (const T*)p.xref;
     const T* yr = (const T*)p.yref; const T* dyp = (const T*)p.dy; T* y = (T*)p.y;
     const long long nvec = p.n / V;
-    const bool vec_ok = !p.force_scalar && ((b == nullptr) || (p.stepB % V == 0) || (p.stepB == 1 && p.sizeB % V == 0));
+    const bool vec_ok = !p.force_scalar && (!p.noise || (p.cl_c ? (p.cl_c % V == 0) : true)) && ((b == nullptr) || (p.stepB % V == 0) || (p.stepB == 1 && p.sizeB % V == 0));
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (vec_ok) {
@@ -105,13 +107,25 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p) {
             long long e0 = i * V;
             S bs = 0;
             bool bvec = false;
+            S nz[V];
+#pragma unroll
+            for (int k = 0; k < V; k++) nz[k] = 0;
+            if (p.noise) {
+                const S st = (S)p.noise_strength[0];
+                if (p.cl_c) { S v = (S)p.noise[(e0 / p.cl_c) % p.hw] * st;
+#pragma unroll
+                    for (int k = 0; k < V; k++) nz[k] = v; }
+                else {
+#pragma unroll
+                    for (int k = 0; k < V; k++) nz[k] = (S)p.noise[(e0 + k) % p.hw] * st; }
+            }
             if (b) {
                 if (p.stepB == 1) { vb = *(const P*)(b + (e0 % p.sizeB)); bvec = true; }
                 else bs = (S)b[(e0 / p.stepB) % p.sizeB];
             }
 #pragma unroll
             for (int k = 0; k < V; k++) {
-                S bb = bvec ? (S)vb.v[k] : bs;
+                S bb = (bvec ? (S)vb.v[k] : bs) + nz[k];
                 out.v[k] = (T)act_eval<S, A>((S)vx.v[k], bb, xr ? (S)vxr.v[k] : (S)0, yr ? (S)vyr.v[k] : (S)0,
                                              dyp ? (S)vdy.v[k] : (S)1, G, alpha, gain, clamp);
             }
@@ -121,6 +135,7 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p) {
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (long long e = (vec_ok ? nvec * V : 0) + tid; e < p.n; e += stride) {
         S bb = b ? (S)b[(e / p.stepB) % p.sizeB] : (S)0;
+        if (p.noise) bb += (S)p.noise[p.cl_c ? (e / p.cl_c) % p.hw : e % p.hw] * (S)p.noise_strength[0];
         y[e] = (T)act_eval<S, A>((S)x[e], bb, xr ? (S)xr[e] : (S)0, yr ? (S)yr[e] : (S)0, dyp ? (S)dyp[e] : (S)1, G,
                                  alpha, gain, clamp);
     }
@@ -144,9 +159,10 @@ void* pick_kernel(int act) {
 
 }  // namespace
 
-extern "C" int spi_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
-                            long long numel, int size_b, int step_b, int dtype, int grad, int act, float alpha,
-                            float gain, float clamp, cudaStream_t stream) {
+static int bias_act_impl(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                         long long numel, int size_b, int step_b, int dtype, int grad, int act, float alpha,
+                         float gain, float clamp, const float* noise, const float* noise_strength, int hw, int cl_c,
+                         cudaStream_t stream) {
     SPI_CHECK_ARG(x && y, "bias_act: x and y must be non-null");
     SPI_CHECK_ARG(numel >= 0 && numel <= 2147483647LL, "bias_act: x is too large");
     SPI_CHECK_ARG(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2");
@@ -162,7 +178,7 @@ extern "C" int spi_bias_act(const void* x, const void* b, const void* xref, cons
     // The vector path needs 16-byte aligned pointers (torch allocations are; offset views may not be).
     uintptr_t al = (uintptr_t)x | (uintptr_t)y | (uintptr_t)xref | (uintptr_t)yref | (uintptr_t)dy | (uintptr_t)b;
     BiasActParams p{x, b, xref, yref, dy, y, grad, act, alpha, gain, clamp, numel, b ? size_b : 1, b ? step_b : 1,
-                    (al & 15) ? 1 : 0};
+                    (al & 15) ? 1 : 0, noise, noise_strength, hw > 0 ? hw : 1, cl_c};
     const int block = 256;
     long long work = p.force_scalar ? numel : (numel + vec - 1) / vec;
     long long blocks = (work + block * 2 - 1) / (block * 2);
@@ -173,4 +189,21 @@ extern "C" int spi_bias_act(const void* x, const void* b, const void* xref, cons
     SPI_COUNT_LAUNCH(1);
     if (e != cudaSuccess) { spi_set_error("bias_act: %s", cudaGetErrorString(e)); return SPI_ERR_CUDA; }
     return SPI_OK;
+}
+
+extern "C" int spi_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y,
+                            long long numel, int size_b, int step_b, int dtype, int grad, int act, float alpha,
+                            float gain, float clamp, cudaStream_t stream) {
+    return bias_act_impl(x, b, xref, yref, dy, y, numel, size_b, step_b, dtype, grad, act, alpha, gain, clamp, nullptr, nullptr, 1, 0, stream);
+}
+
+// Layer epilogue of SynthesisLayer.forward (networks_stylegan2.py:320-329) in one pass:
+//   y = clamp(act(x + noise[h,w] * noise_strength + b[c]) * gain);  x is [N,C,H,W] dense, NCHW (cl_c = 0) or channels-last (cl_c = C).
+extern "C" int spi_bias_act_noise(const void* x, const void* b, void* y, const float* noise, const float* noise_strength,
+                                  long long numel, int size_b, int step_b, int hw, int channels_last_c, int dtype, int act,
+                                  float alpha, float gain, float clamp, cudaStream_t stream) {
+    SPI_CHECK_ARG(noise && noise_strength && hw >= 1, "bias_act_noise: noise map required");
+    SPI_CHECK_ARG(dtype == SPI_DT_F32, "bias_act_noise: float32 only");
+    return bias_act_impl(x, b, nullptr, nullptr, nullptr, y, numel, size_b, step_b, dtype, 0, act, alpha, gain, clamp, noise,
+                         noise_strength, hw, channels_last_c, stream);
 }

@@ -13,7 +13,10 @@ namespace {
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long long n, float lr, float b1, float b2, float eps,
-                                                   float bc1, float bc2, const float* __restrict__ hyper, int zero_grad, float* gz) {
+                                                   float bc1, float bc2, const float* __restrict__ hyper, int zero_grad, float* gz,
+                                                   const float* __restrict__ cond, float cond_thr) {
+    // device-side early exit (rot_bbox_cx_coach.py:148-151 breaks BEFORE optimizer.step()): no update when *cond <= thr
+    if (cond && cond[0] <= cond_thr) return;
     if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }
     const float step_size = lr / bc1;
     const float rsbc2 = 1.f / sqrtf(bc2);
@@ -69,7 +72,8 @@ __global__ void __launch_bounds__(256) half_bwd_kernel(const float* __restrict__
 }  // namespace
 
 extern "C" int spi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
-                             float beta2, float eps, int step, const float* hyper, int zero_grad, cudaStream_t stream) {
+                             float beta2, float eps, int step, const float* hyper, int zero_grad, const float* skip_if_le, float skip_threshold,
+                             cudaStream_t stream) {
     SPI_CHECK_ARG(param && grad && exp_avg && exp_avg_sq, "adam_step: null pointer");
     SPI_CHECK_ARG(step >= 1 || hyper, "adam_step: step must be >= 1");
     SPI_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) & 15) == 0, "adam_step: arenas must be 16-byte aligned");
@@ -82,7 +86,7 @@ extern "C" int spi_adam_step(float* param, const float* grad, float* exp_avg, fl
     long long blocks = (n / 4 + 255) / 256;
     long long cap = (long long)spi_num_sms() * 8;
     int grid = (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
-    adam_kernel<<<grid, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, hyper, zero_grad, (float*)grad);
+    adam_kernel<<<grid, 256, 0, stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, bc1, bc2, hyper, zero_grad, (float*)grad, skip_if_le, skip_threshold);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("adam_step");
     return SPI_OK;

@@ -35,6 +35,8 @@ class FlatAdam:
                 off += sz
         self.param_groups = [dict(params=self.params, lr=lr, betas=betas, eps=eps)]
         self.steps = 0
+        self.hyper = None            # device {lr, bc1, bc2}: enable with use_device_hyper() for CUDA-graph replay
+        self.skip_if_le = None       # (device scalar tensor, threshold): device-side early exit
 
     def zero_grad(self, set_to_none=False):
         self.grads.zero_()
@@ -53,11 +55,31 @@ class FlatAdam:
             p.grad = view
             off += sz
 
-    @torch.no_grad()
-    def step(self):
-        self._reseat()
+    def use_device_hyper(self):
+        """Keep {lr, 1-b1^t, 1-b2^t} in a device tensor refreshed by `advance()` so that `step()` can live inside a CUDA graph."""
+        self.hyper = torch.zeros(3, device=self.arena.device)
+        self._hyper_host = torch.zeros(3).pin_memory()
+
+    def advance(self):
+        """Host side of a graphed step: bump the step counter and upload the scalars the captured kernel reads."""
         self.steps += 1
         g = self.param_groups[0]
+        self._hyper_host[0] = float(g['lr'])
+        self._hyper_host[1] = 1.0 - g['betas'][0] ** self.steps
+        self._hyper_host[2] = 1.0 - g['betas'][1] ** self.steps
+        self.hyper.copy_(self._hyper_host, non_blocking=True)
+
+    @torch.no_grad()
+    def step(self, in_graph=False):
+        if not in_graph:
+            self._reseat()
+            if self.hyper is None:
+                self.steps += 1
+            else:
+                self.advance()
+        g = self.param_groups[0]
+        cond, thr = self.skip_if_le if self.skip_if_le is not None else (None, 0.0)
         _lib.check(_lib.load().spi_adam_step(_lib.ptr(self.arena), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                              self.arena.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
-                                             self.steps, None, 0, _lib.stream()))
+                                             max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None, 0,
+                                             _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))

@@ -127,3 +127,53 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
     if not x.is_cuda:
         raise RuntimeError('spi_b200.bias_act: x must reside on a CUDA device (no CPU path in this build)')
     return _BiasAct.apply(x, b, cfg)
+
+
+class _BiasActNoise(torch.autograd.Function):
+    """SynthesisLayer epilogue (networks_stylegan2.py:320-329) in one pass: y = clamp(act(x + noise*strength + b) * gain)."""
+
+    @staticmethod
+    def forward(ctx, x, b, noise_const, noise_strength, cfg):
+        dim, spec, alpha, gain, clamp = cfg
+        assert dim == 1 and x.ndim == 4 and 'x' not in spec.ref
+        fmt = _dense_like(x)
+        x = x.contiguous(memory_format=fmt)
+        n, c, h, w = x.shape
+        y = torch.empty_like(x)
+        nc = noise_const.contiguous()
+        _lib.check(_lib.load().spi_bias_act_noise(
+            _lib.ptr(x), _lib.ptr(b.contiguous()), _lib.ptr(y), _lib.ptr(nc), _lib.ptr(noise_strength), x.numel(), c, x.stride(1),
+            h * w, c if fmt == torch.channels_last else 0, _lib.dtype_code(x), spec.cuda_idx, alpha, gain, clamp, _lib.stream()))
+        ctx.save_for_backward(b, y, nc, noise_strength)
+        ctx.cfg, ctx.fmt = cfg, fmt
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dim, spec, alpha, gain, clamp = ctx.cfg
+        b, y, nc, strength = ctx.saved_tensors
+        dy = dy.contiguous(memory_format=ctx.fmt)
+        dx = _BiasActGrad.apply(dy, None, b, y, ctx.cfg)
+        db = dn = ds = None
+        if ctx.needs_input_grad[1]:
+            db = dx.sum([0, 2, 3])
+        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
+            pix = dx.sum([0, 1])                      # [H, W]: d/d(noise term)
+            if ctx.needs_input_grad[2]:
+                dn = pix * strength
+            if ctx.needs_input_grad[3]:
+                ds = (pix * nc).sum()
+        return dx, db, dn, ds, None
+
+
+def bias_act_noise(x, b, noise_const, noise_strength, act='lrelu', alpha=None, gain=None, clamp=None):
+    """`bias_act(x + noise_const * noise_strength, b, ...)` fused (x: [N,C,H,W] fp32, noise_const [H,W], noise_strength [])."""
+    assert clamp is None or clamp >= 0
+    spec = activation_funcs[act]
+    cfg = (1, spec, float(alpha if alpha is not None else spec.def_alpha),
+           float(gain if gain is not None else spec.def_gain), float(clamp if clamp is not None else -1))
+    if not x.is_cuda:
+        raise RuntimeError('spi_b200.bias_act_noise: x must reside on a CUDA device (no CPU path in this build)')
+    if x.dtype != torch.float32 or 'x' in spec.ref:
+        return bias_act(x + noise_const * noise_strength, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+    return _BiasActNoise.apply(x, b, noise_const, noise_strength, cfg)

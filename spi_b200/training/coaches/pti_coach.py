@@ -4,6 +4,8 @@ import os
 import torch
 
 from ...configs import global_config, hyperparameters, paths_config
+from ...graphs import GraphedStep
+from ...utils import rng
 from ...criteria.l2_loss import l2_loss
 from .base_coach import BaseCoach
 
@@ -25,16 +27,40 @@ class SingleIDCoach(BaseCoach):
             loss = loss + loss_lpips * hyperparameters.pt_lpips_lambda
         return loss, loss_lpips
 
-    def train_step(self, w_pivot, camera, image):
-        """One iteration of pti_coach.py:62-74; returns (loss_lpips, stepped)."""
+    def _body(self, w_pivot, camera, image):
+        """pti_coach.py:62-74 without host synchronisation; the early exit is applied on the device (conditional Adam)."""
         generated_images = self.G.synthesis(w_pivot, camera, noise_mode='const')['image']
         loss, loss_lpips = self.calc_loss(generated_images, image)
         self.optimizer.zero_grad()
-        if loss_lpips <= hyperparameters.LPIPS_value_threshold:      # one host sync per iteration, as in the reference
-            return loss_lpips, False
         loss.backward()
-        self.optimizer.step()
-        return loss_lpips, True
+        with torch.no_grad():
+            self._lpips_out.copy_(loss_lpips.detach())
+        self.optimizer.skip_if_le = (self._lpips_out, hyperparameters.LPIPS_value_threshold)
+        self.optimizer.step(in_graph=True)
+        return self._lpips_out
+
+    def train_step(self, w_pivot, camera, image):
+        """One iteration; returns (loss_lpips, stepped)."""
+        if not hasattr(self, '_lpips_out') or self._lpips_out.device != w_pivot.device:
+            self._lpips_out = torch.zeros((), device=w_pivot.device)
+            self._graphs = {}
+        if self.optimizer.hyper is None:
+            self.optimizer.use_device_hyper()
+        self.optimizer._reseat()
+        self.optimizer.advance()
+        eager = (not global_config.use_cuda_graphs) or rng.pending() or bool(self.G.renderer._noise_queue)
+        if eager:
+            self._body(w_pivot, camera, image)
+        else:
+            key = (id(w_pivot), id(camera), id(image), id(self.G))
+            if key not in self._graphs:
+                state = [self.optimizer.arena, self.optimizer.exp_avg, self.optimizer.exp_avg_sq]
+                self._graphs[key] = (GraphedStep(lambda: self._body(w_pivot, camera, image), state), w_pivot, camera, image)
+            self._graphs[key][0]()
+        stepped = bool(self._lpips_out > hyperparameters.LPIPS_value_threshold)
+        if not stepped:
+            self.optimizer.steps -= 1
+        return self._lpips_out, stepped
 
     def train(self):
         paths_config.experiments_output_dir += f'{self.coach_name}'

@@ -7,6 +7,8 @@ import os
 import torch
 
 from ...configs import global_config, hyperparameters, paths_config
+from ...graphs import GraphedStep
+from ...utils import rng
 from ...criteria.bbox_cx_loss import BoxCXLoss
 from ...criteria.l2_loss import l2_loss
 from ...criteria.tv_loss import cal_tv_loss
@@ -39,8 +41,10 @@ class RotBboxCoach(BaseCoach):
         self.build_name()
         self.box_cx_loss = box_cx_loss if box_cx_loss is not None else BoxCXLoss().to(global_config.device).eval()
 
-    def train_step(self, i, st, w_pivot, rot_bs=4):
-        """One iteration of rot_bbox_cx_coach.py:68-157; returns (loss_lpips, stepped)."""
+    def _body(self, heavy, st, w_pivot, rot_bs=4):
+        """One iteration of rot_bbox_cx_coach.py:68-157 without host synchronisation (capturable as a CUDA graph).
+        The early exit (`if loss_lpips <= threshold: break` BEFORE `optimizer.step()`, :148-151) is applied on the device:
+        the Adam kernel is a no-op when the LPIPS scalar is below the threshold; the host reads the scalar afterwards."""
         hp = hyperparameters
         self.optimizer.zero_grad()
         gen = self.G.synthesis(w_pivot, st.camera, noise_mode='const')
@@ -52,7 +56,7 @@ class RotBboxCoach(BaseCoach):
             loss_lpips = torch.squeeze(self.lpips_loss(generated_images, st.image))
             loss = loss + loss_lpips * hp.pt_lpips_lambda
         loss.backward()
-        if i % rot_bs == 0:
+        if heavy:
             if hp.pt_rot_lambda > 0:
                 cams = sample_surrounding_camera(st.camera, batch_size=rot_bs, yaw_range=st.yaw_range, pitch_range=0.1)
                 samples = self.G.synthesis(w_pivot.repeat(rot_bs, 1, 1), cams, noise_mode='const')
@@ -83,10 +87,37 @@ class RotBboxCoach(BaseCoach):
                 (l2_loss(stable_depth, sample_depth) * hp.pt_depth_lambda).backward()
             if hp.pt_tv_lambda > 0:
                 (cal_tv_loss(w_pivot, self.G) * hp.pt_tv_lambda).backward()
-        if loss_lpips <= hp.LPIPS_value_threshold:       # early exit happens BEFORE the step (:148-151)
-            return loss_lpips, False
-        self.optimizer.step()
-        return loss_lpips, True
+        with torch.no_grad():
+            self._lpips_out.copy_(loss_lpips.detach())
+        self.optimizer.skip_if_le = (self._lpips_out, hp.LPIPS_value_threshold)
+        self.optimizer.step(in_graph=True)
+        return self._lpips_out
+
+    def train_step(self, i, st, w_pivot, rot_bs=4):
+        """One iteration; returns (loss_lpips, stepped).  Iterations are replayed as CUDA graphs (one for the plain iteration,
+        one for the i % 4 == 0 iteration) unless disabled or a test has injected random draws."""
+        heavy = (i % rot_bs == 0)
+        if not hasattr(self, '_lpips_out') or self._lpips_out.device != w_pivot.device:
+            self._lpips_out = torch.zeros((), device=w_pivot.device)
+            self._graphs = {}
+        if self.optimizer.hyper is None:
+            self.optimizer.use_device_hyper()
+        self.optimizer._reseat()
+        self.optimizer.advance()
+        eager = (not global_config.use_cuda_graphs) or rng.pending() or bool(self.G.renderer._noise_queue) or bool(self.original_G.renderer._noise_queue)
+        if eager:
+            self._body(heavy, st, w_pivot, rot_bs)
+        else:
+            key = (heavy, id(st), id(w_pivot), id(self.G))
+            if key not in self._graphs:
+                state = [self.optimizer.arena, self.optimizer.exp_avg, self.optimizer.exp_avg_sq]
+                self._graphs[key] = (GraphedStep(lambda: self._body(heavy, st, w_pivot, rot_bs), state), st, w_pivot)
+            self._graphs[key][0]()
+        loss_lpips = self._lpips_out
+        stepped = bool(loss_lpips > hyperparameters.LPIPS_value_threshold)      # one host read per iteration, as the reference's `if`
+        if not stepped:
+            self.optimizer.steps -= 1
+        return loss_lpips, stepped
 
     def train(self):
         paths_config.experiments_output_dir += f'{self.coach_name}'

@@ -15,6 +15,7 @@ import numpy as np
 import torch
 
 from ..ops import conv as conv_engine
+from ..ops.modulate import modulate_weights
 from ..torch_utils import misc, persistence
 from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
 
@@ -51,6 +52,14 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     misc.assert_shape(weight, [out_channels, in_channels, kh, kw])
     misc.assert_shape(x, [batch_size, in_channels, None, None])
     misc.assert_shape(styles, [batch_size, in_channels])
+    if fused_modconv and x.dtype == torch.float32:
+        # one launch: w[n,o,i,k] = W*s (*rsqrt(sum (W s)^2 + 1e-8))  (spi_modulate_weights)
+        w = modulate_weights(weight, styles, demodulate)
+        assert down == 1
+        x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
+        if noise is not None:
+            x = x + noise
+        return x
     w = dcoefs = None
     if demodulate or fused_modconv:
         w = weight.unsqueeze(0) * styles.reshape(batch_size, 1, -1, 1, 1)           # [N,O,I,kh,kw]
@@ -89,14 +98,14 @@ class FullyConnectedLayer(torch.nn.Module):
         self.bias_gain = lr_multiplier
 
     def forward(self, x):
-        w = self.weight.to(x.dtype) * self.weight_gain
         b = self.bias
         if b is not None:
             b = b.to(x.dtype)
             if self.bias_gain != 1:
                 b = b * self.bias_gain
-        if self.activation == 'linear' and b is not None:
-            return torch.addmm(b.unsqueeze(0), x, w.t())
+        if self.activation == 'linear' and b is not None:     # (x W^T) * gain + b in one GEMM call (gain as alpha)
+            return torch.addmm(b.unsqueeze(0), x, self.weight.to(x.dtype).t(), alpha=float(self.weight_gain))
+        w = self.weight.to(x.dtype) * self.weight_gain
         return bias_act.bias_act(x.matmul(w.t()), b, act=self.activation)
 
     def extra_repr(self):
@@ -177,12 +186,16 @@ class SynthesisLayer(torch.nn.Module):
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
-        if self.use_noise and noise_mode == 'const':
+        fuse_noise = self.use_noise and noise_mode == 'const' and x.dtype == torch.float32
+        if self.use_noise and noise_mode == 'const' and not fuse_noise:
             noise = self.noise_const * self.noise_strength
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                              resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        if fuse_noise:      # + noise_const*noise_strength + bias -> lrelu*gain -> clamp in one pass
+            return bias_act.bias_act_noise(x, self.bias.to(x.dtype), self.noise_const, self.noise_strength, act=self.activation,
+                                           gain=act_gain, clamp=act_clamp)
         return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
 
     def extra_repr(self):

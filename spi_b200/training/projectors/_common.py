@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 
 from ...configs import global_config
+from ...graphs import GraphedStep
 from ...optim import FlatAdam
 from ...ops.resize import downsample2x
 from ...utils import rng
@@ -68,6 +69,11 @@ class LatentProjector:
             buf[:] = rng.randn_like(buf)
             buf.requires_grad = True
         self.optimizer = FlatAdam([self.w_opt] + list(self.noise_bufs.values()), betas=(0.9, 0.999), lr=initial_learning_rate)
+        self.optimizer.use_device_hyper()
+        self.w_noise_scale = torch.zeros((), device=device)          # per-step scalar, read on device (graph replay)
+        self._scale_host = torch.zeros(()).pin_memory()
+        self._graph = None
+        self._out = dict(loss=torch.zeros((), device=device), dist=torch.zeros((), device=device), image=None)
         self.target, self.c = target, c
         self.lpips_func, self.vgg16 = lpips_func, vgg16
         if kind == 'mir':
@@ -89,11 +95,9 @@ class LatentProjector:
         lr_ramp = lr_ramp * min(1.0, t / hp['up'])
         return hp['lr0'] * lr_ramp, w_noise_scale
 
-    def step(self, step):
-        lr, w_noise_scale = self.schedule(step)
-        for g in self.optimizer.param_groups:
-            g['lr'] = lr
-        ws = self.w_opt + rng.randn_like(self.w_opt) * w_noise_scale
+    def _body(self):
+        """One iteration, free of host synchronisation (capturable): mirror_projector.py:93-131."""
+        ws = self.w_opt + rng.randn_like(self.w_opt) * self.w_noise_scale
         G = self.G
         if self.kind == 'mir':
             out = G.synthesis(ws.repeat(2, 1, 1), self.target_camera, noise_mode='const')
@@ -110,12 +114,34 @@ class LatentProjector:
         loss = dist + reg_loss * self.hp['regw']
         self.optimizer.zero_grad(set_to_none=True)
         loss.backward()
-        self.optimizer.step()
+        self.optimizer.step(in_graph=True)
         with torch.no_grad():
             for buf in self.noise_bufs.values():
                 buf -= buf.mean()
                 buf *= buf.square().mean().rsqrt()
-        self.last = dict(loss=loss.detach(), dist=dist.detach(), image=img.detach())
+            self._out['loss'].copy_(loss.detach())
+            self._out['dist'].copy_(dist.detach())
+            if self._out['image'] is None:
+                self._out['image'] = torch.empty_like(img)
+            self._out['image'].copy_(img.detach())
+        return self._out
+
+    def step(self, step):
+        lr, w_noise_scale = self.schedule(step)
+        for g in self.optimizer.param_groups:
+            g['lr'] = lr
+        self._scale_host.fill_(float(w_noise_scale))
+        self.w_noise_scale.copy_(self._scale_host, non_blocking=True)
+        self.optimizer._reseat()
+        self.optimizer.advance()
+        eager = (not global_config.use_cuda_graphs) or rng.pending() or bool(self.G.renderer._noise_queue)
+        if eager:
+            self.last = self._body()
+        else:
+            if self._graph is None:
+                st = [self.optimizer.arena, self.optimizer.exp_avg, self.optimizer.exp_avg_sq]
+                self._graph = GraphedStep(self._body, st)
+            self.last = self._graph()
         return self.last
 
     def result(self):

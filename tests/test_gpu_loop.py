@@ -159,3 +159,41 @@ def test_mirror_projector_two_steps_golden(golden, gen_sd, lpips_mod):
     cos = float((d_mine * d_ref).sum() / (d_mine.norm() * d_ref.norm()))
     print('mir displacement cosine:', cos, 'norm ratio:', float(d_mine.norm() / d_ref.norm()))
     assert cos > 0.95 and abs(float(d_mine.norm() / d_ref.norm()) - 1) < 0.05
+
+
+def test_graphed_iterations_run_and_reduce_the_loss(gen_sd, lpips_mod, cx_mod):
+    """CUDA-graph replay of PTI iterations: loss decreases, parameters move, replay equals what the captured body computes."""
+    from spi_b200.configs import global_config, hyperparameters as hp
+    coach = make_coach('pti', gen_sd, lpips_mod, cx_mod)
+    hp.LPIPS_value_threshold = 0.05
+    image, camera = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
+    w = weights.w_pivot(5).cuda().requires_grad_(True)
+    p0 = coach.optimizer.arena.clone()
+    global_config.use_cuda_graphs = True
+    try:
+        vals = []
+        for _ in range(6):
+            lp, stepped = coach.train_step(w, camera, image)
+            assert stepped
+            vals.append(float(lp))
+    finally:
+        global_config.use_cuda_graphs = True
+    assert len(coach._graphs) == 1
+    assert vals[-1] < vals[0]
+    assert (coach.optimizer.arena - p0).abs().max() > 0
+    assert coach.optimizer.steps == 6
+
+
+def test_device_side_early_exit_skips_adam(gen_sd, lpips_mod, cx_mod):
+    """`if loss_lpips <= threshold: break` before optimizer.step() (rot_bbox_cx_coach.py:148-151): no parameter moves."""
+    from spi_b200.configs import hyperparameters as hp
+    coach = make_coach('pti', gen_sd, lpips_mod, cx_mod)
+    image, camera = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
+    w = weights.w_pivot(5).cuda().requires_grad_(True)
+    p0 = coach.optimizer.arena.clone()
+    hp.LPIPS_value_threshold = 1e9
+    try:
+        lp, stepped = coach.train_step(w, camera, image)
+    finally:
+        hp.LPIPS_value_threshold = 0.05
+    assert not stepped and torch.equal(coach.optimizer.arena, p0)

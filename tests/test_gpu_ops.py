@@ -181,3 +181,41 @@ def test_filtered_lrelu_larger_and_channels_last(P):
         xg = x.cuda().contiguous(memory_format=torch.channels_last) if cl else x.cuda()
         y = P.filtered_lrelu.filtered_lrelu(xg, fu=fu.cuda(), fd=fu.cuda(), b=b.cuda(), up=2, down=2, padding=[3, 3, 3, 3], clamp=1.0)
         assert rel_l2(y, O.filtered_lrelu(x, fu=fu, fd=fu, b=b, up=2, down=2, padding=[3, 3, 3, 3], clamp=1.0)) < 1e-5
+
+
+def test_modulate_weights_vs_oracle():
+    from spi_b200.ops.modulate import modulate_weights
+    gen = torch.Generator().manual_seed(4)
+    for (n, o, i, k, demod) in ((1, 16, 8, 3, True), (4, 33, 20, 3, True), (2, 7, 64, 1, False), (3, 96, 512, 1, False)):
+        W = torch.randn(o, i, k, k, generator=gen)
+        s = torch.randn(n, i, generator=gen) + 1
+        g = torch.randn(n, o, i, k, k, generator=gen)
+        Wo, so = W.clone().requires_grad_(True), s.clone().requires_grad_(True)
+        w = Wo[None] * so.reshape(n, 1, i, 1, 1)
+        if demod:
+            w = w * (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().reshape(n, o, 1, 1, 1)
+        (w * g).sum().backward()
+        Wg, sg = W.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
+        out = modulate_weights(Wg, sg, demod)
+        assert rel_l2(out, w) < 1e-5
+        (out * g.cuda()).sum().backward()
+        assert rel_l2(Wg.grad, Wo.grad) < 1e-4 and rel_l2(sg.grad, so.grad) < 1e-4
+
+
+def test_bias_act_noise_vs_oracle(P):
+    gen = torch.Generator().manual_seed(6)
+    for cl in (False, True):
+        x = torch.randn(2, 12, 9, 9, generator=gen)
+        b, nc, st = torch.randn(12, generator=gen), torch.randn(9, 9, generator=gen), torch.tensor(0.37)
+        xo, bo, no, so = (t.clone().requires_grad_(True) for t in (x, b, nc, st))
+        yo = O.bias_act(xo + no * so, bo, act='lrelu', clamp=1.2)
+        dy = torch.randn(*yo.shape, generator=gen)
+        yo.backward(dy)
+        xg = x.cuda().contiguous(memory_format=torch.channels_last) if cl else x.cuda()
+        xg.requires_grad_(True)
+        bg, ng, sg = (t.cuda().requires_grad_(True) for t in (b, nc, st))
+        yg = P.bias_act.bias_act_noise(xg, bg, ng, sg, act='lrelu', clamp=1.2)
+        assert rel_l2(yg, yo) < 1e-6
+        yg.backward(dy.cuda())
+        for a, r in ((xg.grad, xo.grad), (bg.grad, bo.grad), (ng.grad, no.grad), (sg.grad, so.grad)):
+            assert rel_l2(a, r) < 1e-5

@@ -11,6 +11,8 @@ import bench
 
 
 def main():
+    from spi_b200.configs import global_config
+    global_config.use_cuda_graphs = '--graphs' in sys.argv
     job = bench.OursJob('cuda:0', bench.synthetic_inputs())
     for kind in ['mir'] * 3 + ['rot'] * 4:
         job.step(kind)
@@ -22,7 +24,8 @@ def main():
                 job.step(k)
             torch.cuda.synchronize()
         print('=' * 30, name)
-        ev = [e for e in prof.key_averages() if e.device_time_total > 0]
+        from torch.autograd import DeviceType
+        ev = [e for e in prof.key_averages() if e.device_type == DeviceType.CUDA and e.device_time_total > 0]
         tot = sum(e.device_time_total for e in ev)
         ev.sort(key=lambda e: -e.device_time_total)
         print(f'total device time {tot / 1e3:.2f} ms over {len(kinds)} iterations; kernels launched: {sum(e.count for e in ev)}')
