@@ -42,9 +42,16 @@ def _decoder_grads(sc, n_rows, lr_mul):
     f, hid, dpre, dout = sc
     g1 = lr_mul / (32 ** 0.5)
     g2 = lr_mul / (64 ** 0.5)
-    dw1 = (dpre[:n_rows].t() @ f[:n_rows]) * g1
+    # K = millions of samples: TF32 tensor-core GEMMs (rounding errors average out over K); bias grads ride along as a
+    # ones-column would, here as plain column sums
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        dw1 = (dpre[:n_rows].t() @ f[:n_rows]) * g1
+        dw2 = (dout[:n_rows].t() @ hid[:n_rows])[:33] * g2
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
     db1 = dpre[:n_rows].sum(0) * lr_mul
-    dw2 = (dout[:n_rows, :33].t() @ hid[:n_rows]) * g2
     db2 = dout[:n_rows, :33].sum(0) * lr_mul
     return dw1, db1, dw2, db2
 

@@ -73,8 +73,8 @@ def cal_canonical_c(yaw_angle=0, pitch_angle=0, batch_size=1, device='cpu'):
 
 def angle_to_rotation(yaw, pitch, roll=0):
     """camera_utils.py:170-193, batched on device: R = R_yaw @ R_pitch @ R_roll for [B] tensors of angles."""
-    yaw, pitch = torch.as_tensor(yaw).reshape(-1), torch.as_tensor(pitch).reshape(-1)
-    roll = torch.as_tensor(roll, dtype=yaw.dtype, device=yaw.device).expand_as(yaw)
+    yaw, pitch = yaw.reshape(-1), pitch.reshape(-1)
+    roll = torch.zeros_like(yaw) + roll if not torch.is_tensor(roll) else roll.reshape(-1).to(yaw)
     z, o = torch.zeros_like(yaw), torch.ones_like(yaw)
     cy, sy, cp, sp, cr, sr = torch.cos(yaw), torch.sin(yaw), torch.cos(pitch), torch.sin(pitch), torch.cos(roll), torch.sin(roll)
     R_roll = torch.stack([cr, -sr, z, sr, cr, z, z, z, o], -1).view(-1, 3, 3)
