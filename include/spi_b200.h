@@ -40,6 +40,11 @@ int spi_bias_act_noise(const void* x, const void* b, void* y, const float* noise
                        int size_b, int step_b, int hw, int channels_last_c, int dtype, int act, float alpha, float gain,
                        float clamp, cudaStream_t stream);
 
+/* Gradient reductions of that epilogue in one pass over dx (channels-last fp32 [pixels, C]): db[c] = sum dx (bias_act.py:166),
+ * dpix[h,w] = sum_{n,c} dx (gradient of the noise term), dstrength = sum dpix*noise.  Any output may be NULL. */
+int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,
+                             float* dstrength, cudaStream_t stream);
+
 /* upfirdn2d plugin op: eg3d/torch_utils/ops/upfirdn2d.cpp:20-105 (kernels upfirdn2d.cu:33-204).
  * f: fp32 [fh, fw]; strides in elements, order (n, c, h, w); y is [n, c, out_h, out_w] with
  * out = (in*up + pad0 + pad1 - f + down) / down (upfirdn2d.cpp:49-50). */
@@ -103,12 +108,14 @@ int spi_unify_samples(const float* depths_coarse, const float* depths_fine, int 
 
 /* ---- modulated-convolution weight preparation: replaces the elementwise chain of modulated_conv2d
  *      (eg3d/training/networks_stylegan2.py:58-68) -------------------------------------------------------- */
-/* out[n,o,i,k] = W[o,i,k]*s[n,i] (* rsqrt(sum_{i,k}(W s)^2 + 1e-8) when demodulate); dcoef [n,o] saved for backward. */
+/* out[n,o,i,k] = W[o,i,k]*s[n,i] (* rsqrt(sum_{i,k}(W s)^2 + 1e-8) when demodulate); dcoef [n,o] saved for backward.
+ * layout of out / grad_out: 0 = [n][o][i][k], 1 = [n][o][k][i] (channels-last conv weight), 2 = [n][i][k][o] (channels-last
+ * weight of the stride-2 transposed conv). */
 int spi_modulate_weights(const float* weight, const float* styles, float* out, float* dcoef, int n, int o, int i, int kk,
-                         int demodulate, cudaStream_t stream);
+                         int demodulate, int layout, cudaStream_t stream);
 int spi_modulate_weights_backward(const float* weight, const float* styles, const float* dcoef, const float* grad_out,
                                   float* grad_weight, float* grad_styles, int n, int o, int i, int kk, int demodulate,
-                                  cudaStream_t stream);
+                                  int layout, cudaStream_t stream);
 
 /* ---- depth-guided 3-D warp: replaces rotate() (spi/utils/rotate.py:92-116) --------------------------- */
 /* cameras [n, 25]; depths [n, 1, depth_res, depth_res]; image [n, 3, res, res]; mask [n, 1, res, res] or NULL;

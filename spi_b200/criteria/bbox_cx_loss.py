@@ -9,6 +9,7 @@ from torchvision.ops import roi_align
 
 from ..ops import conv as conv_engine
 from ..ops.resize import downsample2x
+from ..torch_utils.ops import bias_act
 
 
 def get_landmark_bbox(lm, scale=1):
@@ -57,11 +58,17 @@ class VGG19(torch.nn.Module):
 
     def forward(self, X):
         X = X.contiguous(memory_format=torch.channels_last)
-        for m in self.slice1:
+        mods = list(self.slice1)
+        k = 0
+        while k < len(mods):
+            m = mods[k]
             if isinstance(m, torch.nn.Conv2d):
-                X = conv_engine.conv2d(X, m.weight, padding=1) + m.bias.view(1, -1, 1, 1)
+                relu = k + 1 < len(mods) and isinstance(mods[k + 1], torch.nn.ReLU)
+                X = bias_act.bias_act(conv_engine.conv2d(X, m.weight, padding=1), m.bias, act=('relu' if relu else 'linear'), gain=1)
+                k += 2 if relu else 1
             else:
                 X = m(X)
+                k += 1
         return X
 
 

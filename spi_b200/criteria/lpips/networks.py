@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from ...ops import conv as conv_engine
+from ...torch_utils.ops import bias_act
 from .utils import normalize_activation
 
 VGG16_FEATURES = (64, 64, 'M', 128, 128, 'M', 256, 256, 256, 'M', 512, 512, 512, 'M', 512, 512, 512, 'M')
@@ -54,9 +55,13 @@ class BaseNet(nn.Module):
             raise RuntimeError('spi_b200 LPIPS: tensors must reside on a CUDA device (no CPU path in this build)')
         x = self.z_score(x).contiguous(memory_format=torch.channels_last)
         output = []
+        fused_relu = False
         for i, layer in enumerate(self.layers, 1):
-            if isinstance(layer, nn.Conv2d):
-                x = conv_engine.conv2d(x, layer.weight, padding=1) + layer.bias.view(1, -1, 1, 1)
+            if isinstance(layer, nn.Conv2d):       # conv -> (+bias, ReLU) in one epilogue pass
+                x = bias_act.bias_act(conv_engine.conv2d(x, layer.weight, padding=1), layer.bias, act='relu', gain=1)
+                fused_relu = True
+            elif isinstance(layer, nn.ReLU) and fused_relu:
+                fused_relu = False
             else:
                 x = layer(x)
             if i in self.target_layers:

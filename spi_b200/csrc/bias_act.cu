@@ -207,3 +207,82 @@ extern "C" int spi_bias_act_noise(const void* x, const void* b, void* y, const f
     return bias_act_impl(x, b, nullptr, nullptr, nullptr, y, numel, size_b, step_b, dtype, 0, act, alpha, gain, clamp, noise,
                          noise_strength, hw, channels_last_c, stream);
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Gradient reductions of the layer epilogue in ONE pass over dx (channels-last fp32, C % 4 == 0):
+//   db[c]      = sum_{n,h,w} dx[n,c,h,w]                                   (bias_act.py:166-167)
+//   pix[h,w]   = sum_{n,c} dx[n,c,h,w]  ->  dnoise = pix * strength,  dstrength = sum pix * noise   (noise branch)
+// A warp owns one pixel at a time (lanes stride over the C/4 channel groups with LDG.128); per-channel partials stay in
+// registers for the whole kernel and are combined through shared memory + one atomicAdd per channel per CTA.
+namespace {
+
+constexpr int RG_MAXG = 8;     // channel groups per lane: C <= 4*32*8 = 1024
+
+__global__ void __launch_bounds__(256) epilogue_grad_reduce_kernel(const float* __restrict__ dx, long long pixels, int C, int HW,
+                                                                   const float* __restrict__ noise, float* __restrict__ db,
+                                                                   float* __restrict__ dpix, float* __restrict__ dstrength) {
+    extern __shared__ float sm[];                 // [8 warps][C]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int groups = C / 4;
+    float4 acc[RG_MAXG];
+#pragma unroll
+    for (int g = 0; g < RG_MAXG; g++) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ds = 0.f;
+    const bool want_pix = (dpix != nullptr) || (dstrength != nullptr);
+    for (long long p = (long long)blockIdx.x * 8 + warp; p < pixels; p += (long long)gridDim.x * 8) {
+        const float4* row = (const float4*)(dx + p * C);
+        float ps = 0.f;
+#pragma unroll
+        for (int g = 0; g < RG_MAXG; g++) {
+            const int gi = lane + 32 * g;
+            if (gi < groups) {
+                float4 v = ldg_stream(row + gi);
+                acc[g].x += v.x; acc[g].y += v.y; acc[g].z += v.z; acc[g].w += v.w;
+                ps += (v.x + v.y) + (v.z + v.w);
+            }
+        }
+        if (want_pix) {
+            ps = warp_sum(ps);
+            if (lane == 0) {
+                const int hw = (int)(p % HW);
+                if (dpix) atomicAdd(dpix + hw, ps);
+                if (dstrength) ds += ps * noise[hw];
+            }
+        }
+    }
+    if (db) {
+#pragma unroll
+        for (int g = 0; g < RG_MAXG; g++) {
+            const int gi = lane + 32 * g;
+            if (gi < groups) *(float4*)(sm + warp * C + gi * 4) = acc[g];
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float t = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) t += sm[w * C + c];
+            atomicAdd(db + c, t);
+        }
+    }
+    if (dstrength && lane == 0 && ds != 0.f) atomicAdd(dstrength, ds);
+}
+
+}  // namespace
+
+extern "C" int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,
+                                        float* dstrength, cudaStream_t stream) {
+    SPI_CHECK_ARG(dx && pixels >= 0 && c >= 4 && c % 4 == 0 && c <= 4 * 32 * RG_MAXG, "epilogue_grad_reduce: C must be a multiple of 4, <= 1024");
+    SPI_CHECK_ARG(((uintptr_t)dx & 15) == 0, "epilogue_grad_reduce: dx must be 16-byte aligned");
+    SPI_CHECK_ARG(!dstrength || noise, "epilogue_grad_reduce: noise map required for dstrength");
+    if (db) cudaMemsetAsync(db, 0, sizeof(float) * c, stream);
+    if (dpix) cudaMemsetAsync(dpix, 0, sizeof(float) * hw, stream);
+    if (dstrength) cudaMemsetAsync(dstrength, 0, sizeof(float), stream);
+    if (pixels == 0) return SPI_OK;
+    long long want = (pixels + 7) / 8;
+    long long cap = (long long)spi_num_sms() * 8;
+    int grid = (int)(want < cap ? want : cap);
+    epilogue_grad_reduce_kernel<<<grid, 256, sizeof(float) * 8 * c, stream>>>(dx, pixels, c, hw > 0 ? hw : 1, noise, db, dpix, dstrength);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("epilogue_grad_reduce");
+    return SPI_OK;
+}

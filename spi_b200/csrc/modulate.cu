@@ -13,6 +13,15 @@
 
 namespace {
 
+// memory layout of the per-sample weight tensor (logical [n][o][i][k]):
+//   0: O I K (contiguous OIHW)   1: O K I (channels-last OHWI, what an NHWC conv consumes)   2: I K O (channels-last of the
+//   transposed [I,O,kh,kw] weight a conv_transpose2d consumes)
+__device__ __forceinline__ size_t widx(int layout, int n, int o, int i, int k, int O, int I, int KK) {
+    if (layout == 0) return (((size_t)n * O + o) * I + i) * KK + k;
+    if (layout == 1) return (((size_t)n * O + o) * KK + k) * I + i;
+    return (((size_t)n * I + i) * KK + k) * O + o;
+}
+
 __device__ __forceinline__ float block_sum(float v, float* sh) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -28,24 +37,23 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
 
 // grid (O, N), block 256
 __global__ void __launch_bounds__(256) modulate_fwd_kernel(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ out,
-                                                           float* __restrict__ dcoef, int O, int I, int KK, int demod) {
+                                                           float* __restrict__ dcoef, int O, int I, int KK, int demod, int layout) {
     __shared__ float sh[32];
     const int o = blockIdx.x, n = blockIdx.y;
     const int len = I * KK;
     const float* w = W + (size_t)o * len;
     const float* sn = s + (size_t)n * I;
-    float* y = out + ((size_t)n * O + o) * len;
     float acc = 0.f;
     for (int e = threadIdx.x; e < len; e += blockDim.x) {
         float v = w[e] * sn[e / KK];
-        y[e] = v;
+        out[widx(layout, n, o, e / KK, e % KK, O, I, KK)] = v;
         acc += v * v;
     }
     float d = 1.f;
     if (demod) {
         float tot = block_sum(acc, sh);
         d = rsqrtf(tot + 1e-8f);
-        for (int e = threadIdx.x; e < len; e += blockDim.x) y[e] *= d;     // same thread wrote y[e]
+        for (int e = threadIdx.x; e < len; e += blockDim.x) out[widx(layout, n, o, e / KK, e % KK, O, I, KK)] *= d;     // same thread wrote it
     }
     if (dcoef && threadIdx.x == 0) dcoef[(size_t)n * O + o] = d;
 }
@@ -53,7 +61,7 @@ __global__ void __launch_bounds__(256) modulate_fwd_kernel(const float* __restri
 // grid (O), block 256: loops over n; dW written (no atomics), ds accumulated with atomics across o
 __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restrict__ W, const float* __restrict__ s, const float* __restrict__ dcoef,
                                                            const float* __restrict__ g, float* __restrict__ dW, float* __restrict__ ds,
-                                                           int N, int O, int I, int KK, int demod) {
+                                                           int N, int O, int I, int KK, int demod, int layout) {
     __shared__ float sh[32];
     const int o = blockIdx.x;
     const int len = I * KK;
@@ -61,12 +69,11 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
     float* dw = dW ? dW + (size_t)o * len : nullptr;
     for (int n = 0; n < N; n++) {
         const float* sn = s + (size_t)n * I;
-        const float* gn = g + ((size_t)n * O + o) * len;
         float d = 1.f, A = 0.f;
         if (demod) {
             d = dcoef[(size_t)n * O + o];
             float acc = 0.f;
-            for (int e = threadIdx.x; e < len; e += blockDim.x) acc += gn[e] * w[e] * sn[e / KK];
+            for (int e = threadIdx.x; e < len; e += blockDim.x) acc += g[widx(layout, n, o, e / KK, e % KK, O, I, KK)] * w[e] * sn[e / KK];
             A = block_sum(acc, sh);
         }
         const float dA = d * d * A;
@@ -76,7 +83,8 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
             for (int k = 0; k < KK; k++) {
                 const int e = i * KK + k;
                 const float ws = w[e] * si;
-                const float t = demod ? d * (gn[e] - dA * ws) : gn[e];
+                const float ge = g[widx(layout, n, o, i, k, O, I, KK)];
+                const float t = demod ? d * (ge - dA * ws) : ge;
                 if (dw) dw[e] = (n == 0 ? 0.f : dw[e]) + si * t;
                 dsi += w[e] * t;
             }
@@ -88,10 +96,11 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
 }  // namespace
 
 extern "C" int spi_modulate_weights(const float* weight, const float* styles, float* out, float* dcoef, int n, int o, int i, int kk,
-                                    int demodulate, cudaStream_t stream) {
+                                    int demodulate, int layout, cudaStream_t stream) {
+    SPI_CHECK_ARG(layout >= 0 && layout <= 2, "modulate_weights: layout must be 0 (OIK), 1 (OKI) or 2 (IKO)");
     SPI_CHECK_ARG(weight && styles && out, "modulate_weights: null pointer");
     SPI_CHECK_ARG(n >= 1 && o >= 1 && i >= 1 && kk >= 1 && n <= 65535, "modulate_weights: bad shape");
-    modulate_fwd_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, out, dcoef, o, i, kk, demodulate);
+    modulate_fwd_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, out, dcoef, o, i, kk, demodulate, layout);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("modulate_weights");
     return SPI_OK;
@@ -99,11 +108,11 @@ extern "C" int spi_modulate_weights(const float* weight, const float* styles, fl
 
 extern "C" int spi_modulate_weights_backward(const float* weight, const float* styles, const float* dcoef, const float* grad_out,
                                              float* grad_weight, float* grad_styles, int n, int o, int i, int kk, int demodulate,
-                                             cudaStream_t stream) {
+                                             int layout, cudaStream_t stream) {
     SPI_CHECK_ARG(weight && styles && grad_out, "modulate_weights_backward: null pointer");
     SPI_CHECK_ARG(!demodulate || dcoef, "modulate_weights_backward: dcoef required when demodulating");
     if (grad_styles) cudaMemsetAsync(grad_styles, 0, sizeof(float) * (size_t)n * i, stream);
-    modulate_bwd_kernel<<<o, 256, 0, stream>>>(weight, styles, dcoef, grad_out, grad_weight, grad_styles, n, o, i, kk, demodulate);
+    modulate_bwd_kernel<<<o, 256, 0, stream>>>(weight, styles, dcoef, grad_out, grad_weight, grad_styles, n, o, i, kk, demodulate, layout);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("modulate_weights_backward");
     return SPI_OK;

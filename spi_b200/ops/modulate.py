@@ -1,22 +1,36 @@
 """Weight modulation / demodulation (the fused branch of modulated_conv2d, eg3d/training/networks_stylegan2.py:58-68) as
-one forward and one backward launch (`spi_modulate_weights*`, spi_b200/csrc/modulate.cu)."""
+one forward and one backward launch (`spi_modulate_weights*`, spi_b200/csrc/modulate.cu).
+
+The per-sample weights are produced directly in the memory layout the conv engine consumes (channels-last OHWI, or IHWO
+for the stride-2 transposed convolution), so no layout-conversion copy sits between this op and the convolution."""
 import torch
 
 from .. import _lib
 
+LAYOUTS = {'oihw': 0, 'ohwi': 1, 'ihwo': 2}
+
+
+def _alloc(n, o, i, kh, kw, layout, device):
+    """Logical [N,O,I,kh,kw] tensor whose memory order is the requested layout."""
+    if layout == 0:
+        return torch.empty(n, o, i, kh, kw, device=device)
+    if layout == 1:
+        return torch.empty(n, o, kh, kw, i, device=device).permute(0, 1, 4, 2, 3)
+    return torch.empty(n, i, kh, kw, o, device=device).permute(0, 4, 1, 2, 3)
+
 
 class _Modulate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, weight, styles, demodulate):
+    def forward(ctx, weight, styles, demodulate, layout):
         o, i, kh, kw = weight.shape
         n = styles.shape[0]
         weight, styles = weight.contiguous(), styles.contiguous()
-        out = torch.empty(n, o, i, kh, kw, device=weight.device)
+        out = _alloc(n, o, i, kh, kw, layout, weight.device)
         dcoef = torch.empty(n, o, device=weight.device) if demodulate else None
         _lib.check(_lib.load().spi_modulate_weights(_lib.ptr(weight), _lib.ptr(styles), _lib.ptr(out), _lib.ptr(dcoef), n, o, i, kh * kw,
-                                                    int(demodulate), _lib.stream()))
+                                                    int(demodulate), layout, _lib.stream()))
         ctx.save_for_backward(weight, styles, dcoef)
-        ctx.demodulate = demodulate
+        ctx.demodulate, ctx.layout = demodulate, layout
         return out
 
     @staticmethod
@@ -24,15 +38,20 @@ class _Modulate(torch.autograd.Function):
         weight, styles, dcoef = ctx.saved_tensors
         o, i, kh, kw = weight.shape
         n = styles.shape[0]
+        ref = _alloc(n, o, i, kh, kw, ctx.layout, weight.device)
+        if g.stride() != ref.stride():          # re-lay the incoming gradient only if autograd handed it over differently
+            ref.copy_(g)
+            g = ref
         gw = torch.empty_like(weight) if ctx.needs_input_grad[0] else None
         gs = torch.empty_like(styles) if ctx.needs_input_grad[1] else None
-        _lib.check(_lib.load().spi_modulate_weights_backward(_lib.ptr(weight), _lib.ptr(styles), _lib.ptr(dcoef), _lib.ptr(g.contiguous()),
-                                                             _lib.ptr(gw), _lib.ptr(gs), n, o, i, kh * kw, int(ctx.demodulate), _lib.stream()))
-        return gw, gs, None
+        _lib.check(_lib.load().spi_modulate_weights_backward(_lib.ptr(weight), _lib.ptr(styles), _lib.ptr(dcoef), _lib.ptr(g),
+                                                             _lib.ptr(gw), _lib.ptr(gs), n, o, i, kh * kw, int(ctx.demodulate), ctx.layout,
+                                                             _lib.stream()))
+        return gw, gs, None, None
 
 
-def modulate_weights(weight, styles, demodulate=True):
-    """weight [O,I,kh,kw], styles [N,I] -> per-sample weights [N,O,I,kh,kw]."""
+def modulate_weights(weight, styles, demodulate=True, layout='oihw'):
+    """weight [O,I,kh,kw], styles [N,I] -> per-sample weights, logical shape [N,O,I,kh,kw], memory order `layout`."""
     if not weight.is_cuda:
         raise RuntimeError('spi_b200.modulate_weights: tensors must reside on a CUDA device (no CPU path in this build)')
-    return _Modulate.apply(weight.float(), styles.float(), bool(demodulate))
+    return _Modulate.apply(weight.float(), styles.float(), bool(demodulate), LAYOUTS[layout])

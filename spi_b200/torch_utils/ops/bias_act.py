@@ -32,6 +32,20 @@ def _dense_like(x):
     return torch.contiguous_format
 
 
+def _fused_reductions(dx, want_db, noise=None, want_dpix=False, want_ds=False):
+    """db / per-pixel sum / dstrength from one pass over a channels-last fp32 dx; None when the fast path does not apply."""
+    if not (dx.ndim == 4 and dx.dtype == torch.float32 and dx.shape[1] % 4 == 0 and 4 <= dx.shape[1] <= 1024
+            and dx.is_contiguous(memory_format=torch.channels_last) and dx.data_ptr() % 16 == 0):
+        return None
+    n, c, h, w = dx.shape
+    db = torch.empty(c, device=dx.device) if want_db else None
+    dpix = torch.empty(h, w, device=dx.device) if want_dpix else None
+    ds = torch.empty((), device=dx.device) if want_ds else None
+    _lib.check(_lib.load().spi_epilogue_grad_reduce(_lib.ptr(dx), n * h * w, c, h * w, _lib.ptr(noise) if noise is not None else None,
+                                                    _lib.ptr(db), _lib.ptr(dpix), ds.data_ptr() if ds is not None else None, _lib.stream()))
+    return db, dpix, ds
+
+
 def _plugin_bias_act(x, b, xref, yref, dy, grad, dim, act_idx, alpha, gain, clamp):
     """The plugin entry point `bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)` (bias_act.cpp:36)."""
     if not x.is_cuda:
@@ -112,7 +126,8 @@ class _BiasAct(torch.autograd.Function):
             if spec.cuda_idx != 1 or gain != 1 or clamp >= 0:
                 dx = _BiasActGrad.apply(dy, x, b, y, ctx.cfg)
         if ctx.needs_input_grad[1]:
-            db = dx.sum([i for i in range(dx.ndim) if i != dim])
+            red = _fused_reductions(dx, True) if dim == 1 else None
+            db = red[0] if red is not None else dx.sum([i for i in range(dx.ndim) if i != dim])
         return dx, db, None
 
 
@@ -155,13 +170,20 @@ class _BiasActNoise(torch.autograd.Function):
         dy = dy.contiguous(memory_format=ctx.fmt)
         dx = _BiasActGrad.apply(dy, None, b, y, ctx.cfg)
         db = dn = ds = None
-        if ctx.needs_input_grad[1]:
-            db = dx.sum([0, 2, 3])
-        if ctx.needs_input_grad[2] or ctx.needs_input_grad[3]:
-            pix = dx.sum([0, 1])                      # [H, W]: d/d(noise term)
-            if ctx.needs_input_grad[2]:
+        need_b, need_n, need_s = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
+        red = _fused_reductions(dx, need_b, noise=nc, want_dpix=need_n, want_ds=need_s) if (need_b or need_n or need_s) else None
+        if red is not None:
+            db, pix, ds = red
+            if need_n:
                 dn = pix * strength
-            if ctx.needs_input_grad[3]:
+            return dx, db, dn, ds, None
+        if need_b:
+            db = dx.sum([0, 2, 3])
+        if need_n or need_s:
+            pix = dx.sum([0, 1])                      # [H, W]: d/d(noise term)
+            if need_n:
+                dn = pix * strength
+            if need_s:
                 ds = (pix * nc).sum()
         return dx, db, dn, ds, None
 

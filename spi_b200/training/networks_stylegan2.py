@@ -54,7 +54,7 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     misc.assert_shape(styles, [batch_size, in_channels])
     if fused_modconv and x.dtype == torch.float32:
         # one launch: w[n,o,i,k] = W*s (*rsqrt(sum (W s)^2 + 1e-8))  (spi_modulate_weights)
-        w = modulate_weights(weight, styles, demodulate)
+        w = modulate_weights(weight, styles, demodulate, layout=('ihwo' if up > 1 else 'ohwi'))
         assert down == 1
         x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
         if noise is not None:

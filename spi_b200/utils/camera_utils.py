@@ -11,6 +11,18 @@ import torch
 from . import rng
 
 
+_consts = {}
+
+
+def _const(values, device):
+    """Small constant tensors are uploaded once per device and reused: a host->device copy of pageable memory is not
+    allowed while a CUDA graph is being captured."""
+    key = (str(values), str(device))
+    if key not in _consts:
+        _consts[key] = torch.tensor(values, dtype=torch.float32, device=device)
+    return _consts[key]
+
+
 def normalize_vecs(v):
     return v / torch.norm(v, dim=-1, keepdim=True)
 
@@ -18,7 +30,7 @@ def normalize_vecs(v):
 def create_cam2world_matrix(forward_vector, origin):
     """camera_utils.py:123-143."""
     forward_vector = normalize_vecs(forward_vector)
-    up = torch.tensor([0, 1, 0], dtype=torch.float, device=origin.device).expand_as(forward_vector)
+    up = _const([0, 1, 0], origin.device).expand_as(forward_vector)
     right = -normalize_vecs(torch.cross(up, forward_vector, dim=-1))
     up = normalize_vecs(torch.cross(forward_vector, right, dim=-1))
     n = forward_vector.shape[0]
@@ -51,12 +63,12 @@ class LookAtPoseSampler:
 
 
 def _intrinsics(batch_size, device):
-    return torch.tensor([[4.2647, 0, 0.5], [0, 4.2647, 0.5], [0, 0, 1]], device=device).view(1, 9).repeat(batch_size, 1)
+    return _const([[4.2647, 0, 0.5], [0, 4.2647, 0.5], [0, 0, 1]], device).view(1, 9).repeat(batch_size, 1)
 
 
 def sample_camera(batch_size=1, yaw_range=0.35, pitch_range=0.25, device='cpu'):
     """camera_utils.py:159-167."""
-    lookat = torch.tensor([0, 0, 0.2], device=device)
+    lookat = _const([0, 0, 0.2], device)
     ext = LookAtPoseSampler.sample(horizontal_mean=math.pi / 2, vertical_mean=math.pi / 2 - 0.2, lookat_position=lookat,
                                    horizontal_stddev=yaw_range, vertical_stddev=pitch_range, radius=2.7, batch_size=batch_size,
                                    device=device, sample_mode='uniform')
@@ -65,7 +77,7 @@ def sample_camera(batch_size=1, yaw_range=0.35, pitch_range=0.25, device='cpu'):
 
 def cal_canonical_c(yaw_angle=0, pitch_angle=0, batch_size=1, device='cpu'):
     """camera_utils.py:233-240."""
-    lookat = torch.tensor([0, 0, 0.2], device=device)
+    lookat = _const([0, 0, 0.2], device)
     ext = LookAtPoseSampler.sample(math.pi / 2 + yaw_angle, math.pi / 2 - 0.2 + pitch_angle, lookat, radius=2.7,
                                    batch_size=batch_size, device=device)
     return torch.cat([ext.view(-1, 16), _intrinsics(batch_size, device)], dim=1)

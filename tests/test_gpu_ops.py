@@ -196,7 +196,7 @@ def test_modulate_weights_vs_oracle():
             w = w * (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().reshape(n, o, 1, 1, 1)
         (w * g).sum().backward()
         Wg, sg = W.cuda().requires_grad_(True), s.cuda().requires_grad_(True)
-        out = modulate_weights(Wg, sg, demod)
+        out = modulate_weights(Wg, sg, demod, layout=["oihw","ohwi","ihwo"][(n + o) % 3])
         assert rel_l2(out, w) < 1e-5
         (out * g.cuda()).sum().backward()
         assert rel_l2(Wg.grad, Wo.grad) < 1e-4 and rel_l2(sg.grad, so.grad) < 1e-4
