@@ -35,27 +35,35 @@ __device__ __forceinline__ float block_sum(float v, float* sh) {
     return sh[0];
 }
 
-// grid (O, N), block 256
-__global__ void __launch_bounds__(256) modulate_fwd_kernel(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ out,
-                                                           float* __restrict__ dcoef, int O, int I, int KK, int demod, int layout) {
+// grid (O, N), block 256: demodulation coefficients d[n,o] = rsqrt(sum_{i,k} (W s)^2 + 1e-8)
+__global__ void __launch_bounds__(256) demod_coef_kernel(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ dcoef,
+                                                         int O, int I, int KK) {
     __shared__ float sh[32];
     const int o = blockIdx.x, n = blockIdx.y;
     const int len = I * KK;
     const float* w = W + (size_t)o * len;
     const float* sn = s + (size_t)n * I;
     float acc = 0.f;
-    for (int e = threadIdx.x; e < len; e += blockDim.x) {
-        float v = w[e] * sn[e / KK];
-        out[widx(layout, n, o, e / KK, e % KK, O, I, KK)] = v;
-        acc += v * v;
+    for (int e = threadIdx.x; e < len; e += blockDim.x) { float v = w[e] * sn[e / KK]; acc += v * v; }
+    float tot = block_sum(acc, sh);
+    if (threadIdx.x == 0) dcoef[(size_t)n * O + o] = rsqrtf(tot + 1e-8f);
+}
+
+// elementwise in OUTPUT memory order (coalesced stores for every layout): out = W * s * d
+__global__ void __launch_bounds__(256) modulate_apply_kernel(const float* __restrict__ W, const float* __restrict__ s,
+                                                             const float* __restrict__ dcoef, float* __restrict__ out, int N, int O,
+                                                             int I, int KK, int layout) {
+    const long long total = (long long)N * O * I * KK;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
+        int n, o, i, k;
+        long long r = q;
+        if (layout == 0) { k = (int)(r % KK); r /= KK; i = (int)(r % I); r /= I; o = (int)(r % O); n = (int)(r / O); }
+        else if (layout == 1) { i = (int)(r % I); r /= I; k = (int)(r % KK); r /= KK; o = (int)(r % O); n = (int)(r / O); }
+        else { o = (int)(r % O); r /= O; k = (int)(r % KK); r /= KK; i = (int)(r % I); n = (int)(r / I); }
+        float v = W[((size_t)o * I + i) * KK + k] * s[(size_t)n * I + i];
+        if (dcoef) v *= dcoef[(size_t)n * O + o];
+        out[q] = v;
     }
-    float d = 1.f;
-    if (demod) {
-        float tot = block_sum(acc, sh);
-        d = rsqrtf(tot + 1e-8f);
-        for (int e = threadIdx.x; e < len; e += blockDim.x) out[widx(layout, n, o, e / KK, e % KK, O, I, KK)] *= d;     // same thread wrote it
-    }
-    if (dcoef && threadIdx.x == 0) dcoef[(size_t)n * O + o] = d;
 }
 
 // grid (O), block 256: loops over n; dW written (no atomics), ds accumulated with atomics across o
@@ -73,7 +81,10 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
         if (demod) {
             d = dcoef[(size_t)n * O + o];
             float acc = 0.f;
-            for (int e = threadIdx.x; e < len; e += blockDim.x) acc += g[widx(layout, n, o, e / KK, e % KK, O, I, KK)] * w[e] * sn[e / KK];
+            for (int q = threadIdx.x; q < len; q += blockDim.x) {      // q walks g's memory order for layouts 0 and 1
+                const int i = (layout == 1) ? q % I : q / KK, k = (layout == 1) ? q / I : q % KK;
+                acc += g[widx(layout, n, o, i, k, O, I, KK)] * w[i * KK + k] * sn[i];
+            }
             A = block_sum(acc, sh);
         }
         const float dA = d * d * A;
@@ -100,8 +111,12 @@ extern "C" int spi_modulate_weights(const float* weight, const float* styles, fl
     SPI_CHECK_ARG(layout >= 0 && layout <= 2, "modulate_weights: layout must be 0 (OIK), 1 (OKI) or 2 (IKO)");
     SPI_CHECK_ARG(weight && styles && out, "modulate_weights: null pointer");
     SPI_CHECK_ARG(n >= 1 && o >= 1 && i >= 1 && kk >= 1 && n <= 65535, "modulate_weights: bad shape");
-    modulate_fwd_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, out, dcoef, o, i, kk, demodulate, layout);
-    SPI_COUNT_LAUNCH(1);
+    SPI_CHECK_ARG(!demodulate || dcoef, "modulate_weights: dcoef buffer required when demodulating");
+    if (demodulate) demod_coef_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, dcoef, o, i, kk);
+    long long total = (long long)n * o * i * kk;
+    long long blocks = (total + 255) / 256, cap = (long long)spi_num_sms() * 8;
+    modulate_apply_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, stream>>>(weight, styles, demodulate ? dcoef : nullptr, out, n, o, i, kk, layout);
+    SPI_COUNT_LAUNCH(demodulate ? 2 : 1);
     SPI_LAUNCH_CHECK("modulate_weights");
     return SPI_OK;
 }

@@ -2,9 +2,10 @@
 SURVEY.md §8d).  Call-site contract = `_conv2d_wrapper` (eg3d/torch_utils/ops/conv2d_resample.py:30-43):
 `flip_weight=True` is correlation (what `F.conv2d` computes), `False` flips the taps first.
 
-Round-1 engine: cuDNN through `torch.nn.functional.conv2d/conv_transpose2d` in channels-last layout with TF32
-tensor-core math (library call, counted as baseline -- DESIGN.md "Conv engine").  Grouped-by-batch modulated
-convolutions are executed sample by sample, each a dense GEMM-shaped problem.
+Round-1 engine: cuDNN's sm_100 TF32 tensor-core implicit-GEMM kernels through ATen, channels-last activations and
+weights (library call, counted as baseline -- DESIGN.md "Conv engine").  Modulated convolutions carry one weight set per
+sample (`conv2d_per_sample`): each sample is its own dense problem, executed inside ONE autograd node so that no
+slice / cat / zero-fill traffic is generated around the per-sample calls.
 """
 import torch
 import torch.nn.functional as F
@@ -12,25 +13,73 @@ import torch.nn.functional as F
 ALLOW_TF32 = True
 
 
-def conv2d(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True):
+def _check(x):
     if not x.is_cuda:
         raise RuntimeError('spi_b200 conv engine: x must reside on a CUDA device (no CPU path in this build)')
+
+
+def conv2d(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True):
+    """Shared-weight convolution (VGG layers, generic conv2d_resample callers)."""
+    _check(x)
     if not flip_weight and (w.shape[-1] > 1 or w.shape[-2] > 1):
         w = w.flip([2, 3])
     torch.backends.cudnn.allow_tf32 = ALLOW_TF32
     op = F.conv_transpose2d if transpose else F.conv2d
-    if groups == 1:
-        return op(x.contiguous(memory_format=torch.channels_last), w.contiguous(memory_format=torch.channels_last),
-                  stride=stride, padding=padding)
-    # groups = batch of per-sample weights: run each sample as its own dense problem
-    xs = x.reshape(groups, -1, *x.shape[2:])            # [G, Cin, H, W] (x is [1, G*Cin, H, W])
-    if transpose:
-        ws = w.reshape(groups, w.shape[0] // groups, *w.shape[1:])      # [G, Cin, Cout, kh, kw]
-    else:
-        ws = w.reshape(groups, w.shape[0] // groups, *w.shape[1:])      # [G, Cout, Cin, kh, kw]
-    outs = []
-    for g in range(groups):
-        xg = xs[g:g + 1].contiguous(memory_format=torch.channels_last)
-        outs.append(op(xg, ws[g].contiguous(memory_format=torch.channels_last), stride=stride, padding=padding))
-    y = torch.cat(outs, 0)                               # [G, Cout, H', W']
-    return y.reshape(1, -1, *y.shape[2:])
+    return op(x.contiguous(memory_format=torch.channels_last), w.contiguous(memory_format=torch.channels_last),
+              stride=stride, padding=padding, groups=groups)
+
+
+def _pair(v):
+    return [v, v] if isinstance(v, int) else [int(v[0]), int(v[1])]
+
+
+class _PerSampleConv(torch.autograd.Function):
+    """y[n] = conv(x[n], w[n]) (or conv_transpose) for n in range(N); x [N,C,H,W] channels-last, w [N,O,I,kh,kw] logical."""
+
+    @staticmethod
+    def forward(ctx, x, w, stride, padding, transpose):
+        torch.backends.cudnn.allow_tf32 = ALLOW_TF32
+        n = x.shape[0]
+        x = x.contiguous(memory_format=torch.channels_last)
+        ys = []
+        for k in range(n):
+            wk = w[k].transpose(0, 1) if transpose else w[k]
+            wk = wk.contiguous(memory_format=torch.channels_last)
+            ys.append(torch.ops.aten.convolution(x[k:k + 1], wk, None, _pair(stride), _pair(padding), [1, 1], transpose, [0, 0], 1))
+        y = ys[0] if n == 1 else torch.cat(ys, 0)
+        ctx.save_for_backward(x, w)
+        ctx.cfg = (stride, padding, transpose)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        stride, padding, transpose = ctx.cfg
+        torch.backends.cudnn.allow_tf32 = ALLOW_TF32
+        n = x.shape[0]
+        need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gy = gy.contiguous(memory_format=torch.channels_last)
+        gx = torch.empty_like(x) if (need_x and n > 1) else None
+        gw = torch.empty_like(w) if need_w else None          # preserves w's (conv-native) strides
+        for k in range(n):
+            wk = w[k].transpose(0, 1) if transpose else w[k]
+            wk = wk.contiguous(memory_format=torch.channels_last)
+            gxk, gwk, _ = torch.ops.aten.convolution_backward(gy[k:k + 1], x[k:k + 1], wk, None, _pair(stride), _pair(padding), [1, 1],
+                                                              transpose, [0, 0], 1, [need_x, need_w, False])
+            if need_x:
+                if n == 1:
+                    gx = gxk
+                else:
+                    gx[k:k + 1].copy_(gxk)
+            if need_w:
+                gw[k].copy_(gwk.transpose(0, 1) if transpose else gwk)
+        return gx, gw, None, None, None
+
+
+def conv2d_per_sample(x, w, stride=1, padding=0, transpose=False, flip_weight=True):
+    """x [N,Cin,H,W], w [N,Cout,Cin,kh,kw] (per-sample weights, any strides) -> [N,Cout,H',W'].
+    For `transpose=True` the per-sample weight is used as conv_transpose2d's [Cin,Cout,kh,kw] (= w[n].transpose(0,1))."""
+    _check(x)
+    if not flip_weight and (w.shape[-1] > 1 or w.shape[-2] > 1):
+        w = w.flip([3, 4])
+    return _PerSampleConv.apply(x, w, stride, padding, transpose)

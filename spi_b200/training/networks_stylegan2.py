@@ -27,20 +27,16 @@ def normalize_2nd_moment(x, dim=1, eps=1e-8):
 def _batched_resample_conv(x, w, f, up, padding, flip_weight):
     """conv2d_resample (conv2d_resample.py:48-143) for per-sample weights w [N, O, I, kh, kw]: the two branches a
     generator layer takes (up = 1: plain conv; up = 2: stride-2 transposed conv then 4x4 FIR with gain 4)."""
-    n = x.shape[0]
     o, i, kh, kw = w.shape[1:]
     if up == 1:
-        ys = [conv_engine.conv2d(x[k:k + 1], w[k], padding=[padding, padding], flip_weight=flip_weight) for k in range(n)]
-        return torch.cat(ys, 0) if n > 1 else ys[0]
+        return conv_engine.conv2d_per_sample(x, w, padding=[padding, padding], flip_weight=flip_weight)
     fw, fh = upfirdn2d._get_filter_size(f)
     px0 = padding + (fw + up - 1) // 2 - (kw - 1)
     px1 = padding + (fw - up) // 2 - (kw - up)
     py0 = padding + (fh + up - 1) // 2 - (kh - 1)
     py1 = padding + (fh - up) // 2 - (kh - up)
     pxt, pyt = max(min(-px0, -px1), 0), max(min(-py0, -py1), 0)
-    ys = [conv_engine.conv2d(x[k:k + 1], w[k].transpose(0, 1), stride=up, padding=[pyt, pxt], transpose=True,
-                             flip_weight=(not flip_weight)) for k in range(n)]
-    y = torch.cat(ys, 0) if n > 1 else ys[0]
+    y = conv_engine.conv2d_per_sample(x, w, stride=up, padding=[pyt, pxt], transpose=True, flip_weight=(not flip_weight))
     return upfirdn2d.upfirdn2d(x=y, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2)
 
 
@@ -54,7 +50,7 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     misc.assert_shape(styles, [batch_size, in_channels])
     if fused_modconv and x.dtype == torch.float32:
         # one launch: w[n,o,i,k] = W*s (*rsqrt(sum (W s)^2 + 1e-8))  (spi_modulate_weights)
-        w = modulate_weights(weight, styles, demodulate, layout=('ihwo' if up > 1 else 'ohwi'))
+        w = modulate_weights(weight, styles, demodulate, layout='ohwi')
         assert down == 1
         x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
         if noise is not None:
