@@ -1,7 +1,7 @@
 """LPIPS v0.1 on VGG16 (drop-in for spi/criteria/lpips/lpips.py:10-71).
 
 Differences in execution only: the 512->256 bilinear resize is the exact 2x2 mean (`spi_downsample2x`), and when `y`
-is a constant target (same tensor, no grad, unchanged version counter) its five feature taps are cached instead of
+has been registered as a constant target (`register_target`) its five feature taps are cached instead of
 re-running VGG16 on it every call (the reference recomputes them: +40 GF per call).
 """
 import torch
@@ -42,19 +42,25 @@ class LPIPS(nn.Module):
             return downsample2x(t)
         return F.interpolate(t, size=(256, 256), mode='bilinear', align_corners=False)
 
+    def register_target(self, y):
+        """Declare `y` a constant target (the image being inverted): its five feature taps are computed once and reused by
+        every later forward(x, y) with this very tensor object.  Unregistered `y` (e.g. warped images) are never cached."""
+        self._cache[id(y)] = (y, None, None, None)
+        return y
+
     def _target_feats(self, y, resize):
-        """Feature taps of `y`; cached while `y` is the same constant tensor object (identity + version counter)."""
         if y.requires_grad:
             return self.net(self._resize(y) if resize else y)
         hit = self._cache.get(id(y))
-        if hit is not None and hit[0] is y and hit[1] == y._version and hit[2] == resize:
-            return hit[3]
-        with torch.no_grad():
-            feats = self.net(self._resize(y) if resize else y)
-        if len(self._cache) >= 4:
-            self._cache.pop(next(iter(self._cache)))
-        self._cache[id(y)] = (y, y._version, resize, feats)
-        return feats
+        if hit is None or hit[0] is not y:
+            with torch.no_grad():
+                return self.net(self._resize(y) if resize else y)
+        if hit[3] is None or hit[1] != y._version or hit[2] != resize:
+            with torch.no_grad():
+                feats = self.net(self._resize(y) if resize else y)
+            self._cache[id(y)] = (y, y._version, resize, feats)
+            return feats
+        return hit[3]
 
     def forward(self, x, y, conf_sigma=None, mask=None):
         assert conf_sigma is None and mask is None, 'conf_sigma / mask variants are not used by SPI and not built'

@@ -44,6 +44,9 @@ class SingleIDCoach(BaseCoach):
         if not hasattr(self, '_lpips_out') or self._lpips_out.device != w_pivot.device:
             self._lpips_out = torch.zeros((), device=w_pivot.device)
             self._graphs = {}
+        if hasattr(self.lpips_loss, 'register_target') and getattr(self, '_registered', None) is not image:
+            self.lpips_loss.register_target(image)
+            self._registered = image
         if self.optimizer.hyper is None:
             self.optimizer.use_device_hyper()
         self.optimizer._reseat()

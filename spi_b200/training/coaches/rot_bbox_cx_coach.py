@@ -100,6 +100,9 @@ class RotBboxCoach(BaseCoach):
         if not hasattr(self, '_lpips_out') or self._lpips_out.device != w_pivot.device:
             self._lpips_out = torch.zeros((), device=w_pivot.device)
             self._graphs = {}
+        if hasattr(self.lpips_loss, 'register_target') and getattr(self, '_registered', None) is not st.image:
+            self.lpips_loss.register_target(st.image)          # the inverted image is constant: cache its LPIPS taps
+            self._registered = st.image
         if self.optimizer.hyper is None:
             self.optimizer.use_device_hyper()
         self.optimizer._reseat()

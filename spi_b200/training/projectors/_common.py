@@ -76,8 +76,12 @@ class LatentProjector:
         self._out = dict(loss=torch.zeros((), device=device), dist=torch.zeros((), device=device), image=None)
         self.target, self.c = target, c
         self.lpips_func, self.vgg16 = lpips_func, vgg16
+        if lpips_func is not None and hasattr(lpips_func, 'register_target'):
+            lpips_func.register_target(target)
         if kind == 'mir':
             self.target_m = torch.flip(target, dims=[3])
+            if hasattr(lpips_func, 'register_target'):
+                lpips_func.register_target(self.target_m)
             camera_m = cal_mirror_c(camera=c)
             self.target_camera = torch.cat([c, camera_m], dim=0)
             self.weight_m = cal_camera_weight(camera_m)[0]
