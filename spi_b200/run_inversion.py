@@ -64,7 +64,8 @@ def shard_for_rank(args):
     if world > 1 and args.dataset_block is None:
         args.dataset_block = f"{int(os.environ['RANK']) + 1}/{world}"
         global_config.device = f"cuda:{int(os.environ.get('LOCAL_RANK', '0'))}"
-        torch.cuda.set_device(global_config.device)
+        if torch.cuda.is_available():
+            torch.cuda.set_device(global_config.device)
     return args
 
 
