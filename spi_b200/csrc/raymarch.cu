@@ -27,6 +27,8 @@
 // Compositing is linear in the colours, so recomputing sigma costs +25% decoder FLOPs and zero HBM bytes.
 // The backward kernel re-derives everything from depths_all and scatters plane gradients with red.global.add.v4.f32.
 #include "common.cuh"
+#include "raymarch_mma.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -850,6 +852,391 @@ __global__ void __launch_bounds__(128) unify_kernel(const float* dcs, const floa
     }
 }
 
+// ================================================================= tensor-core (mma.sync 3xTF32) renderer, v2
+// Same algorithm as render_fwd_kernel / render_bwd_kernel; differences:
+//   * the decoder runs on tensor cores per 32-sample tile (raymarch_mma.cuh);
+//   * gathered features are cached in a per-warp shared tile, so every sample is gathered ONCE per kernel
+//     (forward: pass 2b re-reads pass 1 / 2a features; backward: B3 re-reads B1 features);
+//   * pass 2b walks samples in storage order (coarse, then fine) and looks its colour coefficient up by merged rank --
+//     compositing is a sum, so the order is free and the A-fragment loads stay conflict-free.
+__device__ __forceinline__ int rup32(int v) { return (v + 31) & ~31; }
+
+__device__ __forceinline__ size_t fwd2_warp_floats(int dc, int df) {
+    const int D = dc + df;
+    return (size_t)dc /*dcs*/ + rup32(dc) /*sigc*/ + rup32(df) /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall,sigm,w*/ +
+           dc + df /*pos*/ + (size_t)(rup32(dc) + rup32(df)) * mma::FS;
+}
+
+__device__ __forceinline__ void gather_to_tile(const float* __restrict__ pl, int W, int H, const Ray& r, float d, float scale, float* row) {
+    float f[NF];
+    gather_features(pl, W, H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, f);
+#pragma unroll
+    for (int v = 0; v < NF / 4; v++) *(float4*)(row + 4 * v) = make_float4(f[4 * v], f[4 * v + 1], f[4 * v + 2], f[4 * v + 3]);
+}
+
+__global__ void __launch_bounds__(WARPS * 32) render_fwd_mma_kernel(RenderParams p) {
+    extern __shared__ __align__(16) float smem[];
+    mma::DecM* dec = (mma::DecM*)smem;
+    float* wbase = smem + (sizeof(mma::DecM) + 15) / 16 * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dc = p.dc, df = p.df, D = dc + df, dc32 = rup32(dc), df32 = rup32(df);
+    float* b = wbase + warp * ((fwd2_warp_floats(dc, df) + 3) & ~(size_t)3);
+    float* F = b; b += (size_t)(dc32 + df32) * mma::FS;           // 16-byte aligned rows first
+    float* dcs = b; b += dc;
+    float* sigc = b; b += dc32;
+    float* sigf = b; b += df32;
+    float* fine = b; b += df;
+    float* cdf = b; b += dc;
+    float* dall = b; b += D;
+    float* sigm = b; b += D;
+    float* w = b; b += D;
+    int* pos_c = (int*)b; b += dc;
+    int* pos_f = (int*)b;
+    mma::load_dec(dec, p.w1, p.b1, p.w2, p.b2, p.w1_gain, p.w2_gain, p.b_gain);
+    __syncthreads();
+    const int R = p.R;
+    const long long total = (long long)p.n * R;
+    const float scale = 2.f / p.box_warp;
+    const int g = lane >> 2, t = lane & 3;
+    int lmin = 0x7f800000, lmax = 0;
+    for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
+        const int n = (int)(ray / R);
+        const float* pl = p.planes + (size_t)n * p.H * p.W * 96;
+        Ray r;
+        r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
+        r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
+        // ---- pass 1: coarse samples (gather once, sigma on tensor cores)
+        for (int rb = 0; rb < dc32; rb += 32) {
+            const int i = rb + lane;
+            if (i < dc) {
+                float d = coarse_depth(p, i, p.jitter[ray * dc + i]);
+                dcs[i] = d;
+                gather_to_tile(pl, p.W, p.H, r, d, scale, F + (size_t)i * mma::FS);
+            }
+            __syncwarp();
+            mma::tile_sigma(dec, F + (size_t)rb * mma::FS, sigc + rb, lane);
+        }
+        __syncwarp();
+        float depth, wsum;
+        if (df > 0) {
+            warp_weights(dcs, sigc, dc, w, lane);
+            warp_importance(dcs, w, dc, p.u + ray * df, df, cdf, fine, nullptr, lane);
+            warp_merge_ranks(dcs, dc, fine, df, pos_c, pos_f, lane);
+            // ---- pass 2a: fine samples
+            for (int rb = 0; rb < df32; rb += 32) {
+                const int j = rb + lane;
+                if (j < df) gather_to_tile(pl, p.W, p.H, r, fine[j], scale, F + (size_t)(dc32 + j) * mma::FS);
+                __syncwarp();
+                mma::tile_sigma(dec, F + (size_t)(dc32 + rb) * mma::FS, sigf + rb, lane);
+            }
+            __syncwarp();
+            for (int i = lane; i < dc; i += 32) { sigm[pos_c[i]] = sigc[i]; dall[pos_c[i]] = dcs[i]; }
+            for (int j = lane; j < df; j += 32) { sigm[pos_f[j]] = sigf[j]; dall[pos_f[j]] = fine[j]; }
+        } else {
+            for (int i = lane; i < dc; i += 32) { sigm[i] = sigc[i]; dall[i] = dcs[i]; pos_c[i] = i; }
+        }
+        __syncwarp();
+        warp_weights(dall, sigm, D, w, lane);
+        warp_finalize(dall, w, D, depth, wsum, lane);          // w[] now holds the colour coefficients a_q
+        // ---- pass 2b: colours, storage order, features from the shared tile
+        float racc[5][2];
+#pragma unroll
+        for (int nn = 0; nn < 5; nn++) { racc[nn][0] = 0.f; racc[nn][1] = 0.f; }
+        for (int rb = 0; rb < dc32 + df32; rb += 32) {
+            float hid[2][8][4];
+            mma::fc1(dec, F + (size_t)rb * mma::FS, hid, lane);
+            mma::softplus_inplace(hid);
+            float out[2][5][4];
+            mma::fc2<5>(dec, hid, out, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int sr = rb + 16 * mt + g + 8 * hh;
+                    const bool coarse = sr < dc32;
+                    const bool valid = coarse ? (sr < dc) : (sr - dc32 < df);
+                    float a = 0.f;
+                    if (valid) a = w[coarse ? pos_c[sr] : pos_f[sr - dc32]];
+#pragma unroll
+                    for (int nn = 0; nn < 5; nn++)
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const int o = 8 * nn + 2 * t + jj;
+                            if (valid && o >= 1 && o <= 32) racc[nn][jj] = fmaf(a, rgb_act(out[mt][nn][2 * hh + jj]), racc[nn][jj]);
+                        }
+                }
+        }
+#pragma unroll
+        for (int nn = 0; nn < 5; nn++)
+#pragma unroll
+            for (int jj = 0; jj < 2; jj++) {
+                float v = racc[nn][jj];
+                v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
+                const int o = 8 * nn + 2 * t + jj;
+                if (g == 0 && o >= 1 && o <= 32) p.feat[ray * NF + o - 1] = v * 2.f - 1.f;
+            }
+        for (int i = lane; i < D; i += 32) {
+            const float d = dall[i];
+            lmin = min(lmin, float_as_ordered(d)); lmax = max(lmax, float_as_ordered(d));
+            if (p.depths_all) p.depths_all[ray * D + i] = d;
+            if (p.sigma_all) p.sigma_all[ray * D + i] = sigm[i];
+        }
+        if (lane == 0) { p.depth[ray] = depth; p.wsum[ray] = wsum; }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o)); lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o)); }
+    if (lane == 0 && lmax != 0) { atomicMin(p.minmax, lmin); atomicMax(p.minmax + 1, lmax); }
+}
+
+// scatter of a 32-row feature-gradient tile (row stride mma::FS); lane = row; `valid` rows only
+__device__ __forceinline__ void warp_scatter_tile(float* __restrict__ gp, const float* dft, int* s_off, float* s_w, int W, int H, float x,
+                                                  float y, float z, float scale, bool valid, int lane) {
+    float gc[3][2];
+    plane_coords(x, y, z, scale, gc);
+#pragma unroll
+    for (int pp = 0; pp < 3; pp++) {
+        Corner c;
+        corners(gc[pp][0], gc[pp][1], W, H, c);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            s_off[lane * 12 + pp * 4 + q] = (valid && c.off[q] >= 0) ? c.off[q] + pp * NF : -1;
+            s_w[lane * 12 + pp * 4 + q] = c.w[q] * (1.f / 3.f);
+        }
+    }
+    __syncwarp();
+    const int sub = lane & 7;
+    for (int tt = lane >> 3; tt < 32 * 12; tt += 4) {
+        const int off = s_off[tt];
+        if (off < 0) continue;
+        const float ww = s_w[tt];
+        const float4 v = *(const float4*)(dft + (tt / 12) * mma::FS + sub * 4);
+        red_add_v4(gp + off + sub * 4, make_float4(v.x * ww, v.y * ww, v.z * ww, v.w * ww));
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ size_t bwd2_warp_floats(int D) { return (size_t)rup32(D) * mma::FS + 32 * mma::FS + 7 * (size_t)rup32(D) + 32 + 2 * 32 * 12; }
+
+__global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams p) {
+    extern __shared__ __align__(16) float smem[];
+    mma::DecM* dec = (mma::DecM*)smem;
+    mma::DecMBwd* decb = (mma::DecMBwd*)(smem + (sizeof(mma::DecM) + 15) / 16 * 4);
+    float* wbase = (float*)decb + (sizeof(mma::DecMBwd) + 15) / 16 * 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int D = p.dc + p.df, D32 = rup32(D);
+    float* b = wbase + warp * ((bwd2_warp_floats(D) + 3) & ~(size_t)3);
+    float* F = b; b += (size_t)D32 * mma::FS;
+    float* DFt = b; b += 32 * mma::FS;
+    float* dall = b; b += D32; float* sig = b; b += D32; float* w = b; b += D32; float* pdot = b; b += D32;
+    float* alpha = b; b += D32; float* Tarr = b; b += D32; float* gmid = b; b += D32; float* gfe = b; b += 32;
+    int* s_off = (int*)b; b += 32 * 12; float* s_w = b;
+    mma::load_dec(dec, p.w1, p.b1, p.w2, p.b2, p.w1_gain, p.w2_gain, p.b_gain);
+    mma::load_dec_bwd(decb, p.w2, p.w2_gain);
+    __syncthreads();
+    const int R = p.R;
+    const long long total = (long long)p.n * R;
+    const float scale = 2.f / p.box_warp;
+    const float lo = __int_as_float(p.minmax[0]), hi = __int_as_float(p.minmax[1]);
+    const int g = lane >> 2, t = lane & 3;
+    for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
+        const int n = (int)(ray / R);
+        const float* pl = p.planes + (size_t)n * p.H * p.W * 96;
+        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.H * p.W * 96 : nullptr;
+        Ray r;
+        r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
+        r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
+        gfe[lane] = p.g_feat[ray * NF + lane] * 2.f;
+        for (int i = lane; i < D; i += 32) dall[i] = p.depths_all[ray * D + i];
+        __syncwarp();
+        // ---- B1: gather once; sigma_i and p_i = <g_rgb, rgb_i>
+        for (int rb = 0; rb < D32; rb += 32) {
+            const int i = rb + lane;
+            if (i < D) gather_to_tile(pl, p.W, p.H, r, dall[i], scale, F + (size_t)i * mma::FS);
+            __syncwarp();
+            float hid[2][8][4];
+            mma::fc1(dec, F + (size_t)rb * mma::FS, hid, lane);
+            mma::softplus_inplace(hid);
+            float out[2][5][4];
+            mma::fc2<5>(dec, hid, out, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int row = rb + 16 * mt + g + 8 * hh;
+                    float pd = 0.f;
+#pragma unroll
+                    for (int nn = 0; nn < 5; nn++)
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const int o = 8 * nn + 2 * t + jj;
+                            if (o >= 1 && o <= 32) pd = fmaf(gfe[o - 1], rgb_act(out[mt][nn][2 * hh + jj]), pd);
+                        }
+                    pd += __shfl_xor_sync(0xffffffffu, pd, 1); pd += __shfl_xor_sync(0xffffffffu, pd, 2);
+                    if (t == 0 && row < D) { pdot[row] = pd; sig[row] = out[mt][0][2 * hh]; }
+                }
+        }
+        __syncwarp();
+        // ---- B2: compositing adjoint (same arithmetic as render_bwd_kernel)
+        for (int i = lane; i < D - 1; i += 32) {
+            float delta = dall[i + 1] - dall[i];
+            float sm = softplus_f((sig[i] + sig[i + 1]) * 0.5f - 1.f);
+            alpha[i] = 1.f - expf(-(sm * delta));
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float T = 1.f;
+            for (int i = 0; i < D - 1; i++) { float a = alpha[i]; Tarr[i] = T; w[i] = a * T; T *= (1.f - a + 1e-10f); }
+            w[D - 1] = 0.f;
+        }
+        __syncwarp();
+        float ws = 0.f, wd = 0.f;
+        for (int i = lane; i < D - 1; i += 32) { ws += w[i]; wd += w[i] * (0.5f * (dall[i] + dall[i + 1])); }
+        ws = warp_sum(ws); wd = warp_sum(wd);
+        const float depth = wd / ws;
+        const float gd = p.g_depth ? p.g_depth[ray] : 0.f;
+        const bool depth_live = (ws > 0.f) && (depth == depth) && (depth >= lo) && (depth <= hi);
+        for (int i = lane; i < D - 1; i += 32) {
+            float gw = 0.5f * (pdot[i] + pdot[i + 1]);
+            if (depth_live) gw += gd * (0.5f * (dall[i] + dall[i + 1]) - depth) / ws;
+            gmid[i] = gw;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            float S = 0.f;
+            for (int i = D - 2; i >= 0; i--) {
+                float gw = gmid[i];
+                gmid[i] = gw * Tarr[i] - S / (1.f - alpha[i] + 1e-10f);
+                S += gw * w[i];
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < D - 1; i += 32) {
+            float delta = dall[i + 1] - dall[i];
+            float smid = (sig[i] + sig[i + 1]) * 0.5f - 1.f;
+            gmid[i] = gmid[i] * delta * (1.f - alpha[i]) * sigmoid_f(smid);
+        }
+        __syncwarp();
+        // ---- B3: decoder backward per tile, features from the shared tile
+        for (int rb = 0; rb < D32; rb += 32) {
+            float hid[2][8][4];
+            mma::fc1(dec, F + (size_t)rb * mma::FS, hid, lane);
+            mma::softplus_inplace(hid);
+            float dout[2][5][4];
+            mma::fc2<5>(dec, hid, dout, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int row = rb + 16 * mt + g + 8 * hh;
+                    const bool valid = row < D;
+                    float gs = 0.f, a = 0.f;
+                    if (valid) {
+                        gs = 0.5f * ((row > 0 ? gmid[row - 1] : 0.f) + (row < D - 1 ? gmid[row] : 0.f));
+                        a = 0.5f * ((row > 0 ? w[row - 1] : 0.f) + w[row]);
+                    }
+#pragma unroll
+                    for (int nn = 0; nn < 5; nn++)
+#pragma unroll
+                        for (int jj = 0; jj < 2; jj++) {
+                            const int o = 8 * nn + 2 * t + jj;
+                            float v = 0.f;
+                            if (valid) {
+                                if (o == 0) v = gs;
+                                else if (o <= 32) { float so = sigmoid_f(dout[mt][nn][2 * hh + jj]); v = gfe[o - 1] * a * (1.f + 2.f * 0.001f) * so * (1.f - so); }
+                            }
+                            dout[mt][nn][2 * hh + jj] = v;
+                        }
+                }
+            const long long srow0 = ray * D + rb;
+            if (p.sc_dout) {
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int rr = 16 * mt + g + 8 * hh;
+                        if (rb + rr < D) {
+#pragma unroll
+                            for (int nn = 0; nn < 5; nn++) {
+                                const int o = 8 * nn + 2 * t;
+                                if (o < 36) *(float2*)(p.sc_dout + (srow0 + rr) * 36 + o) = make_float2(dout[mt][nn][2 * hh], dout[mt][nn][2 * hh + 1]);
+                            }
+                        }
+                    }
+            }
+            if (p.sc_hid) {
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int rr = 16 * mt + g + 8 * hh;
+                        if (rb + rr < D) {
+#pragma unroll
+                            for (int nt = 0; nt < 8; nt++)
+                                *(float2*)(p.sc_hid + (srow0 + rr) * NH + 8 * nt + 2 * t) = make_float2(hid[mt][nt][2 * hh], hid[mt][nt][2 * hh + 1]);
+                        }
+                    }
+            }
+            float dh[2][8][4];
+            mma::bwd_fc2(decb, dout, dh, lane);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) dh[mt][nt][j] *= (1.f - expf(-hid[mt][nt][j]));      // softplus' = 1 - exp(-softplus)
+            if (p.sc_dpre) {
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int rr = 16 * mt + g + 8 * hh;
+                        if (rb + rr < D) {
+#pragma unroll
+                            for (int nt = 0; nt < 8; nt++)
+                                *(float2*)(p.sc_dpre + (srow0 + rr) * NH + 8 * nt + 2 * t) = make_float2(dh[mt][nt][2 * hh], dh[mt][nt][2 * hh + 1]);
+                        }
+                    }
+            }
+            if (p.sc_f) {
+                for (int e = lane; e < 32 * 8; e += 32) {        // 32 rows x 8 float4
+                    const int rr = e >> 3, v = e & 7;
+                    if (rb + rr < D) *(float4*)(p.sc_f + (srow0 + rr) * NF + 4 * v) = *(const float4*)(F + (size_t)(rb + rr) * mma::FS + 4 * v);
+                }
+            }
+            if (gpl) {
+                float dfr[2][4][4];
+                mma::bwd_fc1(dec, dh, dfr, lane);
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+                        for (int nt = 0; nt < 4; nt++)
+                            *(float2*)(DFt + (16 * mt + g + 8 * hh) * mma::FS + 8 * nt + 2 * t) = make_float2(dfr[mt][nt][2 * hh], dfr[mt][nt][2 * hh + 1]);
+                __syncwarp();
+                const int i = min(rb + lane, D - 1);
+                const float d = dall[i];
+                warp_scatter_tile(gpl, DFt, s_off, s_w, p.W, p.H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, rb + lane < D, lane);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+size_t fwd2_smem_bytes(int dc, int df) {
+    int D = dc + df;
+    size_t per = (size_t)dc + ((dc + 31) & ~31) + ((df + 31) & ~31) + df + dc + 3 * (size_t)D + dc + df + (size_t)(((dc + 31) & ~31) + ((df + 31) & ~31)) * mma::FS;
+    per = (per + 3) & ~(size_t)3;
+    return ((sizeof(mma::DecM) + 15) / 16) * 16 + WARPS * per * sizeof(float);
+}
+size_t bwd2_smem_bytes(int D) {
+    size_t D32 = (D + 31) & ~31;
+    size_t per = D32 * mma::FS + 32 * mma::FS + 7 * D32 + 32 + 2 * 32 * 12;
+    per = (per + 3) & ~(size_t)3;
+    return ((sizeof(mma::DecM) + 15) / 16) * 16 + ((sizeof(mma::DecMBwd) + 15) / 16) * 16 + WARPS * per * sizeof(float);
+}
+
 size_t fwd_smem_bytes(int dc, int df) {
     size_t per_warp = (size_t)dc + (dc + df) + (dc + df) + dc + df + (dc + df) + dc + df + 32 * 33;
     return ((sizeof(Decoder) + 15) / 16) * 16 + WARPS * per_warp * sizeof(float);
@@ -886,17 +1273,20 @@ extern "C" int spi_render_forward(const float* planes, const float* origins, con
     if (rc) return rc;
     SPI_CHECK_ARG(jitter && (df == 0 || u) && feat && depth && wsum && minmax, "render_forward: null pointer");
     if (n == 0) return SPI_OK;
-    size_t smem = fwd_smem_bytes(dc, df);
-    cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool simt = getenv("SPI_RENDER_SIMT") != nullptr;      // v1 SIMT kernels kept for A/B comparison
+    size_t smem = simt ? fwd_smem_bytes(dc, df) : fwd2_smem_bytes(dc, df);
+    SPI_CHECK_ARG(smem <= 227 * 1024, "render_forward: %d+%d samples per ray need %zu B of shared memory (> 227 KB)", dc, df, smem);
+    auto kern = simt ? render_fwd_kernel : render_fwd_mma_kernel;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long rays = (long long)n * rays_per_image;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, render_fwd_kernel, WARPS * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
     if (occ < 1) occ = 1;
     long long want = (rays + WARPS - 1) / WARPS;
     long long cap = (long long)spi_num_sms() * occ;
     int grid = (int)(want < cap ? want : cap);
     minmax_init_kernel<<<1, 1, 0, stream>>>(minmax);
-    render_fwd_kernel<<<grid, WARPS * 32, smem, stream>>>(p);
+    kern<<<grid, WARPS * 32, smem, stream>>>(p);
     depth_clamp_kernel<<<cdiv(rays, 256) > 1184 ? 1184 : cdiv(rays, 256), 256, 0, stream>>>(depth, minmax, rays);
     SPI_COUNT_LAUNCH(3);
     SPI_LAUNCH_CHECK("render_forward");
@@ -918,16 +1308,19 @@ extern "C" int spi_render_backward(const float* planes, const float* origins, co
     if (rc) return rc;
     SPI_CHECK_ARG(depths_all && minmax && g_feat, "render_backward: null pointer");
     if (n == 0) return SPI_OK;
-    size_t smem = bwd_smem_bytes(dc + df);
-    cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool simt = getenv("SPI_RENDER_SIMT") != nullptr;
+    size_t smem = simt ? bwd_smem_bytes(dc + df) : bwd2_smem_bytes(dc + df);
+    SPI_CHECK_ARG(smem <= 227 * 1024, "render_backward: %d samples per ray need %zu B of shared memory (> 227 KB)", dc + df, smem);
+    auto kern = simt ? render_bwd_kernel : render_bwd_mma_kernel;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     long long rays = (long long)n * rays_per_image;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, render_bwd_kernel, WARPS * 32, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
     if (occ < 1) occ = 1;
     long long want = (rays + WARPS - 1) / WARPS;
     long long cap = (long long)spi_num_sms() * occ;
     int grid = (int)(want < cap ? want : cap);
-    render_bwd_kernel<<<grid, WARPS * 32, smem, stream>>>(p);
+    kern<<<grid, WARPS * 32, smem, stream>>>(p);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("render_backward");
     return SPI_OK;

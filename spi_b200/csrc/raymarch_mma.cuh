@@ -1,0 +1,220 @@
+// Tensor-core evaluation of the OSG decoder (triplane.py:112-135) inside the fused renderer.
+//
+// The decoder is a genuine dense contraction ([R*D, 32] x [32, 64] -> softplus -> x [64, 33]); a warp owns a tile of
+// 32 samples and evaluates it with mma.sync.m16n8k8 TF32.  To stay inside the 1e-3 render budget the products are
+// formed with the 3xTF32 split (a = a_hi + a_lo, b = b_hi + b_lo; a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32
+// accumulate), which restores ~fp32 accuracy at 3 MMAs per product -- still ~5x fewer issue slots than the SIMT
+// formulation, and no per-FMA shared-memory weight load.
+//
+// Layout tricks
+//   * sample features live in a per-warp shared tile F[rows][36] (stride 36 floats -> conflict-free A-fragment loads);
+//   * the C fragment of layer 1 is reused directly as the A fragment of layer 2 by permuting layer 2's K order
+//     (virtual k = t <-> hidden 8ks+2t, k = t+4 <-> hidden 8ks+2t+1), so the hidden activations never leave registers;
+//   * weights are pre-split into hi/lo TF32 arrays once per CTA; strides (36 / 72 / 40) make every B-fragment load
+//     conflict-free (32-bit loads per warp, 64-bit loads per half-warp).
+#pragma once
+#include "common.cuh"
+
+namespace mma {
+
+constexpr int NF = 32, NH = 64, NO = 33, NOP = 40;    // NOP: outputs padded to 5 n-tiles
+constexpr int FS = 36;                                  // feature tile row stride (floats)
+constexpr int W1S = 36, W2S = 72, W2TS = 40;
+
+struct DecM {
+    float w1h[NH * W1S], w1l[NH * W1S];       // [h][k]
+    float w2h[NOP * W2S], w2l[NOP * W2S];     // [o][h], rows >= 33 are zero
+    float b1[NH], b2[NOP];
+};
+struct DecMBwd {                               // extra for the backward pass
+    float w2th[NH * W2TS], w2tl[NH * W2TS];   // [h][o]
+};
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
+    hi = to_tf32(x);
+    lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                     uint32_t bl0, uint32_t bl1) {
+    mma_tf32(d, al, bh0, bh1);
+    mma_tf32(d, ah, bl0, bl1);
+    mma_tf32(d, ah, bh0, bh1);
+}
+
+// one-time staging of the decoder into shared memory (gains folded, hi/lo split)
+__device__ __forceinline__ void load_dec(DecM* s, const float* w1, const float* b1, const float* w2, const float* b2, float g1, float g2,
+                                         float gb) {
+    for (int i = threadIdx.x; i < NH * W1S; i += blockDim.x) {
+        int h = i / W1S, k = i % W1S;
+        float v = (k < NF) ? w1[h * NF + k] * g1 : 0.f;
+        uint32_t hi, lo; split(v, hi, lo);
+        s->w1h[i] = __uint_as_float(hi); s->w1l[i] = __uint_as_float(lo);
+    }
+    for (int i = threadIdx.x; i < NOP * W2S; i += blockDim.x) {
+        int o = i / W2S, h = i % W2S;
+        float v = (o < NO && h < NH) ? w2[o * NH + h] * g2 : 0.f;
+        uint32_t hi, lo; split(v, hi, lo);
+        s->w2h[i] = __uint_as_float(hi); s->w2l[i] = __uint_as_float(lo);
+    }
+    for (int i = threadIdx.x; i < NH; i += blockDim.x) s->b1[i] = b1[i] * gb;
+    for (int i = threadIdx.x; i < NOP; i += blockDim.x) s->b2[i] = i < NO ? b2[i] * gb : 0.f;
+}
+__device__ __forceinline__ void load_dec_bwd(DecMBwd* s, const float* w2, float g2) {
+    for (int i = threadIdx.x; i < NH * W2TS; i += blockDim.x) {
+        int h = i / W2TS, o = i % W2TS;
+        float v = (o < NO) ? w2[o * NH + h] * g2 : 0.f;
+        uint32_t hi, lo; split(v, hi, lo);
+        s->w2th[i] = __uint_as_float(hi); s->w2tl[i] = __uint_as_float(lo);
+    }
+}
+
+// ---- layer 1: pre[32 x 64] = F[32 x 32] W1^T + b1.  acc[mt][nt][j]: row 16mt + g + 8(j>>1), hidden 8nt + 2t + (j&1)
+__device__ __forceinline__ void fc1(const DecM* d, const float* F, float (&acc)[2][8][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+        const float bb0 = d->b1[8 * nt + 2 * t], bb1 = d->b1[8 * nt + 2 * t + 1];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) { acc[mt][nt][0] = bb0; acc[mt][nt][1] = bb1; acc[mt][nt][2] = bb0; acc[mt][nt][3] = bb1; }
+    }
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            const float* r0 = F + (16 * mt + g) * FS + 8 * ks + t;
+            const float* r1 = r0 + 8 * FS;
+            split(r0[0], ah[mt][0], al[mt][0]); split(r1[0], ah[mt][1], al[mt][1]);
+            split(r0[4], ah[mt][2], al[mt][2]); split(r1[4], ah[mt][3], al[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const int o = (8 * nt + g) * W1S + 8 * ks + t;
+            const uint32_t bh0 = __float_as_uint(d->w1h[o]), bh1 = __float_as_uint(d->w1h[o + 4]);
+            const uint32_t bl0 = __float_as_uint(d->w1l[o]), bl1 = __float_as_uint(d->w1l[o + 4]);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) mma3(acc[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
+        }
+    }
+}
+
+// ---- layer 2: out[32 x 8*NT2] = hid[32 x 64] W2^T + b2 (first NT2 n-tiles).  out[mt][n][j]: row as above, output 8n + 2t + (j&1)
+template <int NT2>
+__device__ __forceinline__ void fc2(const DecM* d, const float (&hid)[2][8][4], float (&out)[2][NT2][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int n = 0; n < NT2; n++) {
+        const float bb0 = d->b2[8 * n + 2 * t], bb1 = d->b2[8 * n + 2 * t + 1];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) { out[mt][n][0] = bb0; out[mt][n][1] = bb1; out[mt][n][2] = bb0; out[mt][n][3] = bb1; }
+    }
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {     // C fragment of layer 1 -> A fragment (a0=c0, a1=c2, a2=c1, a3=c3)
+            split(hid[mt][ks][0], ah[mt][0], al[mt][0]); split(hid[mt][ks][2], ah[mt][1], al[mt][1]);
+            split(hid[mt][ks][1], ah[mt][2], al[mt][2]); split(hid[mt][ks][3], ah[mt][3], al[mt][3]);
+        }
+#pragma unroll
+        for (int n = 0; n < NT2; n++) {
+            const int o = (8 * n + g) * W2S + 8 * ks + 2 * t;
+            const float2 bh = *(const float2*)(d->w2h + o), bl = *(const float2*)(d->w2l + o);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+                mma3(out[mt][n], ah[mt], al[mt], __float_as_uint(bh.x), __float_as_uint(bh.y), __float_as_uint(bl.x), __float_as_uint(bl.y));
+        }
+    }
+}
+
+__device__ __forceinline__ void softplus_inplace(float (&a)[2][8][4]) {
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) a[mt][nt][j] = softplus_f(a[mt][nt][j]);
+}
+
+// sigma of the 32 rows of a tile -> sig_tile[row] (written by the lanes with t == 0)
+__device__ __forceinline__ void tile_sigma(const DecM* d, const float* F, float* sig_tile, int lane) {
+    float hid[2][8][4];
+    fc1(d, F, hid, lane);
+    softplus_inplace(hid);
+    float out[2][1][4];
+    fc2<1>(d, hid, out, lane);
+    if ((lane & 3) == 0) {
+        const int g = lane >> 2;
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) { sig_tile[16 * mt + g] = out[mt][0][0]; sig_tile[16 * mt + g + 8] = out[mt][0][2]; }
+    }
+}
+
+// ---- backward GEMMs -------------------------------------------------------------------------------------------------
+// dhid[32 x 64] = dout[32 x 40] W2  (K = outputs; A = dout via the C->A trick, B from the transposed copy W2T[h][o])
+__device__ __forceinline__ void bwd_fc2(const DecMBwd* d, const float (&dout)[2][5][4], float (&dh)[2][8][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) dh[mt][nt][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 5; ks++) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            split(dout[mt][ks][0], ah[mt][0], al[mt][0]); split(dout[mt][ks][2], ah[mt][1], al[mt][1]);
+            split(dout[mt][ks][1], ah[mt][2], al[mt][2]); split(dout[mt][ks][3], ah[mt][3], al[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const int o = (8 * nt + g) * W2TS + 8 * ks + 2 * t;
+            const float2 bh = *(const float2*)(d->w2th + o), bl = *(const float2*)(d->w2tl + o);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++)
+                mma3(dh[mt][nt], ah[mt], al[mt], __float_as_uint(bh.x), __float_as_uint(bh.y), __float_as_uint(bl.x), __float_as_uint(bl.y));
+        }
+    }
+}
+
+// df[32 x 32] = dpre[32 x 64] W1  (K = hidden via the C->A trick; B[k][n] = W1[h = 8ks+2t(+1)][feature 8nt+g])
+__device__ __forceinline__ void bwd_fc1(const DecM* d, const float (&dp)[2][8][4], float (&df)[2][4][4], int lane) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) df[mt][nt][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ks++) {
+        uint32_t ah[2][4], al[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; mt++) {
+            split(dp[mt][ks][0], ah[mt][0], al[mt][0]); split(dp[mt][ks][2], ah[mt][1], al[mt][1]);
+            split(dp[mt][ks][1], ah[mt][2], al[mt][2]); split(dp[mt][ks][3], ah[mt][3], al[mt][3]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            const int o0 = (8 * ks + 2 * t) * W1S + 8 * nt + g;
+            const uint32_t bh0 = __float_as_uint(d->w1h[o0]), bh1 = __float_as_uint(d->w1h[o0 + W1S]);
+            const uint32_t bl0 = __float_as_uint(d->w1l[o0]), bl1 = __float_as_uint(d->w1l[o0 + W1S]);
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) mma3(df[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
+        }
+    }
+}
+
+}  // namespace mma
