@@ -294,7 +294,7 @@ def run_ours(args):
     if rf:
         bytes_per_img = render_fwd_bytes(*DEPTH)
         ach = bytes_per_img / (rf['ms_per_unit'] * 1e-3) / 1e9
-        roofline = {'kernel': 'render_fwd_kernel (spi_b200/csrc/raymarch.cu)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+        roofline = {'kernel': 'render_fwd_mma_kernel (spi_b200/csrc/raymarch.cu)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                     'frac': ach / peak, 'traffic': None, 'peak_source': peak_src, 'algorithmic_bytes_per_image': bytes_per_img,
                     'ms_per_image': rf['ms_per_unit'], 'launches_timed': rf['launches'],
                     'note': 'intensity ~385 FLOP/B: the kernel is FP32-issue / L2-gather bound, HBM fraction reported as the contract asks'}
