@@ -865,7 +865,7 @@ __device__ __forceinline__ int rup32(int v) { return (v + 31) & ~31; }
 __device__ __forceinline__ size_t fwd2_warp_floats(int dc, int df) {
     const int D = dc + df;
     return (size_t)dc /*dcs*/ + rup32(dc) /*sigc*/ + rup32(df) /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall,sigm,w*/ +
-           dc + df /*pos*/ + (size_t)(rup32(dc) + rup32(df)) * mma::FS + GATHER_FLOATS;
+           dc + df /*pos*/ + (size_t)(rup32(dc) + rup32(df)) * mma::FS + GATHER_FLOATS + 32 + 40;
 }
 
 __device__ __forceinline__ void gather_to_tile(const float* __restrict__ pl, int W, int H, const Ray& r, float d, float scale, float* row) {
@@ -932,7 +932,9 @@ __global__ void __launch_bounds__(WARPS * 32) render_fwd_mma_kernel(RenderParams
     int* pos_c = (int*)b; b += dc;
     int* pos_f = (int*)b; b += df;
     int* g_off = (int*)b; b += 32 * 12;
-    float* g_w = b;
+    float* g_w = b; b += 32 * 12;
+    float* a_tile = b; b += 32;
+    float* acc40 = b;
     mma::load_dec(dec, p.w1, p.b1, p.w2, p.b2, p.w1_gain, p.w2_gain, p.b_gain);
     __syncthreads();
     const int R = p.R;
@@ -977,42 +979,16 @@ __global__ void __launch_bounds__(WARPS * 32) render_fwd_mma_kernel(RenderParams
         warp_weights(dall, sigm, D, w, lane);
         warp_finalize(dall, w, D, depth, wsum, lane);          // w[] now holds the colour coefficients a_q
         // ---- pass 2b: colours, storage order, features from the shared tile
-        float racc[5][2];
-#pragma unroll
-        for (int nn = 0; nn < 5; nn++) { racc[nn][0] = 0.f; racc[nn][1] = 0.f; }
+        for (int o = lane; o < 40; o += 32) acc40[o] = 0.f;
         for (int rb = 0; rb < dc32 + df32; rb += 32) {
-            float hid[2][8][4];
-            mma::fc1(dec, F + (size_t)rb * mma::FS, hid, lane);
-            mma::softplus_inplace(hid);
-            float out[2][5][4];
-            mma::fc2<5>(dec, hid, out, lane);
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int sr = rb + 16 * mt + g + 8 * hh;
-                    const bool coarse = sr < dc32;
-                    const bool valid = coarse ? (sr < dc) : (sr - dc32 < df);
-                    float a = 0.f;
-                    if (valid) a = w[coarse ? pos_c[sr] : pos_f[sr - dc32]];
-#pragma unroll
-                    for (int nn = 0; nn < 5; nn++)
-#pragma unroll
-                        for (int jj = 0; jj < 2; jj++) {
-                            const int o = 8 * nn + 2 * t + jj;
-                            if (valid && o >= 1 && o <= 32) racc[nn][jj] = fmaf(a, rgb_act(out[mt][nn][2 * hh + jj]), racc[nn][jj]);
-                        }
-                }
+            const int sr = rb + lane;
+            const bool coarse = sr < dc32;
+            const bool valid = coarse ? (sr < dc) : (sr - dc32 < df);
+            a_tile[lane] = valid ? w[coarse ? pos_c[sr] : pos_f[sr - dc32]] : 0.f;
+            __syncwarp();
+            mma::tile_color(dec, F + (size_t)rb * mma::FS, a_tile, acc40, lane);
         }
-#pragma unroll
-        for (int nn = 0; nn < 5; nn++)
-#pragma unroll
-            for (int jj = 0; jj < 2; jj++) {
-                float v = racc[nn][jj];
-                v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);
-                const int o = 8 * nn + 2 * t + jj;
-                if (g == 0 && o >= 1 && o <= 32) p.feat[ray * NF + o - 1] = v * 2.f - 1.f;
-            }
+        p.feat[ray * NF + lane] = acc40[lane + 1] * 2.f - 1.f;          // rgb*2-1 (ray_marcher.py:55)
         for (int i = lane; i < D; i += 32) {
             const float d = dall[i];
             lmin = min(lmin, float_as_ordered(d)); lmax = max(lmax, float_as_ordered(d));
@@ -1092,27 +1068,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
             const int i = rb + lane;
             const float dd = (i < D) ? dall[i] : 0.f;
             warp_gather_tile(pl, p.W, p.H, r.ox + dd * r.dx, r.oy + dd * r.dy, r.oz + dd * r.dz, scale, i < D, F + (size_t)rb * mma::FS, s_off, s_w, lane);
-            float hid[2][8][4];
-            mma::fc1(dec, F + (size_t)rb * mma::FS, hid, lane);
-            mma::softplus_inplace(hid);
-            float out[2][5][4];
-            mma::fc2<5>(dec, hid, out, lane);
-#pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-#pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int row = rb + 16 * mt + g + 8 * hh;
-                    float pd = 0.f;
-#pragma unroll
-                    for (int nn = 0; nn < 5; nn++)
-#pragma unroll
-                        for (int jj = 0; jj < 2; jj++) {
-                            const int o = 8 * nn + 2 * t + jj;
-                            if (o >= 1 && o <= 32) pd = fmaf(gfe[o - 1], rgb_act(out[mt][nn][2 * hh + jj]), pd);
-                        }
-                    pd += __shfl_xor_sync(0xffffffffu, pd, 1); pd += __shfl_xor_sync(0xffffffffu, pd, 2);
-                    if (t == 0 && row < D) { pdot[row] = pd; sig[row] = out[mt][0][2 * hh]; }
-                }
+            mma::tile_sigma_pdot(dec, F + (size_t)rb * mma::FS, gfe, sig + rb, pdot + rb, lane);     // arrays are padded to D32
         }
         __syncwarp();
         // ---- B2: compositing adjoint (same arithmetic as render_bwd_kernel)
@@ -1181,7 +1137,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
                             float v = 0.f;
                             if (valid) {
                                 if (o == 0) v = gs;
-                                else if (o <= 32) { float so = sigmoid_f(dout[mt][nn][2 * hh + jj]); v = gfe[o - 1] * a * (1.f + 2.f * 0.001f) * so * (1.f - so); }
+                                else if (o <= 32) { float so = mma::sigmoid_fast(dout[mt][nn][2 * hh + jj]); v = gfe[o - 1] * a * (1.f + 2.f * 0.001f) * so * (1.f - so); }
                             }
                             dout[mt][nn][2 * hh + jj] = v;
                         }
@@ -1222,7 +1178,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) dh[mt][nt][j] *= (1.f - expf(-hid[mt][nt][j]));      // softplus' = 1 - exp(-softplus)
+                    for (int j = 0; j < 4; j++) dh[mt][nt][j] *= (1.f - __expf(-hid[mt][nt][j]));      // softplus' = 1 - exp(-softplus)
             if (p.sc_dpre) {
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)
@@ -1264,7 +1220,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
 
 size_t fwd2_smem_bytes(int dc, int df) {
     int D = dc + df;
-    size_t per = (size_t)dc + ((dc + 31) & ~31) + ((df + 31) & ~31) + df + dc + 3 * (size_t)D + dc + df + (size_t)(((dc + 31) & ~31) + ((df + 31) & ~31)) * mma::FS + GATHER_FLOATS;
+    size_t per = (size_t)dc + ((dc + 31) & ~31) + ((df + 31) & ~31) + df + dc + 3 * (size_t)D + dc + df + (size_t)(((dc + 31) & ~31) + ((df + 31) & ~31)) * mma::FS + GATHER_FLOATS + 32 + 40;
     per = (per + 3) & ~(size_t)3;
     return ((sizeof(mma::DecM) + 15) / 16) * 16 + WARPS * per * sizeof(float);
 }
