@@ -466,6 +466,27 @@ def golden_steps(G, sd, nets, fast):
     np.savez_compressed(os.path.join(OUT, 'steps.npz'), **g)
 
 
+def golden_idloss():
+    print('[id loss]')
+    from spi.criteria.id_loss.model_irse import Backbone
+    from . import idloss
+    sd = weights.irse50_state_dict(3)
+    net = Backbone(input_size=112, num_layers=50, drop_ratio=0.6, mode='ir_se').eval()
+    print('  load:', net.load_state_dict({k[len('facenet.'):]: v for k, v in sd.items()}, strict=True))
+    x = weights.target_image()
+    y = torch.flip(weights.target_image(seed=9), dims=[3]) * 0.8
+    pool = torch.nn.AdaptiveAvgPool2d((112, 112))
+
+    def ref_feats(t):      # IDLoss.extract_feats (id_loss.py:17-21)
+        return net(pool(t[:, :, 35:223, 32:220]))
+    with torch.no_grad():
+        fx, fy = ref_feats(x), ref_feats(y)
+        sim = fx[0].dot(fy[0])
+        note('id/feats', fx, idloss.extract_feats(x, sd))
+        note('id/similarity', sim.reshape(()), idloss.similarity(x, y, sd).reshape(()))
+    np.savez_compressed(os.path.join(OUT, 'idloss.npz'), feats_x=npy(fx), feats_y=npy(fy), sim=npy(sim))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--fast', action='store_true', help='skip the ~6 min RotBbox reference step')
@@ -494,6 +515,8 @@ def main():
         golden_geometry_losses(ref_out, nets)
     if want('steps'):
         golden_steps(G, sd, nets, args.fast)
+    if want('idloss'):
+        golden_idloss()
     path = os.path.join(OUT, 'REPORT.json')
     old = {}
     if only is not None and os.path.exists(path):

@@ -156,3 +156,42 @@ def landmarks68():
 
 def w_pivot(seed=5):
     return _randn('w_pivot', seed, [1, 14, 512], 0.5)
+
+
+def irse50_state_dict(seed=3, prefix='facenet.'):
+    """Seeded IR-SE50 (spi/criteria/id_loss/model_irse.py:10-42) state dict with the reference's names; BatchNorm running
+    statistics are positive, conv weights He-scaled so that 24 residual units stay O(1)."""
+    from .idloss import unit_list
+    sd = {}
+
+    def bn(p, c):
+        sd[p + 'weight'] = _randn(p + 'weight', seed, [c], 0.1, 1.0)
+        sd[p + 'bias'] = _randn(p + 'bias', seed, [c], 0.1)
+        sd[p + 'running_mean'] = _randn(p + 'running_mean', seed, [c], 0.1)
+        sd[p + 'running_var'] = torch.from_numpy(_rs(p + 'running_var', seed).uniform(0.5, 1.5, size=c).astype(np.float32))
+        sd[p + 'num_batches_tracked'] = torch.tensor(0, dtype=torch.long)
+
+    def conv(p, cout, cin, k):
+        sd[p] = _randn(p, seed, [cout, cin, k, k], math.sqrt(1.0 / (cin * k * k)))
+
+    p = prefix
+    conv(p + 'input_layer.0.weight', 64, 3, 3)
+    bn(p + 'input_layer.1.', 64)
+    sd[p + 'input_layer.2.weight'] = torch.full([64], 0.25)
+    for i, (cin, depth, stride) in enumerate(unit_list()):
+        q = f'{p}body.{i}.'
+        if cin != depth:
+            conv(q + 'shortcut_layer.0.weight', depth, cin, 1)
+            bn(q + 'shortcut_layer.1.', depth)
+        bn(q + 'res_layer.0.', cin)
+        conv(q + 'res_layer.1.weight', depth, cin, 3)
+        sd[q + 'res_layer.2.weight'] = torch.full([depth], 0.25)
+        conv(q + 'res_layer.3.weight', depth, depth, 3)
+        bn(q + 'res_layer.4.', depth)
+        conv(q + 'res_layer.5.fc1.weight', depth // 16, depth, 1)
+        conv(q + 'res_layer.5.fc2.weight', depth, depth // 16, 1)
+    bn(p + 'output_layer.0.', 512)
+    sd[p + 'output_layer.3.weight'] = _randn(p + 'output_layer.3.weight', seed, [512, 512 * 7 * 7], math.sqrt(1.0 / (512 * 49)))
+    sd[p + 'output_layer.3.bias'] = _randn(p + 'output_layer.3.bias', seed, [512], 0.1)
+    bn(p + 'output_layer.4.', 512)
+    return sd

@@ -197,3 +197,45 @@ def test_device_side_early_exit_skips_adam(gen_sd, lpips_mod, cx_mod):
     finally:
         hp.LPIPS_value_threshold = 0.05
     assert not stepped and torch.equal(coach.optimizer.arena, p0)
+
+
+def test_id_similarity_golden(golden):
+    """ArcFace IR-SE50 similarity (metrics path, id_loss.py:17-28) against the reference's recorded features."""
+    from spi_b200.criteria.id_loss.id_loss import IDLoss
+    g = golden('idloss')
+    sd = weights.irse50_state_dict(3)
+    m = IDLoss()
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    x = weights.target_image().cuda()
+    y = (torch.flip(weights.target_image(seed=9), dims=[3]) * 0.8).cuda()
+    with torch.no_grad():
+        fx = m.extract_feats(x)
+        sim = m.calculate_similarity(x, y)
+    assert rel_l2(fx, g['feats_x']) < 5e-3           # 50 conv layers with TF32 contraction
+    assert abs(float(sim) - float(g['sim'])) < 5e-3
+
+
+@pytest.mark.parametrize('kind', ['sg', 'sgw+'])
+def test_w_projectors_vs_oracle(kind, gen_sd, lpips_mod, nets):
+    """`first_inv_type` = sg / sgw+ (w_projector.py, w_plus_projector.py): two steps against the CPU oracle restatement."""
+    from spi_b200.criteria.lpips.vgg16_pt import VGG16LPIPSFeatures
+    from spi_b200.training.projectors._common import LatentProjector
+    from spi_b200.utils import load_utils, rng
+    rk = OG.RENDERING_DEFAULTS
+    target, c = weights.target_image(), weights.canonical_camera(0.3)
+    ref = OL.Projector(gen_sd, target, c, nets, kind=kind, num_steps=500, noise=OL.NoiseSource(300))
+    ref_infos = [ref.step(i) for i in range(2)]
+    G = load_utils.build_generator(state_dict=gen_sd, device='cuda')
+    src = OL.NoiseSource(300)
+    rng.inject(*[src.randn(*gen_sd[k].shape) for k in OL.noise_buffer_names(gen_sd)])
+    vgg = VGG16LPIPSFeatures().load_weights(nets['vgg16'], nets['lin']).cuda().eval()
+    p = LatentProjector(G, target.cuda(), c.cuda(), kind, lpips_func=lpips_mod, vgg16=vgg, num_steps=500, w_avg_samples=600)
+    for i in range(2):
+        rng.inject(src.randn(*p.w_opt.shape))
+        jit, u = src.render(1, 128 * 128, rk)
+        p.G.renderer.inject_noise(jit.cuda(), u.cuda())
+        out = p.step(i)
+        assert abs(float(out['dist']) / ref_infos[i]['dist'] - 1) < 5e-3
+    assert p.result().shape == (1, 14, 512)
+    assert rel_l2(p.result(), ref.result()) < 1e-3

@@ -130,3 +130,14 @@ def test_pti_step_matches_reference(golden):
     info = coach.step(0)
     assert abs(info['l2'] / float(g['pti_l2']) - 1) < 1e-4 and abs(info['lpips'] / float(g['pti_lpips']) - 1) < 1e-4
     assert rel_l2(coach.w.grad, g['pti_wgrad']) < 1e-4
+
+
+def test_id_similarity(golden):
+    from oracle import idloss
+    g = golden('idloss')
+    sd = weights.irse50_state_dict(3)
+    x = weights.target_image()
+    y = torch.flip(weights.target_image(seed=9), dims=[3]) * 0.8
+    with torch.no_grad():
+        assert rel_l2(idloss.extract_feats(x, sd), g['feats_x']) < TOL
+        assert abs(float(idloss.similarity(x, y, sd)) - float(g['sim'])) < 1e-5
