@@ -98,17 +98,15 @@ class _RenderFn(torch.autograd.Function):
         g_planes = torch.zeros_like(planes) if need_planes else None       # channels-last arena, accumulated with RED
         gw = None
         if need_dec:
-            rows = r * (dc + df)
+            # all images in one launch: the per-sample rows (784 B/sample) of the whole batch feed two TF32 GEMMs
+            rows = n * r * (dc + df)
             sc = [torch.empty(rows, c, device=planes.device) for c in SCRATCH_COLS]
-            for k in range(n):       # per image: bounds the scratch to rows*784 B and keeps it L2/HBM friendly
-                _lib.check(lib.spi_render_backward(
-                    _lib.ptr(planes[k:k + 1]), _lib.ptr(origins[k:k + 1]), _lib.ptr(dirs[k:k + 1]), _lib.ptr(depths_all[k:k + 1]),
-                    _lib.ptr(minmax), _lib.ptr(w1), _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'],
-                    _lib.ptr(g_feat[k:k + 1]), _lib.ptr(g_depth[k:k + 1]) if g_depth is not None else None,
-                    _lib.ptr(g_planes[k:k + 1]) if need_planes else None, _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]),
-                    _lib.ptr(sc[3]), 1, r, h, w, dc, df, opts['box_warp'], _lib.stream()))
-                g = _decoder_grads(sc, rows, opts['lr_mul'])
-                gw = g if gw is None else tuple(a + b for a, b in zip(gw, g))
+            _lib.check(lib.spi_render_backward(
+                _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
+                _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
+                _lib.ptr(g_planes), _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]), _lib.ptr(sc[3]), n, r, h, w, dc, df,
+                opts['box_warp'], _lib.stream()))
+            gw = _decoder_grads(sc, rows, opts['lr_mul'])
         else:
             _lib.check(lib.spi_render_backward(
                 _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
