@@ -10,8 +10,8 @@
 //   * sample features live in a per-warp shared tile F[rows][36] (stride 36 floats -> conflict-free A-fragment loads);
 //   * the C fragment of layer 1 is reused directly as the A fragment of layer 2 by permuting layer 2's K order
 //     (virtual k = t <-> hidden 8ks+2t, k = t+4 <-> hidden 8ks+2t+1), so the hidden activations never leave registers;
-//   * weights are pre-split into hi/lo TF32 arrays once per CTA; strides (36 / 72 / 40) make every B-fragment load
-//     conflict-free (32-bit loads per warp, 64-bit loads per half-warp).
+//   * weights sit once, in fp32, in shared memory; strides (36 / 72 / 40) make every B-fragment load conflict-free
+//     (32-bit loads per warp, 64-bit loads per half-warp); the hi/lo split happens in registers.
 #pragma once
 #include "common.cuh"
 
@@ -21,13 +21,15 @@ constexpr int NF = 32, NH = 64, NO = 33, NOP = 40;    // NOP: outputs padded to 
 constexpr int FS = 36;                                  // feature tile row stride (floats)
 constexpr int W1S = 36, W2S = 72, W2TS = 40;
 
+// fp32 weights, one copy: the hi/lo TF32 split of a B fragment is done in registers right after its load (6 ALU ops per 6
+// MMAs) so that the shared-memory footprint stays small enough for 2-3 CTAs per SM.
 struct DecM {
-    float w1h[NH * W1S], w1l[NH * W1S];       // [h][k]
-    float w2h[NOP * W2S], w2l[NOP * W2S];     // [o][h], rows >= 33 are zero
+    float w1[NH * W1S];        // [h][k]
+    float w2[NOP * W2S];       // [o][h], rows >= 33 are zero
     float b1[NH], b2[NOP];
 };
-struct DecMBwd {                               // extra for the backward pass
-    float w2th[NH * W2TS], w2tl[NH * W2TS];   // [h][o]
+struct DecMBwd {               // extra for the backward pass
+    float w2t[NH * W2TS];      // [h][o]
 };
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -56,15 +58,11 @@ __device__ __forceinline__ void load_dec(DecM* s, const float* w1, const float* 
                                          float gb) {
     for (int i = threadIdx.x; i < NH * W1S; i += blockDim.x) {
         int h = i / W1S, k = i % W1S;
-        float v = (k < NF) ? w1[h * NF + k] * g1 : 0.f;
-        uint32_t hi, lo; split(v, hi, lo);
-        s->w1h[i] = __uint_as_float(hi); s->w1l[i] = __uint_as_float(lo);
+        s->w1[i] = (k < NF) ? w1[h * NF + k] * g1 : 0.f;
     }
     for (int i = threadIdx.x; i < NOP * W2S; i += blockDim.x) {
         int o = i / W2S, h = i % W2S;
-        float v = (o < NO && h < NH) ? w2[o * NH + h] * g2 : 0.f;
-        uint32_t hi, lo; split(v, hi, lo);
-        s->w2h[i] = __uint_as_float(hi); s->w2l[i] = __uint_as_float(lo);
+        s->w2[i] = (o < NO && h < NH) ? w2[o * NH + h] * g2 : 0.f;
     }
     for (int i = threadIdx.x; i < NH; i += blockDim.x) s->b1[i] = b1[i] * gb;
     for (int i = threadIdx.x; i < NOP; i += blockDim.x) s->b2[i] = i < NO ? b2[i] * gb : 0.f;
@@ -72,9 +70,7 @@ __device__ __forceinline__ void load_dec(DecM* s, const float* w1, const float* 
 __device__ __forceinline__ void load_dec_bwd(DecMBwd* s, const float* w2, float g2) {
     for (int i = threadIdx.x; i < NH * W2TS; i += blockDim.x) {
         int h = i / W2TS, o = i % W2TS;
-        float v = (o < NO) ? w2[o * NH + h] * g2 : 0.f;
-        uint32_t hi, lo; split(v, hi, lo);
-        s->w2th[i] = __uint_as_float(hi); s->w2tl[i] = __uint_as_float(lo);
+        s->w2t[i] = (o < NO) ? w2[o * NH + h] * g2 : 0.f;
     }
 }
 
@@ -100,8 +96,8 @@ __device__ __forceinline__ void fc1(const DecM* d, const float* F, float (&acc)[
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
             const int o = (8 * nt + g) * W1S + 8 * ks + t;
-            const uint32_t bh0 = __float_as_uint(d->w1h[o]), bh1 = __float_as_uint(d->w1h[o + 4]);
-            const uint32_t bl0 = __float_as_uint(d->w1l[o]), bl1 = __float_as_uint(d->w1l[o + 4]);
+            uint32_t bh0, bh1, bl0, bl1;
+            split(d->w1[o], bh0, bl0); split(d->w1[o + 4], bh1, bl1);
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) mma3(acc[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
         }
@@ -129,10 +125,11 @@ __device__ __forceinline__ void fc2(const DecM* d, const float (&hid)[2][8][4], 
 #pragma unroll
         for (int n = 0; n < NT2; n++) {
             const int o = (8 * n + g) * W2S + 8 * ks + 2 * t;
-            const float2 bh = *(const float2*)(d->w2h + o), bl = *(const float2*)(d->w2l + o);
+            const float2 bw = *(const float2*)(d->w2 + o);
+            uint32_t bh0, bh1, bl0, bl1;
+            split(bw.x, bh0, bl0); split(bw.y, bh1, bl1);
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-                mma3(out[mt][n], ah[mt], al[mt], __float_as_uint(bh.x), __float_as_uint(bh.y), __float_as_uint(bl.x), __float_as_uint(bl.y));
+            for (int mt = 0; mt < 2; mt++) mma3(out[mt][n], ah[mt], al[mt], bh0, bh1, bl0, bl1);
         }
     }
 }
@@ -249,10 +246,11 @@ __device__ __forceinline__ void bwd_fc2(const DecMBwd* d, const float (&dout)[2]
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
             const int o = (8 * nt + g) * W2TS + 8 * ks + 2 * t;
-            const float2 bh = *(const float2*)(d->w2th + o), bl = *(const float2*)(d->w2tl + o);
+            const float2 bw = *(const float2*)(d->w2t + o);
+            uint32_t bh0, bh1, bl0, bl1;
+            split(bw.x, bh0, bl0); split(bw.y, bh1, bl1);
 #pragma unroll
-            for (int mt = 0; mt < 2; mt++)
-                mma3(dh[mt][nt], ah[mt], al[mt], __float_as_uint(bh.x), __float_as_uint(bh.y), __float_as_uint(bl.x), __float_as_uint(bl.y));
+            for (int mt = 0; mt < 2; mt++) mma3(dh[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
         }
     }
 }
@@ -277,8 +275,8 @@ __device__ __forceinline__ void bwd_fc1(const DecM* d, const float (&dp)[2][8][4
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
             const int o0 = (8 * ks + 2 * t) * W1S + 8 * nt + g;
-            const uint32_t bh0 = __float_as_uint(d->w1h[o0]), bh1 = __float_as_uint(d->w1h[o0 + W1S]);
-            const uint32_t bl0 = __float_as_uint(d->w1l[o0]), bl1 = __float_as_uint(d->w1l[o0 + W1S]);
+            uint32_t bh0, bh1, bl0, bl1;
+            split(d->w1[o0], bh0, bl0); split(d->w1[o0 + W1S], bh1, bl1);
 #pragma unroll
             for (int mt = 0; mt < 2; mt++) mma3(df[mt][nt], ah[mt], al[mt], bh0, bh1, bl0, bl1);
         }
