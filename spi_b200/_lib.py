@@ -102,3 +102,22 @@ def launch_count():
 
 def reset_launch_count():
     load().spi_reset_launch_count()
+
+
+# ---- optional per-kernel timing hook (bench.py installs an object with .start(tag, units) / .stop(tag)); events are
+#      recorded on the launching stream around the C-ABI call, only in eager passes (never inside graph capture)
+KERNEL_TIMER = None
+
+
+class timed:
+    def __init__(self, tag, units=1):
+        self.tag, self.units = tag, units
+
+    def __enter__(self):
+        if KERNEL_TIMER is not None:
+            KERNEL_TIMER.start(self.tag, self.units)
+
+    def __exit__(self, *exc):
+        if KERNEL_TIMER is not None:
+            KERNEL_TIMER.stop(self.tag)
+        return False

@@ -39,14 +39,23 @@ class _PerSampleConv(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, stride, padding, transpose):
         torch.backends.cudnn.allow_tf32 = ALLOW_TF32
-        n = x.shape[0]
+        n, _, h, wd = x.shape
+        o, kh, kw = w.shape[1], w.shape[3], w.shape[4]
+        st, pd = _pair(stride), _pair(padding)
         x = x.contiguous(memory_format=torch.channels_last)
-        ys = []
+        if transpose:
+            oh, ow = (h - 1) * st[0] - 2 * pd[0] + kh, (wd - 1) * st[1] - 2 * pd[1] + kw
+        else:
+            oh, ow = (h + 2 * pd[0] - kh) // st[0] + 1, (wd + 2 * pd[1] - kw) // st[1] + 1
+        # every sample's result is written by cuDNN straight into its slice of the batch tensor (no cat, no copy)
+        y = torch.empty(n, o, oh, ow, device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
         for k in range(n):
             wk = w[k].transpose(0, 1) if transpose else w[k]
             wk = wk.contiguous(memory_format=torch.channels_last)
-            ys.append(torch.ops.aten.convolution(x[k:k + 1], wk, None, _pair(stride), _pair(padding), [1, 1], transpose, [0, 0], 1))
-        y = ys[0] if n == 1 else torch.cat(ys, 0)
+            if transpose:
+                torch.ops.aten.cudnn_convolution_transpose.out(x[k:k + 1], wk, pd, [0, 0], st, [1, 1], 1, False, False, ALLOW_TF32, out=y[k:k + 1])
+            else:
+                torch.ops.aten.cudnn_convolution.out(x[k:k + 1], wk, pd, st, [1, 1], 1, False, False, ALLOW_TF32, out=y[k:k + 1])
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, transpose)
         return y

@@ -79,7 +79,8 @@ class FlatAdam:
                 self.advance()
         g = self.param_groups[0]
         cond, thr = self.skip_if_le if self.skip_if_le is not None else (None, 0.0)
-        _lib.check(_lib.load().spi_adam_step(_lib.ptr(self.arena), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
-                                             self.arena.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
-                                             max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None, 0,
-                                             _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))
+        with _lib.timed('adam', self.arena.numel() * 28):
+            _lib.check(_lib.load().spi_adam_step(_lib.ptr(self.arena), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
+                                                 self.arena.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+                                                 max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None, 0,
+                                                 _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))

@@ -66,10 +66,12 @@ def _plugin_bias_act(x, b, xref, yref, dy, grad, dim, act_idx, alpha, gain, clam
         if t is not None and t.numel() and (t.shape != x.shape or t.stride() != x.stride()):
             raise RuntimeError('xref/yref/dy must have the same shape and layout as x')
     has_b = b is not None and b.numel() > 0
-    _lib.check(_lib.load().spi_bias_act(
+    nbytes = x.numel() * x.element_size() * (2 + (xref is not None) + (yref is not None) + (dy is not None))
+    with _lib.timed('bias_act', nbytes):
+        _lib.check(_lib.load().spi_bias_act(
         _lib.ptr(x), _lib.ptr(b), _lib.ptr(xref), _lib.ptr(yref), _lib.ptr(dy), _lib.ptr(y), x.numel(),
-        b.numel() if has_b else 1, x.stride(dim) if has_b else 1, _lib.dtype_code(x), grad, act_idx,
-        alpha, gain, clamp, _lib.stream()))
+            b.numel() if has_b else 1, x.stride(dim) if has_b else 1, _lib.dtype_code(x), grad, act_idx,
+            alpha, gain, clamp, _lib.stream()))
     return y
 
 

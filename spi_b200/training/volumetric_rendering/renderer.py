@@ -97,6 +97,8 @@ class _RenderFn(torch.autograd.Function):
         g_depth = g_depth.contiguous() if g_depth is not None else None
         g_planes = torch.zeros_like(planes) if need_planes else None       # channels-last arena, accumulated with RED
         gw = None
+        if KERNEL_TIMER is not None:
+            KERNEL_TIMER.start('render_bwd', n)
         if need_dec:
             # all images in one launch: the per-sample rows (784 B/sample) of the whole batch feed two TF32 GEMMs
             rows = n * r * (dc + df)
@@ -113,6 +115,8 @@ class _RenderFn(torch.autograd.Function):
                 _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
                 _lib.ptr(g_planes), None, None, None, None, n, r, h, w, dc, df, opts['box_warp'], _lib.stream()))
             gw = (None, None, None, None)
+        if KERNEL_TIMER is not None:
+            KERNEL_TIMER.stop('render_bwd')
         return (g_planes, *gw, None, None, None, None, None)
 
 
