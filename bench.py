@@ -73,38 +73,52 @@ def synthetic_inputs(seed=4):
     return dict(img=img, c=cal_canonical_c(0.3, 0.0, 1, 'cpu'), mask=m[None, None], lm=torch.from_numpy(pts)[None])
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms 200`
+    child started from the main thread before the timed region and killed after it (no fork while CUDA calls are in flight)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc, self.path = index, None, None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits'],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([v.strip() for v in out.split(',')])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        import tempfile
+        fd, self.path = tempfile.mkstemp(prefix='clocks_', suffix='.csv')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=fd, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        os.close(fd)
+        time.sleep(0.25)
 
     def finish(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        rows = []
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            rows = [[v.strip() for v in line.split(',')] for line in open(self.path).read().splitlines() if line.strip()]
+        if self.path and os.path.exists(self.path):
+            os.remove(self.path)
+
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
                 if v.lower().startswith('active'):
                     reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': sorted(reasons),
-                'samples': len(self.rows)}
+                'samples': len(rows)}
 
 
 class KernelTimer:
