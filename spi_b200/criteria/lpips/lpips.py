@@ -28,6 +28,7 @@ class LPIPS(nn.Module):
             self.lin.load_state_dict(lin_state_dict)
         self.num_scales = num_scales
         self._cache = {}                 # id(y) -> (y, version, resize, feats); holds y alive so its id/ptr cannot be recycled
+        self._retired = []
 
     def load_weights(self, vgg_features_state_dict, lin_weights):
         """vgg_features_state_dict: torchvision `vgg16().features` names ('0.weight', ...); lin_weights: 5 x [1,C,1,1]."""
@@ -45,7 +46,9 @@ class LPIPS(nn.Module):
     def register_target(self, y):
         """Declare `y` a constant target (the image being inverted): its five feature taps are computed once and reused by
         every later forward(x, y) with this very tensor object.  Unregistered `y` (e.g. warped images) are never cached."""
-        self._cache[id(y)] = (y, None, None, None)
+        hit = self._cache.get(id(y))
+        if hit is None or hit[0] is not y:        # keep an existing entry: captured CUDA graphs hold pointers to its tensors
+            self._cache[id(y)] = (y, None, None, None)
         return y
 
     def _target_feats(self, y, resize):
@@ -58,6 +61,8 @@ class LPIPS(nn.Module):
         if hit[3] is None or hit[1] != y._version or hit[2] != resize:
             with torch.no_grad():
                 feats = self.net(self._resize(y) if resize else y)
+            if hit[3] is not None:
+                self._retired.append(hit[3])      # never free tensors a captured graph may still read
             self._cache[id(y)] = (y, y._version, resize, feats)
             return feats
         return hit[3]
