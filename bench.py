@@ -324,7 +324,7 @@ def run_ours(args):
     rb = timer.summary('render_bwd')
     if roofline is not None:
         roofline['streaming_kernels'] = streaming
-        roofline['render_bwd_ms_per_image'] = rb['ms_per_unit'] if rb else None
+        roofline['render_bwd_incl_decoder_grad_gemms_ms_per_image_eager'] = rb['ms_per_unit'] if rb else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(job, budget_s=min(args.cpu_budget_s, 60.0), heavy=False)
