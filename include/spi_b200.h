@@ -69,7 +69,8 @@ int spi_filtered_lrelu_act(void* x, unsigned char* s, int dtype, int n, int c, i
  *      and OSGDecoder (eg3d/training/triplane.py:112-135) ---------------------------------------------- */
 
 /* ImportanceRenderer.forward (renderer.py:88-140) fused with RaySampler.forward (ray_sampler.py:24-61).
- * planes: channels-last [n, plane_h, plane_w, 96]; origins/dirs [n, R, 3]; jitter [n, R, dc]; u [n*R, df];
+ * planes: channels-last [n, plane_h, plane_w, 96] with batch stride plane_batch_stride floats (0 = one tri-plane set shared
+ * by all n views: the backbone output does not depend on the camera); origins/dirs [n, R, 3]; jitter [n, R, dc]; u [n*R, df];
  * decoder tensors as stored in the state dict (decoder.net.0/2.{weight,bias}), lr_mul = decoder_lr_mul; outputs feat [n, R, 32],
  * depth [n, R] (clamped to the global sample-depth range, ray_marcher.py:49-50), wsum [n, R];
  * depths_all [n, R, dc+df] is the sorted merged depth list the backward pass needs; sigma_all optional (NULL);
@@ -77,7 +78,7 @@ int spi_filtered_lrelu_act(void* x, unsigned char* s, int dtype, int n, int c, i
 int spi_render_forward(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
                        const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
                        float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n, int rays_per_image,
-                       int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end, float box_warp, int disparity,
+                       long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end, float box_warp, int disparity,
                        cudaStream_t stream);
 /* Backward of the above w.r.t. planes (accumulated into g_planes, may be NULL) and, when the sc_* buffers are
  * given, the per-sample rows [S,32] [S,64] [S,64] [S,36] from which the decoder weight gradients are formed
@@ -85,7 +86,7 @@ int spi_render_forward(const float* planes, const float* origins, const float* d
 int spi_render_backward(const float* planes, const float* origins, const float* dirs, const float* depths_all, const int* minmax,
                         const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, const float* g_feat,
                         const float* g_depth, float* g_planes, float* sc_f, float* sc_hid, float* sc_dpre, float* sc_dout, int n,
-                        int rays_per_image, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream);
+                        int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream);
 /* ImportanceRenderer.run_model (renderer.py:142-149) on arbitrary points: coords [n, m, 3] -> rgb [n, m, 32],
  * sigma [n, m]; used by TriPlaneGenerator.sample / sample_mixed (triplane.py:91-102). */
 int spi_points_forward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,

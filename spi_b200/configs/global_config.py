@@ -9,3 +9,7 @@ run_name = ''
 
 ## spi_b200: replay each optimisation iteration as a captured CUDA graph (eager when False or when tests inject noise)
 use_cuda_graphs = True
+
+## spi_b200: within an iteration every view shares w_pivot, so the camera-independent tri-plane backbone is evaluated once and
+## shared (results identical to re-evaluating it per view, as the reference does); one backward over the summed losses
+share_backbone = True

@@ -61,6 +61,7 @@ struct RenderParams {
     float* sigma_all;          // optional debug output [N, R, D]
     int* minmax;               // 2 ints: ordered-int min / max of all sample depths (ray_marcher.py:50)
     int n, R, H, W, dc, df;    // R = rays per image
+    long long plane_bs;        // batch stride of planes / g_planes in floats (0: one tri-plane set shared by all n views)
     float ray_start, ray_end, box_warp;
     int disparity;
     // backward
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_fwd_kernel(RenderParams p) 
     int lmin = 0x7f800000, lmax = 0;
     for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
         const int n = (int)(ray / R);
-        const float* pl = p.planes + (size_t)n * p.H * p.W * 96;
+        const float* pl = p.planes + (size_t)n * p.plane_bs;
         Ray r;
         r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
         r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
@@ -518,8 +519,8 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_kernel(RenderParams p) 
     const float lo = __int_as_float(p.minmax[0]), hi = __int_as_float(p.minmax[1]);
     for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
         const int n = (int)(ray / R);
-        const float* pl = p.planes + (size_t)n * p.H * p.W * 96;
-        float* gpl = p.g_planes + (size_t)n * p.H * p.W * 96;
+        const float* pl = p.planes + (size_t)n * p.plane_bs;
+        float* gpl = p.g_planes + (size_t)n * p.plane_bs;
         Ray r;
         r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
         r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
@@ -944,7 +945,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_fwd_mma_kernel(RenderParams
     int lmin = 0x7f800000, lmax = 0;
     for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
         const int n = (int)(ray / R);
-        const float* pl = p.planes + (size_t)n * p.H * p.W * 96;
+        const float* pl = p.planes + (size_t)n * p.plane_bs;
         Ray r;
         r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
         r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
@@ -1055,8 +1056,8 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
     const int g = lane >> 2, t = lane & 3;
     for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
         const int n = (int)(ray / R);
-        const float* pl = p.planes + (size_t)n * p.H * p.W * 96;
-        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.H * p.W * 96 : nullptr;
+        const float* pl = p.planes + (size_t)n * p.plane_bs;
+        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.plane_bs : nullptr;
         Ray r;
         r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
         r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
@@ -1255,13 +1256,13 @@ int check_render(const RenderParams& p) {
 extern "C" int spi_render_forward(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
                                   const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
                                   float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n,
-                                  int rays_per_image, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end,
+                                  int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end,
                                   float box_warp, int disparity, cudaStream_t stream) {
     RenderParams p;
     memset(&p, 0, sizeof(p));
     p.planes = planes; p.origins = origins; p.dirs = dirs; p.jitter = jitter; p.u = u; FILL_DECODER(p);
     p.feat = feat; p.depth = depth; p.wsum = wsum; p.depths_all = depths_all; p.sigma_all = sigma_all; p.minmax = minmax;
-    p.n = n; p.R = rays_per_image; p.H = plane_h; p.W = plane_w; p.dc = dc; p.df = df;
+    p.n = n; p.R = rays_per_image; p.H = plane_h; p.W = plane_w; p.dc = dc; p.df = df; p.plane_bs = plane_batch_stride;
     p.ray_start = ray_start; p.ray_end = ray_end; p.box_warp = box_warp; p.disparity = disparity;
     int rc = check_render(p);
     if (rc) return rc;
@@ -1290,14 +1291,15 @@ extern "C" int spi_render_forward(const float* planes, const float* origins, con
 extern "C" int spi_render_backward(const float* planes, const float* origins, const float* dirs, const float* depths_all,
                                    const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
                                    float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_f,
-                                   float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image, int plane_h,
-                                   int plane_w, int dc, int df, float box_warp, cudaStream_t stream) {
+                                   float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
+                                   long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream) {
     RenderParams p;
     memset(&p, 0, sizeof(p));
     p.planes = planes; p.origins = origins; p.dirs = dirs; FILL_DECODER(p);
     p.depths_all = (float*)depths_all; p.minmax = (int*)minmax; p.g_feat = g_feat; p.g_depth = g_depth; p.g_planes = g_planes;
     p.sc_f = sc_f; p.sc_hid = sc_hid; p.sc_dpre = sc_dpre; p.sc_dout = sc_dout;
     p.n = n; p.R = rays_per_image; p.H = plane_h; p.W = plane_w; p.dc = dc; p.df = df; p.box_warp = box_warp;
+    p.plane_bs = plane_batch_stride;
     int rc = check_render(p);
     if (rc) return rc;
     SPI_CHECK_ARG(depths_all && minmax && g_feat, "render_backward: null pointer");

@@ -49,13 +49,15 @@ class _PerSampleConv(torch.autograd.Function):
             oh, ow = (h + 2 * pd[0] - kh) // st[0] + 1, (wd + 2 * pd[1] - kw) // st[1] + 1
         # every sample's result is written by cuDNN straight into its slice of the batch tensor (no cat, no copy)
         y = torch.empty(n, o, oh, ow, device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
-        for k in range(n):
-            wk = w[k].transpose(0, 1) if transpose else w[k]
+        shared = (w.shape[0] == 1 and n > 1)       # one weight set for the whole batch: a single batched call
+        for k in ([slice(0, n)] if shared else [slice(i, i + 1) for i in range(n)]):
+            wi = 0 if shared else k.start
+            wk = w[wi].transpose(0, 1) if transpose else w[wi]
             wk = wk.contiguous(memory_format=torch.channels_last)
             if transpose:
-                torch.ops.aten.cudnn_convolution_transpose.out(x[k:k + 1], wk, pd, [0, 0], st, [1, 1], 1, False, False, ALLOW_TF32, out=y[k:k + 1])
+                torch.ops.aten.cudnn_convolution_transpose.out(x[k], wk, pd, [0, 0], st, [1, 1], 1, False, False, ALLOW_TF32, out=y[k])
             else:
-                torch.ops.aten.cudnn_convolution.out(x[k:k + 1], wk, pd, st, [1, 1], 1, False, False, ALLOW_TF32, out=y[k:k + 1])
+                torch.ops.aten.cudnn_convolution.out(x[k], wk, pd, st, [1, 1], 1, False, False, ALLOW_TF32, out=y[k])
         ctx.save_for_backward(x, w)
         ctx.cfg = (stride, padding, transpose)
         return y
@@ -68,20 +70,23 @@ class _PerSampleConv(torch.autograd.Function):
         n = x.shape[0]
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gy = gy.contiguous(memory_format=torch.channels_last)
-        gx = torch.empty_like(x) if (need_x and n > 1) else None
+        shared = (w.shape[0] == 1 and n > 1)
+        single = shared or n == 1
+        gx = torch.empty_like(x) if (need_x and not single) else None
         gw = torch.empty_like(w) if need_w else None          # preserves w's (conv-native) strides
-        for k in range(n):
-            wk = w[k].transpose(0, 1) if transpose else w[k]
+        for k in ([slice(0, n)] if shared else [slice(i, i + 1) for i in range(n)]):
+            wi = 0 if shared else k.start
+            wk = w[wi].transpose(0, 1) if transpose else w[wi]
             wk = wk.contiguous(memory_format=torch.channels_last)
-            gxk, gwk, _ = torch.ops.aten.convolution_backward(gy[k:k + 1], x[k:k + 1], wk, None, _pair(stride), _pair(padding), [1, 1],
+            gxk, gwk, _ = torch.ops.aten.convolution_backward(gy[k], x[k], wk, None, _pair(stride), _pair(padding), [1, 1],
                                                               transpose, [0, 0], 1, [need_x, need_w, False])
             if need_x:
-                if n == 1:
+                if single:
                     gx = gxk
                 else:
-                    gx[k:k + 1].copy_(gxk)
+                    gx[k].copy_(gxk)
             if need_w:
-                gw[k].copy_(gwk.transpose(0, 1) if transpose else gwk)
+                gw[wi].copy_(gwk.transpose(0, 1) if transpose else gwk)
         return gx, gw, None, None, None
 
 

@@ -46,8 +46,13 @@ class RotBboxCoach(BaseCoach):
         The early exit (`if loss_lpips <= threshold: break` BEFORE `optimizer.step()`, :148-151) is applied on the device:
         the Adam kernel is a no-op when the LPIPS scalar is below the threshold; the host reads the scalar afterwards."""
         hp = hyperparameters
+        share = global_config.share_backbone and heavy
+        # share=True: the tri-plane backbone (camera-independent) runs once per iteration and is reused by every view; the
+        # four losses are summed and back-propagated once.  share=False replays the reference's structure literally.
+        kw = dict(use_cached_backbone=True) if share else {}
+        rep = (lambda t, k: t.expand(k, -1, -1)) if share else (lambda t, k: t.repeat(k, 1, 1))
         self.optimizer.zero_grad()
-        gen = self.G.synthesis(w_pivot, st.camera, noise_mode='const')
+        gen = self.G.synthesis(w_pivot, st.camera, noise_mode='const', cache_backbone=share)
         generated_images, generated_depths = gen['image'], gen['image_depth']
         loss = 0.0
         if hp.pt_l2_lambda > 0:
@@ -55,19 +60,24 @@ class RotBboxCoach(BaseCoach):
         if hp.pt_lpips_lambda > 0:
             loss_lpips = torch.squeeze(self.lpips_loss(generated_images, st.image))
             loss = loss + loss_lpips * hp.pt_lpips_lambda
-        loss.backward()
+        if not share:
+            loss.backward()
+            loss = 0.0
         if heavy:
             if hp.pt_rot_lambda > 0:
                 cams = sample_surrounding_camera(st.camera, batch_size=rot_bs, yaw_range=st.yaw_range, pitch_range=0.1)
-                samples = self.G.synthesis(w_pivot.repeat(rot_bs, 1, 1), cams, noise_mode='const')
+                samples = self.G.synthesis(rep(w_pivot, rot_bs), cams, noise_mode='const', **kw)
                 with torch.no_grad():       # broadcast sources instead of .repeat(rot_bs, ...) copies
                     warp_img, warp_mask = rotate(target_camera=cams, target_depth=samples['image_depth'], src_image=st.image,
                                                  src_camera=st.camera, src_depth=generated_depths, src_mask=st.face_mask, EPS=5e-2)
                 loss_rot = self.lpips_loss(samples['image'] * warp_mask, warp_img) * hp.pt_rot_lambda * rot_bs
-                loss_rot.backward()
+                if share:
+                    loss = loss + loss_rot
+                else:
+                    loss_rot.backward()
             if hp.pt_mirror_rot_lambda > 0 and st.mirror_on:
                 cams_m = sample_surrounding_camera(st.camera_m, batch_size=rot_bs, yaw_range=st.yaw_range, pitch_range=0.1)
-                samples_m = self.G.synthesis(w_pivot.repeat(rot_bs, 1, 1), cams_m, noise_mode='const')
+                samples_m = self.G.synthesis(rep(w_pivot, rot_bs), cams_m, noise_mode='const', **kw)
                 with torch.no_grad():
                     depths_m = torch.flip(generated_depths, dims=[3])
                     warp_img_m, warp_mask_m = rotate(target_camera=cams_m, target_depth=samples_m['image_depth'], src_image=st.image_m,
@@ -77,16 +87,30 @@ class RotBboxCoach(BaseCoach):
                 lm = st.lm.repeat(rot_bs, 1, 1)
                 flip_gen_image = torch.flip(samples_m['image'], dims=[3])
                 loss_rot_m = self.box_cx_loss(flip_gen_image * flip_warp_mask_m, flip_warp_img_m, lm) * hp.pt_mirror_rot_lambda * rot_bs
-                loss_rot_m.backward()
+                if share:
+                    loss = loss + loss_rot_m
+                else:
+                    loss_rot_m.backward()
             if hp.pt_depth_lambda > 0:
                 new_camera = sample_camera(batch_size=4, yaw_range=0.7, pitch_range=0.4, device=global_config.device)
-                new_ws = w_pivot.repeat(4, 1, 1)
-                sample_depth = self.G.synthesis(new_ws, new_camera, noise_mode='const')['image_depth']
+                new_ws = rep(w_pivot, 4)
+                # only image_depth is consumed here (:133-139): the super-resolution network is dead code for this branch
+                sample_depth = self.G.synthesis(new_ws, new_camera, noise_mode='const', need_image=not share, **kw)['image_depth']
                 with torch.no_grad():
-                    stable_depth = self.original_G.synthesis(new_ws, new_camera, noise_mode='const')['image_depth']
-                (l2_loss(stable_depth, sample_depth) * hp.pt_depth_lambda).backward()
+                    stable_depth = self.original_G.synthesis(new_ws, new_camera, noise_mode='const', need_image=not share)['image_depth']
+                loss_depth = l2_loss(stable_depth, sample_depth) * hp.pt_depth_lambda
+                if share:
+                    loss = loss + loss_depth
+                else:
+                    loss_depth.backward()
             if hp.pt_tv_lambda > 0:
-                (cal_tv_loss(w_pivot, self.G) * hp.pt_tv_lambda).backward()
+                loss_tv = cal_tv_loss(w_pivot, self.G) * hp.pt_tv_lambda
+                if share:
+                    loss = loss + loss_tv
+                else:
+                    loss_tv.backward()
+        if share:
+            loss.backward()
         with torch.no_grad():
             self._lpips_out.copy_(loss_lpips.detach())
         self.optimizer.skip_if_le = (self._lpips_out, hp.LPIPS_value_threshold)

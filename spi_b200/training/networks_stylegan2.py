@@ -47,7 +47,7 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     out_channels, in_channels, kh, kw = weight.shape
     misc.assert_shape(weight, [out_channels, in_channels, kh, kw])
     misc.assert_shape(x, [batch_size, in_channels, None, None])
-    misc.assert_shape(styles, [batch_size, in_channels])
+    assert styles.ndim == 2 and styles.shape[1] == in_channels and styles.shape[0] in (1, batch_size)     # 1: one style shared by the batch
     if fused_modconv and x.dtype == torch.float32:
         # one launch: w[n,o,i,k] = W*s (*rsqrt(sum (W s)^2 + 1e-8))  (spi_modulate_weights)
         w = modulate_weights(weight, styles, demodulate, layout='ohwi')
@@ -178,6 +178,8 @@ class SynthesisLayer(torch.nn.Module):
         assert noise_mode in ['random', 'const', 'none']
         in_resolution = self.resolution // self.up
         misc.assert_shape(x, [None, self.in_channels, in_resolution, in_resolution])
+        if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
+            w = w[:1]            # one latent broadcast over the batch: one weight set, one batched convolution
         styles = self.affine(w)
         noise = None
         if self.use_noise and noise_mode == 'random':
@@ -210,6 +212,8 @@ class ToRGBLayer(torch.nn.Module):
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
     def forward(self, x, w, fused_modconv=True):
+        if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
+            w = w[:1]
         styles = self.affine(w) * self.weight_gain
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)

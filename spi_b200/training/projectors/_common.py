@@ -104,7 +104,9 @@ class LatentProjector:
         ws = self.w_opt + rng.randn_like(self.w_opt) * self.w_noise_scale
         G = self.G
         if self.kind == 'mir':
-            out = G.synthesis(ws.repeat(2, 1, 1), self.target_camera, noise_mode='const')
+            # both views use the same latent: an expanded view lets the generator evaluate the tri-plane backbone once
+            ws2 = ws.expand(2, -1, -1) if global_config.share_backbone else ws.repeat(2, 1, 1)
+            out = G.synthesis(ws2, self.target_camera, noise_mode='const')
             img = out['image']
             dist = self.lpips_func(img[:1], self.target) + self.lpips_func(img[1:], self.target_m) * self.weight_m
         elif self.kind == 'sgw+':

@@ -28,7 +28,7 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
                                      use_fp16=use_fp16, conv_clamp=(256 if use_fp16 else None), **block_kwargs)
 
     def forward(self, rgb, x, ws, **block_kwargs):
-        ws = ws[:, -1:, :].repeat(1, 3, 1)
+        ws = ws[:, -1:, :].expand(-1, 3, -1)        # a view: keeps a broadcast batch (stride 0) recognisable downstream
         if x.shape[-1] != self.input_resolution:
             size = (self.input_resolution, self.input_resolution)
             x = torch.nn.functional.interpolate(x, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)

@@ -40,7 +40,11 @@ class TriPlaneGenerator(torch.nn.Module):
                                      truncation_cutoff=truncation_cutoff, update_emas=update_emas)
 
     def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
-                  use_cached_backbone=False, **synthesis_kwargs):
+                  use_cached_backbone=False, need_image=True, **synthesis_kwargs):
+        """triplane.py:53-89.  Two execution facts the reference leaves on the table (results identical):
+        the backbone output does not depend on the camera, so when `ws` is one latent broadcast over N views (an expanded
+        view, `ws.stride(0) == 0`) the tri-planes are synthesised ONCE and shared by all views; and `need_image=False`
+        skips the super-resolution network for callers that only consume `image_depth` (rot_bbox_cx_coach.py:133-139)."""
         cam2world_matrix = c[:, :16].view(-1, 4, 4)
         intrinsics = c[:, 16:25].view(-1, 3, 3)
         if neural_rendering_resolution is None:
@@ -49,10 +53,11 @@ class TriPlaneGenerator(torch.nn.Module):
             self.neural_rendering_resolution = neural_rendering_resolution
         ray_origins, ray_directions = self.ray_sampler(cam2world_matrix, intrinsics, neural_rendering_resolution)
         N, M, _ = ray_origins.shape
+        shared = ws.shape[0] > 1 and ws.stride(0) == 0
         if use_cached_backbone and self._last_planes is not None:
             planes = self._last_planes
         else:
-            planes = self.backbone.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)
+            planes = self.backbone.synthesis(ws[:1] if shared else ws, update_emas=update_emas, **synthesis_kwargs)
         if cache_backbone:
             self._last_planes = planes
         planes = planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1])
@@ -63,6 +68,8 @@ class TriPlaneGenerator(torch.nn.Module):
         feature_image = feature_samples.reshape(N, H, W, feature_samples.shape[-1]).permute(0, 3, 1, 2)
         depth_image = depth_samples.permute(0, 2, 1).reshape(N, 1, H, W)
         rgb_image = feature_image[:, :3]
+        if not need_image:
+            return {'image': None, 'image_raw': rgb_image, 'image_depth': depth_image}
         sr_image = self.superresolution(rgb_image, feature_image, ws, noise_mode=self.rendering_kwargs['superresolution_noise_mode'],
                                         **{k: synthesis_kwargs[k] for k in synthesis_kwargs.keys() if k != 'noise_mode'})
         return {'image': sr_image, 'image_raw': rgb_image, 'image_depth': depth_image}

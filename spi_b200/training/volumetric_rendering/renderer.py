@@ -60,8 +60,10 @@ class _RenderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, planes, w1, b1, w2, b2, origins, dirs, jitter, u, opts):
         lib = _lib.load()
-        n, _, h, w = planes.shape
-        r = origins.shape[1]
+        np_, _, h, w = planes.shape
+        n, r = origins.shape[0], origins.shape[1]
+        assert np_ in (1, n), 'planes batch must be 1 (shared by all views) or match the number of cameras'
+        plane_bs = 0 if (np_ == 1 and n > 1) else h * w * 96
         dc, df = opts['dc'], opts['df']
         dev = planes.device
         feat = torch.empty(n, r, 32, device=dev)
@@ -74,12 +76,12 @@ class _RenderFn(torch.autograd.Function):
         _lib.check(lib.spi_render_forward(
             _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(jitter), _lib.ptr(u), _lib.ptr(w1), _lib.ptr(b1),
             _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(feat), _lib.ptr(depth), _lib.ptr(wsum), _lib.ptr(depths_all),
-            None, _lib.ptr(minmax), n, r, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
+            None, _lib.ptr(minmax), n, r, plane_bs, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
             int(opts['disparity']), _lib.stream()))
         if KERNEL_TIMER is not None:
             KERNEL_TIMER.stop('render_fwd')
         ctx.save_for_backward(planes, w1, b1, w2, b2, origins, dirs, depths_all, minmax)
-        ctx.opts = opts
+        ctx.opts, ctx.plane_bs = opts, plane_bs
         ctx.mark_non_differentiable(wsum)
         return feat, depth, wsum
 
@@ -88,8 +90,9 @@ class _RenderFn(torch.autograd.Function):
         planes, w1, b1, w2, b2, origins, dirs, depths_all, minmax = ctx.saved_tensors
         opts = ctx.opts
         lib = _lib.load()
-        n, _, h, w = planes.shape
-        r = origins.shape[1]
+        _, _, h, w = planes.shape
+        n, r = origins.shape[0], origins.shape[1]
+        plane_bs = ctx.plane_bs
         dc, df = opts['dc'], opts['df']
         need_planes = ctx.needs_input_grad[0]
         need_dec = any(ctx.needs_input_grad[1:5])
@@ -106,14 +109,14 @@ class _RenderFn(torch.autograd.Function):
             _lib.check(lib.spi_render_backward(
                 _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
                 _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
-                _lib.ptr(g_planes), _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]), _lib.ptr(sc[3]), n, r, h, w, dc, df,
+                _lib.ptr(g_planes), _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]), _lib.ptr(sc[3]), n, r, plane_bs, h, w, dc, df,
                 opts['box_warp'], _lib.stream()))
             gw = _decoder_grads(sc, rows, opts['lr_mul'])
         else:
             _lib.check(lib.spi_render_backward(
                 _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
                 _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
-                _lib.ptr(g_planes), None, None, None, None, n, r, h, w, dc, df, opts['box_warp'], _lib.stream()))
+                _lib.ptr(g_planes), None, None, None, None, n, r, plane_bs, h, w, dc, df, opts['box_warp'], _lib.stream()))
             gw = (None, None, None, None)
         if KERNEL_TIMER is not None:
             KERNEL_TIMER.stop('render_bwd')

@@ -239,3 +239,43 @@ def test_w_projectors_vs_oracle(kind, gen_sd, lpips_mod, nets):
         assert abs(float(out['dist']) / ref_infos[i]['dist'] - 1) < 5e-3
     assert p.result().shape == (1, 14, 512)
     assert rel_l2(p.result(), ref.result()) < 1e-3
+
+
+def test_shared_backbone_equals_per_view_evaluation(gen_sd, lpips_mod, cx_mod):
+    """The i%4==0 iteration with the camera-independent backbone evaluated once (default) must give the same losses and
+    gradients as the reference's literal structure (backbone re-evaluated for each of the 13 views, four backward calls)."""
+    from spi_b200.configs import global_config, hyperparameters as hp
+    from spi_b200.training.coaches.rot_bbox_cx_coach import SPIState
+    from spi_b200.utils import rng
+    rk = OG.RENDERING_DEFAULTS
+    image, camera = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
+    grads, lps = [], []
+    for share in (True, False):
+        global_config.share_backbone = share
+        try:
+            coach = make_coach('RotBbox', gen_sd, lpips_mod, cx_mod)
+            hp.pt_rot_lambda, hp.pt_mirror_rot_lambda, hp.pt_depth_lambda, hp.pt_tv_lambda = 0.1, 0.05, 1.0, 0.0
+            src = OL.NoiseSource(77)
+            w = weights.w_pivot(5).cuda().requires_grad_(True)
+            jit, u = src.render(1, 128 * 128, rk)
+            coach.G.renderer.inject_noise(jit.cuda(), u.cuda())
+            for which in ('G', 'G', 'G', 'O'):
+                if which == 'G' or True:
+                    pass
+            for k in range(3):
+                r = src.rand(4, 2)
+                rng.inject(r[:, 0:1].clone(), r[:, 1:2].clone())
+                jit, u = src.render(4, 128 * 128, rk)
+                coach.G.renderer.inject_noise(jit.cuda(), u.cuda())
+            jit, u = src.render(4, 128 * 128, rk)
+            coach.original_G.renderer.inject_noise(jit.cuda(), u.cuda())
+            st = SPIState(image, camera, weights.parsing_mask().cuda(), weights.landmarks68().cuda())
+            lp, stepped = coach.train_step(0, st, w)
+            assert stepped and rng.pending() == 0
+            lps.append(float(lp))
+            grads.append((coach.optimizer.grads.clone(), w.grad.clone()))
+        finally:
+            global_config.share_backbone = True
+    assert abs(lps[0] / lps[1] - 1) < 1e-4
+    assert rel_l2(grads[0][0], grads[1][0]) < 2e-2          # TF32 contractions, different summation order
+    assert rel_l2(grads[0][1], grads[1][1]) < 2e-2
