@@ -335,6 +335,7 @@ def run_ours(args):
                 'config': {'workload': 'configs[1]: single 512^2 image per GPU, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
                            'execution': 'each iteration replayed as a captured CUDA graph; roofline kernel timed with CUDA events in an eager pass of the same K steps',
                            'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': f'{k // 3} mir + {k - k // 3} RotBbox iterations',
+                           'dedup': 'views of one iteration share w_pivot: the camera-independent tri-plane backbone is evaluated once per iteration and the SR net is skipped for the depth-only views (identical results, tests/test_gpu_loop.py::test_shared_backbone_equals_per_view_evaluation); global_config.share_backbone=False restores the literal structure',
                            'l2_policy': 'per-step working set (weights + activations, > 1 GB) exceeds the 126 MB L2', 'images_per_gpu': 1},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line))
