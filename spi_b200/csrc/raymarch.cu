@@ -1179,7 +1179,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
 #pragma unroll
                 for (int nt = 0; nt < 8; nt++)
 #pragma unroll
-                    for (int j = 0; j < 4; j++) dh[mt][nt][j] *= (1.f - __expf(-hid[mt][nt][j]));      // softplus' = 1 - exp(-softplus)
+                    for (int j = 0; j < 4; j++) dh[mt][nt][j] *= (1.f - mma::ex2_ftz(-1.4426950408889634f * hid[mt][nt][j]));      // softplus' = 1 - exp(-softplus)
             if (p.sc_dpre) {
 #pragma unroll
                 for (int mt = 0; mt < 2; mt++)

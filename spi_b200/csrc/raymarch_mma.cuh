@@ -32,19 +32,20 @@ struct DecMBwd {               // extra for the backward pass
     float w2t[NH * W2TS];      // [h][o]
 };
 
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
-}
+// hi/lo split for 3xTF32.  `cvt.rna.tf32.f32` is emulated on sm_100 (FSETP + IADD3 + SEL + LOP3 per conversion, 9
+// instructions per split -- 2.5x the HMMA count of a tile); a truncating split is 2 instructions: hi = x with the 13 low
+// mantissa bits cleared, lo = x - hi (exact).  The tensor core reads only the top 19 bits of a tf32 operand, so lo goes in
+// unmasked; the dropped terms (lo*lo and lo's own truncation) are <= 2^-20 relative.
 __device__ __forceinline__ void split(float x, uint32_t& hi, uint32_t& lo) {
-    hi = to_tf32(x);
-    lo = to_tf32(x - __uint_as_float(hi));
+    hi = __float_as_uint(x) & 0xffffe000u;
+    lo = __float_as_uint(x - __uint_as_float(hi));
 }
+// not `volatile`: the instruction is a pure function of its operands, and ptxas must be free to interleave the three
+// dependent MMAs of one accumulator with those of its neighbours
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
                                      uint32_t bl0, uint32_t bl1) {
@@ -134,9 +135,15 @@ __device__ __forceinline__ void fc2(const DecM* d, const float (&hid)[2][8][4], 
     }
 }
 
-// MUFU-based activations: |abs err| <~ 5e-7 on softplus / sigmoid outputs, 4x fewer instructions than log1pf(expf(x))
-__device__ __forceinline__ float softplus_fast(float x) { return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x))); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+// MUFU-based activations, one MUFU per transcendental (the .ftz forms skip the denormal pre/post-scaling that `__expf` /
+// `__logf` / `__fdividef` wrap around them): |abs err| <~ 5e-7 on softplus / sigmoid outputs.
+__device__ __forceinline__ float ex2_ftz(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_ftz(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_ftz(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float softplus_fast(float x) {
+    return fmaf(lg2_ftz(1.f + ex2_ftz(-1.4426950408889634f * fabsf(x))), 0.6931471805599453f, fmaxf(x, 0.f));
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_ftz(1.f + ex2_ftz(-1.4426950408889634f * x)); }
 __device__ __forceinline__ float rgb_act_fast(float x) { return sigmoid_fast(x) * (1.f + 2.f * 0.001f) - 0.001f; }
 
 __device__ __forceinline__ void softplus_inplace(float (&a)[2][8][4]) {

@@ -31,6 +31,11 @@ def main():
         print(f'total device time {tot / 1e3:.2f} ms over {len(kinds)} iterations; kernels launched: {sum(e.count for e in ev)}')
         for e in ev[:45]:
             print(f'{e.device_time_total / 1e3:9.3f} ms {100 * e.device_time_total / tot:5.1f}%  n={e.count:5d}  {e.key[:110]}')
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        with open(os.path.join(ROOT, 'gpurun_out', 'prof_' + name.split()[0] + '.txt'), 'w') as f:
+            f.write(f'total device time {tot / 1e3:.2f} ms over {len(kinds)} iterations; kernels launched: {sum(e.count for e in ev)}\n')
+            for e in ev:
+                f.write(f'{e.device_time_total / 1e3:9.3f} ms {100 * e.device_time_total / tot:5.1f}%  n={e.count:5d}  {e.key[:160]}\n')
         import time
         t0 = time.perf_counter()
         for k in kinds:
