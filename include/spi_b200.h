@@ -139,6 +139,24 @@ int spi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
  * w_projector.py:50,83); contiguous [planes, 2*out_h, 2*out_w] -> [planes, out_h, out_w]; backward != 0 runs the adjoint. */
 int spi_downsample2x(const float* x, float* y, long long planes, int out_h, int out_w, int backward, cudaStream_t stream);
 
+/* ---- dense convolution on tcgen05 tensor cores (opt-in engine; the default engine of the dense layers is cuDNN) ---------
+ * Implicit GEMM for the stride-1 'same' convolutions behind `_conv2d_wrapper` (eg3d/torch_utils/ops/conv2d_resample.py:30-43)
+ * as issued by `modulated_conv2d` (eg3d/training/networks_stylegan2.py:34-91), SuperresolutionHybrid8XDC
+ * (eg3d/training/superresolution.py:279-290) and the VGG taps (spi/criteria/lpips/networks.py:53-63).
+ * x [n,h,w,ci], y [n,h,w,co] channels-last fp32; w [g][co][kh][kw][ci] with g = n when per_sample else 1; correlation with
+ * zero padding (kh-1)/2; TF32 operands (round-to-nearest on the TMA load unless flags & 1), fp32 accumulation in tensor memory.
+ * Optional fused epilogue = SynthesisLayer tail (networks_stylegan2.py:320-329) / bias_act (bias_act.py:54):
+ *   y = clamp(act(acc + noise[h,w]*strength + bias[c]) * gain); act 0 linear, 1 relu, 2 lrelu(slope); clamp < 0 = off.
+ * spi_conv2d_tc_supported: ci, co multiples of 32, kh = kw in {1, 3}, w >= 16, h >= 8.
+ * spi_conv2d_tc_error: synchronises and returns non-zero if a pipeline barrier timed out since the last call (never hangs). */
+int spi_conv2d_tc_supported(int h, int w, int ci, int co, int kh, int kw);
+int spi_conv2d_tc(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int kh, int kw, int per_sample,
+                  const float* bias, const float* noise, const float* noise_strength, int act, float slope, float gain, float clamp,
+                  int flags, cudaStream_t stream);
+int spi_conv2d_tc_error(void);
+/* w [g][o][taps][i] -> wt [g][i][taps reversed][o]: weights of the data-gradient convolution (F.conv2d backward w.r.t. input). */
+int spi_conv_weight_flip_transpose(const float* w, float* wt, int g, int o, int taps, int i, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,3 +97,43 @@ def conv2d_per_sample(x, w, stride=1, padding=0, transpose=False, flip_weight=Tr
     if not flip_weight and (w.shape[-1] > 1 or w.shape[-2] > 1):
         w = w.flip([3, 4])
     return _PerSampleConv.apply(x, w, stride, padding, transpose)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Opt-in engine: hand-written tcgen05 + TMA implicit GEMM (spi_b200/csrc/conv_tc05.cu).  Measured on B200 it reaches
+# 225-375 TFLOP/s TF32 on the big layers against cuDNN's 540-750, so cuDNN stays the default engine.
+
+def conv2d_tc05(x, w, per_sample=False, bias=None, noise=None, noise_strength=None, act='linear', slope=0.2, gain=1.0, clamp=None):
+    """Stride-1 'same' correlation on the tcgen05 engine with the fused SynthesisLayer epilogue.
+    x [N,I,H,W] (channels-last), w [G,O,I,kh,kw] logical with memory order [G][O][kh][kw][I] (G = N if per_sample else 1)."""
+    from .. import _lib
+    _check(x)
+    lib = _lib.load()
+    n, ci, h, wd = x.shape
+    if w.ndim == 4:
+        w = w.unsqueeze(0)
+    g, co, _, kh, kw = w.shape
+    assert g == (n if per_sample else 1)
+    if not lib.spi_conv2d_tc_supported(h, wd, ci, co, kh, kw):
+        raise RuntimeError(f'conv2d_tc05: unsupported shape {tuple(x.shape)} x {tuple(w.shape)}')
+    x = x.contiguous(memory_format=torch.channels_last)
+    wk = w.permute(0, 1, 3, 4, 2).contiguous()                  # [G][O][kh][kw][I]
+    y = torch.empty(n, co, h, wd, device=x.device, dtype=x.dtype, memory_format=torch.channels_last)
+    code = {'linear': 0, 'relu': 1, 'lrelu': 2}[act]
+    _lib.check(lib.spi_conv2d_tc(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, kh, kw, int(per_sample), _lib.ptr(bias),
+                                 _lib.ptr(noise), _lib.ptr(noise_strength), code, float(slope), float(gain),
+                                 -1.0 if clamp is None else float(clamp), 0, _lib.stream()))
+    return y
+
+
+def conv2d_tc05_input_grad(gy, w, per_sample=False):
+    """Gradient of conv2d_tc05 (no epilogue) w.r.t. x: the same kernel on dy with the flipped / transposed weights."""
+    from .. import _lib
+    lib = _lib.load()
+    if w.ndim == 4:
+        w = w.unsqueeze(0)
+    g, co, ci, kh, kw = w.shape
+    wk = w.permute(0, 1, 3, 4, 2).contiguous()
+    wt = torch.empty(g, ci, kh, kw, co, device=w.device, dtype=w.dtype)
+    _lib.check(lib.spi_conv_weight_flip_transpose(_lib.ptr(wk), _lib.ptr(wt), g, co, kh * kw, ci, _lib.stream()))
+    return conv2d_tc05(gy, wt.permute(0, 1, 4, 2, 3), per_sample=per_sample)
