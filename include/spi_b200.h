@@ -41,7 +41,7 @@ int spi_bias_act_noise(const void* x, const void* b, void* y, const float* noise
                        float clamp, cudaStream_t stream);
 
 /* Gradient reductions of that epilogue in one pass over dx (channels-last fp32 [pixels, C]): db[c] = sum dx (bias_act.py:166),
- * dpix[h,w] = sum_{n,c} dx (gradient of the noise term), dstrength = sum dpix*noise.  Any output may be NULL. */
+ * dpix[h,w] = sum_{n,c} dx (gradient of the noise term), dstrength = sum dpix*noise.  Any output may be NULL; pixels = n * hw. */
 int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,
                              float* dstrength, cudaStream_t stream);
 
@@ -156,6 +156,17 @@ int spi_conv2d_tc(const float* x, const float* w, float* y, int n, int h, int wd
 int spi_conv2d_tc_error(void);
 /* w [g][o][taps][i] -> wt [g][i][taps reversed][o]: weights of the data-gradient convolution (F.conv2d backward w.r.t. input). */
 int spi_conv_weight_flip_transpose(const float* w, float* wt, int g, int o, int taps, int i, cudaStream_t stream);
+
+/* ---- stage-1 noise-buffer regulariser + re-normalisation: spi/training/projectors/mirror_projector.py:107-115,128-131 (same loops
+ *      in w_projector.py / w_plus_projector.py), all buffers in one launch each.
+ * table: device array of `count` records {float* x; long long out_off; int size; int pad} describing square fp32 [size,size]
+ * buffers (size a power of two <= 256).  forward: partial[b] = sum over the average-pool pyramid (down to size <= 8) of
+ * mean(x*roll(x,1,W))^2 + mean(x*roll(x,1,H))^2; stats[b][8][2] keeps the per-level means for backward.
+ * backward: (out_base + out_off_b)[i,j] = gout[0] * d(sum_b partial[b]) / d x_b[i,j].  renorm: x -= mean(x); x *= rsqrt(mean(x^2)). */
+int spi_noise_reg_forward(const void* table, int count, int max_size, float* partial, float* stats, cudaStream_t stream);
+int spi_noise_reg_backward(const void* table, int count, int max_size, const float* stats, const float* gout, float* out_base,
+                           cudaStream_t stream);
+int spi_noise_renorm(const void* table, int count, cudaStream_t stream);
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,85 @@ __global__ void __launch_bounds__(256) bias_act_kernel(BiasActParams p) {
     }
 }
 
+
+// ---- hot path: fp32, bias along the fastest dimension (channels-last rows of C floats) or no bias at all --------------------
+// Every thread keeps ONE column of 4 channels for its whole life (the total thread count is a multiple of the vectors per
+// row), so the bias vector sits in registers and the pixel index advances by a constant: no division or modulo in the loop.
+// Four independent 16-byte loads per operand are in flight per thread.
+template <int A, int G>
+__global__ void __launch_bounds__(256) bias_act_rows_kernel(BiasActParams p, unsigned c4, unsigned rows) {
+    const float* __restrict__ x = (const float*)p.x;
+    const float* __restrict__ yr = (const float*)p.yref;
+    float* __restrict__ y = (float*)p.y;
+    const unsigned T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned col = t % c4, rstep = T / c4;
+    unsigned row = t / c4;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (G == 0 && p.b) bv = *(const float4*)((const float*)p.b + 4 * col);
+    const bool nz = G == 0 && p.noise != nullptr;
+    const float st = nz ? p.noise_strength[0] : 0.f;
+    const unsigned hw = (unsigned)p.hw;
+    unsigned rhw = row % hw;
+    const unsigned hstep = rstep % hw;
+    constexpr int U = 4;
+    const unsigned hstep_u = (U * hstep) % hw;
+    while (row < rows) {
+        float4 vx[U], vy[U];
+        float nv[U];
+        unsigned rr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            rr[u] = row + u * rstep;
+            const bool ok = rr[u] < rows;
+            const size_t off = ((size_t)rr[u] * c4 + col) * 4;
+            vx[u] = ok ? ldg_stream((const float4*)(x + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (G == 1) vy[u] = ok ? ldg_stream((const float4*)(yr + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nv[u] = 0.f;
+            if (nz) {
+                unsigned h = rhw + u * hstep;            // < 4*hw: at most three conditional subtractions, no division
+                if (h >= 2 * hw) h -= 2 * hw;
+                if (h >= hw) h -= hw;
+                if (h >= hw) h -= hw;
+                nv[u] = ok ? __ldg(p.noise + h) * st : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rr[u] < rows) {
+                float4 o;
+                if (G == 0) {
+                    o.x = act_eval<float, A>(vx[u].x, bv.x + nv[u], 0.f, 0.f, 1.f, 0, p.alpha, p.gain, p.clamp);
+                    o.y = act_eval<float, A>(vx[u].y, bv.y + nv[u], 0.f, 0.f, 1.f, 0, p.alpha, p.gain, p.clamp);
+                    o.z = act_eval<float, A>(vx[u].z, bv.z + nv[u], 0.f, 0.f, 1.f, 0, p.alpha, p.gain, p.clamp);
+                    o.w = act_eval<float, A>(vx[u].w, bv.w + nv[u], 0.f, 0.f, 1.f, 0, p.alpha, p.gain, p.clamp);
+                } else {
+                    o.x = act_eval<float, A>(vx[u].x, 0.f, 0.f, vy[u].x, 1.f, 1, p.alpha, p.gain, p.clamp);
+                    o.y = act_eval<float, A>(vx[u].y, 0.f, 0.f, vy[u].y, 1.f, 1, p.alpha, p.gain, p.clamp);
+                    o.z = act_eval<float, A>(vx[u].z, 0.f, 0.f, vy[u].z, 1.f, 1, p.alpha, p.gain, p.clamp);
+                    o.w = act_eval<float, A>(vx[u].w, 0.f, 0.f, vy[u].w, 1.f, 1, p.alpha, p.gain, p.clamp);
+                }
+                stg_stream((float4*)(y + ((size_t)rr[u] * c4 + col) * 4), o);
+            }
+        }
+        row += U * rstep;
+        if (nz) {
+            unsigned h = rhw + hstep_u;
+            rhw = h >= hw ? h - hw : h;
+        }
+    }
+}
+
+template <int G>
+void* pick_rows_kernel(int act) {
+    switch (act) {
+        case 1: return (void*)bias_act_rows_kernel<1, G>;
+        case 2: return (void*)bias_act_rows_kernel<2, G>;
+        case 3: return (void*)bias_act_rows_kernel<3, G>;
+        case 5: return (void*)bias_act_rows_kernel<5, G>;
+    }
+    return nullptr;
+}
+
 template <class T>
 void* pick_kernel(int act) {
     switch (act) {
@@ -179,6 +258,31 @@ static int bias_act_impl(const void* x, const void* b, const void* xref, const v
     uintptr_t al = (uintptr_t)x | (uintptr_t)y | (uintptr_t)xref | (uintptr_t)yref | (uintptr_t)dy | (uintptr_t)b;
     BiasActParams p{x, b, xref, yref, dy, y, grad, act, alpha, gain, clamp, numel, b ? size_b : 1, b ? step_b : 1,
                     (al & 15) ? 1 : 0, noise, noise_strength, hw > 0 ? hw : 1, cl_c};
+    // hot path: fp32 rows (see bias_act_rows_kernel).  grad=1 of relu / lrelu / linear / sigmoid reads only dy and yref.
+    {
+        // grad = 1 of relu / lrelu / linear / sigmoid depends on dy and yref only (the bias enters through xref, which they ignore)
+        const bool g1 = grad == 1 && yref && !xref && !dy && !noise && (act == 1 || act == 2 || act == 3 || act == 5);
+        const bool g_ok = (grad == 0 && !xref && !yref && !dy) || g1;
+        long long c = 0;
+        if (g1) c = (numel % 128 == 0) ? 128 : 0;
+        else if (b) { if (step_b == 1 && size_b % 4 == 0 && (!noise || cl_c == size_b)) c = size_b; }
+        else c = noise ? ((cl_c > 0 && cl_c % 4 == 0) ? cl_c : 0) : ((numel % 128 == 0) ? 128 : 0);
+        void* rk = grad == 0 ? pick_rows_kernel<0>(act) : pick_rows_kernel<1>(act);
+        if (dtype == SPI_DT_F32 && g_ok && rk && c > 0 && numel % c == 0 && !(al & 15) && numel >= 4096) {
+            const unsigned c4 = (unsigned)(c / 4), rows = (unsigned)(numel / c);
+            unsigned need = c4, r256 = 256;                      // grid * 256 must be a multiple of c4
+            while (need % 2 == 0 && r256 % 2 == 0) { need /= 2; r256 /= 2; }
+            long long want = (numel / 4 + 256 * 4 - 1) / (256 * 4);
+            long long capb = (long long)spi_num_sms() * 8;
+            long long grid = want < capb ? want : capb;
+            grid = (grid + need - 1) / need * need;
+            void* args[] = {&p, (void*)&c4, (void*)&rows};
+            cudaError_t e = cudaLaunchKernel(rk, dim3((unsigned)grid), dim3(256), args, 0, stream);
+            SPI_COUNT_LAUNCH(1);
+            if (e != cudaSuccess) { spi_set_error("bias_act: %s", cudaGetErrorString(e)); return SPI_ERR_CUDA; }
+            return SPI_OK;
+        }
+    }
     const int block = 256;
     long long work = p.force_scalar ? numel : (numel + vec - 1) / vec;
     long long blocks = (work + block * 2 - 1) / (block * 2);
@@ -217,42 +321,65 @@ extern "C" int spi_bias_act_noise(const void* x, const void* b, void* y, const f
 namespace {
 
 constexpr int RG_MAXG = 8;     // channel groups per lane: C <= 4*32*8 = 1024
+constexpr int RG_U = 4;        // pixels in flight per warp
 
-__global__ void __launch_bounds__(256) epilogue_grad_reduce_kernel(const float* __restrict__ dx, long long pixels, int C, int HW,
+// A warp owns RG_U pixels (hw positions) at a time and walks the batch for them, so the per-pixel sum over (n, c) is complete
+// in registers and is stored once (no atomics, no memset); per-channel partials stay in registers for the whole kernel and are
+// combined through shared memory + one atomicAdd per channel per CTA.  NG = ceil(C / 128): float4 groups per lane (32-bit index
+// math, no predicates inside the unrolled loads for the common C % 128 == 0 case).
+template <int NG>
+__global__ void __launch_bounds__(256) epilogue_grad_reduce_kernel(const float* __restrict__ dx, int n, int C, int HW,
                                                                    const float* __restrict__ noise, float* __restrict__ db,
                                                                    float* __restrict__ dpix, float* __restrict__ dstrength) {
     extern __shared__ float sm[];                 // [8 warps][C]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int groups = C / 4;
-    float4 acc[RG_MAXG];
+    const int groups = C >> 2;
+    float4 acc[NG];
 #pragma unroll
-    for (int g = 0; g < RG_MAXG; g++) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int g = 0; g < NG; g++) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
     float ds = 0.f;
     const bool want_pix = (dpix != nullptr) || (dstrength != nullptr);
-    for (long long p = (long long)blockIdx.x * 8 + warp; p < pixels; p += (long long)gridDim.x * 8) {
-        const float4* row = (const float4*)(dx + p * C);
-        float ps = 0.f;
+    const int wstride = gridDim.x * 8 * RG_U;
+    for (int hw0 = (blockIdx.x * 8 + warp) * RG_U; hw0 < HW; hw0 += wstride) {
+        float ps[RG_U];
 #pragma unroll
-        for (int g = 0; g < RG_MAXG; g++) {
-            const int gi = lane + 32 * g;
-            if (gi < groups) {
-                float4 v = ldg_stream(row + gi);
-                acc[g].x += v.x; acc[g].y += v.y; acc[g].z += v.z; acc[g].w += v.w;
-                ps += (v.x + v.y) + (v.z + v.w);
+        for (int u = 0; u < RG_U; u++) ps[u] = 0.f;
+        for (int nn = 0; nn < n; nn++) {
+            float4 v[RG_U][NG];
+#pragma unroll
+            for (int u = 0; u < RG_U; u++) {
+                const bool ok = hw0 + u < HW;
+                const float4* row = (const float4*)(dx + ((size_t)nn * HW + hw0 + u) * C);
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    const int gi = lane + 32 * g;
+                    v[u][g] = (ok && gi < groups) ? ldg_stream(row + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
+#pragma unroll
+            for (int u = 0; u < RG_U; u++)
+#pragma unroll
+                for (int g = 0; g < NG; g++) {
+                    acc[g].x += v[u][g].x; acc[g].y += v[u][g].y; acc[g].z += v[u][g].z; acc[g].w += v[u][g].w;
+                    ps[u] += (v[u][g].x + v[u][g].y) + (v[u][g].z + v[u][g].w);
+                }
         }
         if (want_pix) {
-            ps = warp_sum(ps);
+#pragma unroll
+            for (int u = 0; u < RG_U; u++) ps[u] = warp_sum(ps[u]);
             if (lane == 0) {
-                const int hw = (int)(p % HW);
-                if (dpix) atomicAdd(dpix + hw, ps);
-                if (dstrength) ds += ps * noise[hw];
+#pragma unroll
+                for (int u = 0; u < RG_U; u++)
+                    if (hw0 + u < HW) {
+                        if (dpix) dpix[hw0 + u] = ps[u];
+                        if (dstrength) ds = fmaf(ps[u], noise[hw0 + u], ds);
+                    }
             }
         }
     }
     if (db) {
 #pragma unroll
-        for (int g = 0; g < RG_MAXG; g++) {
+        for (int g = 0; g < NG; g++) {
             const int gi = lane + 32 * g;
             if (gi < groups) *(float4*)(sm + warp * C + gi * 4) = acc[g];
         }
@@ -274,14 +401,27 @@ extern "C" int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c
     SPI_CHECK_ARG(dx && pixels >= 0 && c >= 4 && c % 4 == 0 && c <= 4 * 32 * RG_MAXG, "epilogue_grad_reduce: C must be a multiple of 4, <= 1024");
     SPI_CHECK_ARG(((uintptr_t)dx & 15) == 0, "epilogue_grad_reduce: dx must be 16-byte aligned");
     SPI_CHECK_ARG(!dstrength || noise, "epilogue_grad_reduce: noise map required for dstrength");
-    if (db) cudaMemsetAsync(db, 0, sizeof(float) * c, stream);
-    if (dpix) cudaMemsetAsync(dpix, 0, sizeof(float) * hw, stream);
-    if (dstrength) cudaMemsetAsync(dstrength, 0, sizeof(float), stream);
-    if (pixels == 0) return SPI_OK;
-    long long want = (pixels + 7) / 8;
+    if (hw <= 0) hw = 1;
+    SPI_CHECK_ARG(pixels % hw == 0 && pixels / hw <= 2147483647LL && pixels * c <= (1LL << 40), "epilogue_grad_reduce: pixels must be n * hw");
+    if (db && dstrength == db + c) cudaMemsetAsync(db, 0, sizeof(float) * (c + 1), stream);      // one fill when the caller packed them
+    else {
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * c, stream);
+        if (dstrength) cudaMemsetAsync(dstrength, 0, sizeof(float), stream);
+    }
+    if (pixels == 0) {
+        if (dpix) cudaMemsetAsync(dpix, 0, sizeof(float) * hw, stream);
+        return SPI_OK;
+    }
+    const int n = (int)(pixels / hw);
+    long long want = ((long long)hw + 8 * RG_U - 1) / (8 * RG_U);
     long long cap = (long long)spi_num_sms() * 8;
     int grid = (int)(want < cap ? want : cap);
-    epilogue_grad_reduce_kernel<<<grid, 256, sizeof(float) * 8 * c, stream>>>(dx, pixels, c, hw > 0 ? hw : 1, noise, db, dpix, dstrength);
+    const size_t smem = sizeof(float) * 8 * c;
+    const int ng = (c + 127) / 128;
+    if (ng <= 1) epilogue_grad_reduce_kernel<1><<<grid, 256, smem, stream>>>(dx, n, c, hw, noise, db, dpix, dstrength);
+    else if (ng <= 2) epilogue_grad_reduce_kernel<2><<<grid, 256, smem, stream>>>(dx, n, c, hw, noise, db, dpix, dstrength);
+    else if (ng <= 4) epilogue_grad_reduce_kernel<4><<<grid, 256, smem, stream>>>(dx, n, c, hw, noise, db, dpix, dstrength);
+    else epilogue_grad_reduce_kernel<8><<<grid, 256, smem, stream>>>(dx, n, c, hw, noise, db, dpix, dstrength);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("epilogue_grad_reduce");
     return SPI_OK;

@@ -38,9 +38,13 @@ def _fused_reductions(dx, want_db, noise=None, want_dpix=False, want_ds=False):
             and dx.is_contiguous(memory_format=torch.channels_last) and dx.data_ptr() % 16 == 0):
         return None
     n, c, h, w = dx.shape
-    db = torch.empty(c, device=dx.device) if want_db else None
+    if want_db and want_ds:                      # packed so the library zero-fills both with one memset
+        buf = torch.empty(c + 1, device=dx.device)
+        db, ds = buf[:c], buf[c]
+    else:
+        db = torch.empty(c, device=dx.device) if want_db else None
+        ds = torch.empty((), device=dx.device) if want_ds else None
     dpix = torch.empty(h, w, device=dx.device) if want_dpix else None
-    ds = torch.empty((), device=dx.device) if want_ds else None
     _lib.check(_lib.load().spi_epilogue_grad_reduce(_lib.ptr(dx), n * h * w, c, h * w, _lib.ptr(noise) if noise is not None else None,
                                                     _lib.ptr(db), _lib.ptr(dpix), ds.data_ptr() if ds is not None else None, _lib.stream()))
     return db, dpix, ds

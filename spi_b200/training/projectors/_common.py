@@ -15,23 +15,15 @@ import torch.nn.functional as F
 from ...configs import global_config
 from ...graphs import GraphedStep
 from ...optim import FlatAdam
+from ...ops import noise_reg
 from ...ops.resize import downsample2x
 from ...utils import rng
 from ...utils.camera_utils import cal_camera_weight, cal_mirror_c
 
 
 def noise_regulariser(noise_bufs):
-    """mirror_projector.py:107-115."""
-    reg_loss = 0.0
-    for v in noise_bufs:
-        noise = v[None, None, :, :]
-        while True:
-            reg_loss = reg_loss + (noise * torch.roll(noise, shifts=1, dims=3)).mean() ** 2
-            reg_loss = reg_loss + (noise * torch.roll(noise, shifts=1, dims=2)).mean() ** 2
-            if noise.shape[2] <= 8:
-                break
-            noise = F.avg_pool2d(noise, kernel_size=2)
-    return reg_loss
+    """mirror_projector.py:107-115 -- one fused launch for all buffers (spi_b200/ops/noise_reg.py)."""
+    return noise_reg.noise_regulariser(list(noise_bufs))
 
 
 def area_256(img):
@@ -122,9 +114,7 @@ class LatentProjector:
         loss.backward()
         self.optimizer.step(in_graph=True)
         with torch.no_grad():
-            for buf in self.noise_bufs.values():
-                buf -= buf.mean()
-                buf *= buf.square().mean().rsqrt()
+            noise_reg.renormalise_noise_(self.noise_bufs.values())         # mirror_projector.py:128-131
             self._out['loss'].copy_(loss.detach())
             self._out['dist'].copy_(dist.detach())
             if self._out['image'] is None:
