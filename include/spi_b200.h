@@ -154,6 +154,8 @@ int spi_conv2d_tc(const float* x, const float* w, float* y, int n, int h, int wd
                   const float* bias, const float* noise, const float* noise_strength, int act, float slope, float gain, float clamp,
                   int flags, cudaStream_t stream);
 int spi_conv2d_tc_error(void);
+/* same flag for every tcgen05 kernel of the library (convolution, fused renderer): synchronises, returns and clears it */
+int spi_tc_error(void);
 /* w [g][o][taps][i] -> wt [g][i][taps reversed][o]: weights of the data-gradient convolution (F.conv2d backward w.r.t. input). */
 int spi_conv_weight_flip_transpose(const float* w, float* wt, int g, int o, int taps, int i, cudaStream_t stream);
 

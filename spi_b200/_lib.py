@@ -43,6 +43,7 @@ _SIGS = {
     'spi_conv2d_tc_supported': [c_int] * 6,
     'spi_conv2d_tc': [c_void_p] * 3 + [c_int] * 8 + [c_void_p] * 3 + [c_int] + [c_float] * 3 + [c_int, c_void_p],
     'spi_conv2d_tc_error': [],
+    'spi_tc_error': [],
     'spi_conv_weight_flip_transpose': [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p],
 }
 

@@ -16,6 +16,8 @@
 #define SPI_DT_F64 2
 
 void spi_set_error(const char* fmt, ...);
+int* spi_tc_err_flag();          // device int, non-zero after a tcgen05 pipeline barrier timed out (lib.cu)
+extern "C" int spi_tc_error();
 
 #define SPI_CHECK_ARG(cond, ...)                      \
     do {                                              \

@@ -242,15 +242,6 @@ bool make_map(CUtensorMap* m, const void* ptr, int rank, const cuuint64_t* dims,
     return r == CUDA_SUCCESS;
 }
 
-int* err_flag() {
-    static int* flag = nullptr;
-    if (!flag) {
-        cudaMalloc(&flag, sizeof(int));
-        cudaMemset(flag, 0, sizeof(int));
-    }
-    return flag;
-}
-
 template <int BN, int STAGES>
 int launch(const CUtensorMap& mx, const CUtensorMap& mw, const CUtensorMap& my, const ConvParams& p, int max_ctas, cudaStream_t stream) {
     using S = Smem<BN, STAGES>;
@@ -311,21 +302,15 @@ extern "C" int spi_conv2d_tc(const float* x, const float* w, float* y, int n, in
     p.per_sample = per_sample ? 1 : 0;
     p.bias = bias; p.noise = noise; p.noise_strength = noise_strength;
     p.act = act; p.slope = slope; p.gain = gain; p.clamp = clamp;
-    p.err = err_flag();
+    p.err = spi_tc_err_flag();
     const int sms = spi_num_sms();
     if (bn == 256) return launch<256, 4>(mx, mw, my, p, sms, stream);
     if (bn == 128) return launch<128, 6>(mx, mw, my, p, sms, stream);
     return launch<64, 8>(mx, mw, my, p, sms, stream);
 }
 
-/* non-zero if any spi_conv2d_tc launch since the last call hit a barrier time-out (synchronises the device) */
-extern "C" int spi_conv2d_tc_error(void) {
-    int v = 0;
-    cudaDeviceSynchronize();
-    cudaMemcpy(&v, err_flag(), sizeof(int), cudaMemcpyDeviceToHost);
-    if (v) cudaMemset(err_flag(), 0, sizeof(int));
-    return v;
-}
+/* kept for callers of the convolution alone: same flag as spi_tc_error() */
+extern "C" int spi_conv2d_tc_error(void) { return spi_tc_error(); }
 
 extern "C" int spi_conv_weight_flip_transpose(const float* w, float* wt, int g, int o, int taps, int i, cudaStream_t stream) {
     SPI_CHECK_ARG(w && wt && g > 0 && o > 0 && taps > 0 && i > 0, "spi_conv_weight_flip_transpose: bad arguments");

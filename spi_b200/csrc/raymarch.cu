@@ -28,6 +28,7 @@
 // The backward kernel re-derives everything from depths_all and scatters plane gradients with red.global.add.v4.f32.
 #include "common.cuh"
 #include "raymarch_mma.cuh"
+#include "tc05.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -1004,6 +1005,8 @@ __global__ void __launch_bounds__(WARPS * 32) render_fwd_mma_kernel(RenderParams
     if (lane == 0 && lmax != 0) { atomicMin(p.minmax, lmin); atomicMax(p.minmax + 1, lmax); }
 }
 
+#include "raymarch_tc.cuh"
+
 // scatter of a 32-row feature-gradient tile (row stride mma::FS); lane = row; `valid` rows only
 __device__ __forceinline__ void warp_scatter_tile(float* __restrict__ gp, const float* dft, int* s_off, float* s_w, int W, int H, float x,
                                                   float y, float z, float scale, bool valid, int lane) {
@@ -1269,11 +1272,24 @@ extern "C" int spi_render_forward(const float* planes, const float* origins, con
     SPI_CHECK_ARG(jitter && (df == 0 || u) && feat && depth && wsum && minmax, "render_forward: null pointer");
     if (n == 0) return SPI_OK;
     const bool simt = getenv("SPI_RENDER_SIMT") != nullptr;      // v1 SIMT kernels kept for A/B comparison
+    long long rays = (long long)n * rays_per_image;
+    // tcgen05 kernel: one 128-sample decoder tile per round, D2 of both rounds resident in tensor memory (<= 32 + 32 samples per ray)
+    if (!simt && getenv("SPI_RENDER_MMA") == nullptr && dc <= 32 && df <= 32) {
+        const size_t smem_tc = tcr::smem_bytes(dc, df);
+        cudaFuncSetAttribute(tcr::render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
+        long long groups = (rays + 3) / 4, cap = 2LL * spi_num_sms();
+        int grid = (int)(groups < cap ? groups : cap);
+        minmax_init_kernel<<<1, 1, 0, stream>>>(minmax);
+        tcr::render_fwd_tc_kernel<<<grid, tcr::TC_THREADS, smem_tc, stream>>>(p, spi_tc_err_flag());
+        depth_clamp_kernel<<<cdiv(rays, 256) > 1184 ? 1184 : cdiv(rays, 256), 256, 0, stream>>>(depth, minmax, rays);
+        SPI_COUNT_LAUNCH(3);
+        SPI_LAUNCH_CHECK("render_forward");
+        return SPI_OK;
+    }
     size_t smem = simt ? fwd_smem_bytes(dc, df) : fwd2_smem_bytes(dc, df);
     SPI_CHECK_ARG(smem <= 227 * 1024, "render_forward: %d+%d samples per ray need %zu B of shared memory (> 227 KB)", dc, df, smem);
     auto kern = simt ? render_fwd_kernel : render_fwd_mma_kernel;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long rays = (long long)n * rays_per_image;
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
     if (occ < 1) occ = 1;

@@ -1,0 +1,310 @@
+// Fused renderer forward on the 5th-generation tensor cores (tcgen05 + TMEM).  Included by raymarch.cu inside its anonymous
+// namespace (uses RenderParams, Ray, corners / plane_coords, the per-ray warp stages and the MUFU activations).
+//
+// Same arithmetic as render_fwd_mma_kernel (renderer.py:88-253, ray_marcher.py:25-57, triplane.py:123-135), different machine
+// mapping.  A CTA of 4 warps owns 4 rays at a time, one ray per warp, one sample per lane, so the 4 x 32 samples of a "round"
+// (coarse samples, then importance samples) form ONE M = 128 decoder tile:
+//
+//   gather     8 lanes per texel line (128 B), features -> hi / lo TF32 halves -> shared memory, SWIZZLE_128B K-major rows
+//   layer 1    D1[128x64] = F W1^T   12 tcgen05.mma (3xTF32: hi*hi + lo*hi + hi*lo), accumulator in tensor memory
+//   softplus   tcgen05.ld -> +b1, softplus (2 MUFU) -> hi / lo -> tcgen05.st back to TMEM (the hidden layer never touches smem)
+//   layer 2    D2[128x48] = H W2^T   24 tcgen05.mma with the A operand read from TMEM; ALL 33 outputs at once
+//   D2 of both rounds stays in TMEM; sigma (one column) feeds the per-ray stages (weights, inverse-CDF sampling, merge by rank),
+//   and once the final weights are known the colours are read back, activated and composited with a 31-shuffle transpose-reduce.
+//
+// Compared with the mma.sync kernel every sample goes through the decoder exactly once (no sigma-only pre-pass + recompute), the
+// SM's issue slots are left to the gather and the activations, and nothing of size [R*D, 32] is stored anywhere.
+// TMEM columns (256 per CTA, two CTAs per SM): [0,48) D2 coarse | [64,112) D2 fine | [128,192) D1, then H_hi in place | [192,256) H_lo.
+// Rows of W2 are permuted so that the 32 colours are columns 0..31 and sigma is column 32.
+#pragma once
+
+namespace tcr {
+
+using namespace tc05;
+
+constexpr int TC_THREADS = 128;
+constexpr int A_TILE = 128 * 128;                 // bytes of one 128 x 32 fp32 operand tile
+constexpr int W1_TILE = 64 * 128;
+constexpr int W2_SLAB = 48 * 128;                 // one K slab (32 hidden units) of W2
+constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE, OFF_W1_HI = 2 * A_TILE, OFF_W1_LO = OFF_W1_HI + W1_TILE;
+constexpr int OFF_W2_HI = OFF_W1_LO + W1_TILE, OFF_W2_LO = OFF_W2_HI + 2 * W2_SLAB;
+constexpr int OFF_BIAS = OFF_W2_LO + 2 * W2_SLAB;  // b1[64], b2 permuted [48]
+constexpr int OFF_BARS = OFF_BIAS + (64 + 48) * 4;
+constexpr int OFF_WARP = OFF_BARS + 64;            // per-warp scratch starts here (16-byte aligned)
+constexpr uint32_t TM_COLS = 256, TM_D2 = 0, TM_D2_STRIDE = 64, TM_H_HI = 128, TM_H_LO = 192;
+
+__host__ __device__ inline size_t warp_floats(int dc, int df) {
+    const int D = dc + df;
+    size_t f = (size_t)dc /*dcs*/ + 32 /*sigc*/ + 32 /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall, sigm, w*/ + dc + df /*pos*/ + 2 * 32 * 12 + 2 /*int2 alignment*/;
+    return (f + 3) & ~(size_t)3;
+}
+__host__ __device__ inline size_t smem_bytes(int dc, int df) { return OFF_WARP + 4 * warp_floats(dc, df) * sizeof(float) + 1024; }
+
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& v) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+    v = __uint_as_float(r);
+}
+
+// Warp-cooperative gather of this warp's 32 samples into rows row0 .. row0+31 of the A tiles (hi / lo halves, swizzled).
+// Every lane publishes its own sample's 12 (texel offset, weight) pairs; then 8 lanes serve one sample, each owning 4 of the 32
+// channels, so a texel read is one coalesced 128-byte line.  Out-of-range corners read texel 0 with weight 0 (grid_sample's
+// zeros padding) so the inner loop has no branches and all 12 loads of a sample are in flight together.
+__device__ __forceinline__ void gather_rows(const float* __restrict__ pl, int W, int H, float x, float y, float z, float scale, bool valid,
+                                            uint8_t* a_hi, uint8_t* a_lo, int row0, int2* s_ow, int lane) {
+    float gc[3][2];
+    plane_coords(x, y, z, scale, gc);
+#pragma unroll
+    for (int pp = 0; pp < 3; pp++) {
+        Corner c;
+        corners(gc[pp][0], gc[pp][1], W, H, c);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const bool in = valid && c.off[q] >= 0;
+            s_ow[lane * 12 + pp * 4 + q] = make_int2(in ? c.off[q] + pp * NF : 0, __float_as_int(in ? c.w[q] * (1.f / 3.f) : 0.f));
+        }
+    }
+    __syncwarp();
+    const int sub = lane & 7, grp = lane >> 3;
+    const float4* pls = reinterpret_cast<const float4*>(pl) + sub;
+#pragma unroll 2
+    for (int k = 0; k < 8; k++) {
+        const int smp = grp + 4 * k;
+        float4 v[12];
+        float ww[12];
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            const int2 ow = s_ow[smp * 12 + c];
+            ww[c] = __int_as_float(ow.y);
+            v[c] = __ldg(pls + (ow.x >> 2));
+        }
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 12; c++) {
+            acc.x = fmaf(v[c].x, ww[c], acc.x); acc.y = fmaf(v[c].y, ww[c], acc.y); acc.z = fmaf(v[c].z, ww[c], acc.z); acc.w = fmaf(v[c].w, ww[c], acc.w);
+        }
+        uint4 h, l;
+        split(acc.x, h.x, l.x); split(acc.y, h.y, l.y); split(acc.z, h.z, l.z); split(acc.w, h.w, l.w);
+        const uint32_t o = swz(row0 + smp, sub);
+        *reinterpret_cast<uint4*>(a_hi + o) = h;
+        *reinterpret_cast<uint4*>(a_lo + o) = l;
+    }
+    __syncwarp();
+}
+
+// v[c] (c = 0..31) per lane -> lane c returns sum over the 32 lanes of v[c]  (31 shuffles)
+__device__ __forceinline__ float transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16, n = 16; off >= 1; off >>= 1, n >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const float send = up ? v[i] : v[i + n];
+            const float keep = up ? v[i + n] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+    return v[0];
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderParams p, int* err) {
+    extern __shared__ uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* sm = raw + (base - smem_u32(raw));
+    uint8_t* a_hi = sm + OFF_A_HI; uint8_t* a_lo = sm + OFF_A_LO;
+    uint8_t* w1_hi = sm + OFF_W1_HI; uint8_t* w1_lo = sm + OFF_W1_LO;
+    uint8_t* w2_hi = sm + OFF_W2_HI; uint8_t* w2_lo = sm + OFF_W2_LO;
+    float* b1s = reinterpret_cast<float*>(sm + OFF_BIAS);
+    float* b2s = b1s + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BARS);
+    uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int dc = p.dc, df = p.df, D = dc + df;
+    float* b = reinterpret_cast<float*>(sm + OFF_WARP) + warp * warp_floats(dc, df);
+    float* dcs = b; b += dc;
+    float* sigc = b; b += 32;
+    float* sigf = b; b += 32;
+    float* fine = b; b += df;
+    float* cdf = b; b += dc;
+    float* dall = b; b += D;
+    float* sigm = b; b += D;
+    float* w = b; b += D;
+    int* pos_c = (int*)b; b += dc;
+    int* pos_f = (int*)b; b += df;
+    int2* g_ow = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(b) + 7) & ~(uintptr_t)7);
+
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    if (warp == 0) { __syncwarp(); tmem_alloc(slot, TM_COLS); }
+    // decoder -> shared memory: gains folded, hi / lo split, canonical K-major SWIZZLE_128B rows
+    for (int i = tid; i < 64 * 32; i += TC_THREADS) {
+        const int n = i >> 5, k = i & 31;
+        uint32_t h, l;
+        split(p.w1[i] * p.w1_gain, h, l);
+        const uint32_t o = swz(n, k >> 2) + (k & 3) * 4;
+        *reinterpret_cast<uint32_t*>(w1_hi + o) = h;
+        *reinterpret_cast<uint32_t*>(w1_lo + o) = l;
+    }
+    for (int i = tid; i < 48 * 64; i += TC_THREADS) {
+        const int n = i >> 6, k = i & 63, kk = k & 31;
+        const int o_src = n < 32 ? n + 1 : (n == 32 ? 0 : -1);        // colours first, sigma in column 32
+        uint32_t h, l;
+        split(o_src >= 0 ? p.w2[o_src * 64 + k] * p.w2_gain : 0.f, h, l);
+        const uint32_t o = (k >> 5) * W2_SLAB + swz(n, kk >> 2) + (kk & 3) * 4;
+        *reinterpret_cast<uint32_t*>(w2_hi + o) = h;
+        *reinterpret_cast<uint32_t*>(w2_lo + o) = l;
+    }
+    if (tid < 64) b1s[tid] = p.b1[tid] * p.b_gain;
+    if (tid < 48) b2s[tid] = tid < 32 ? p.b2[tid + 1] * p.b_gain : (tid == 32 ? p.b2[0] * p.b_gain : 0.f);
+    fence_async_smem();
+    fence_before();
+    __syncthreads();
+    fence_after();
+    const uint32_t tm = *slot;
+    const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t id1 = idesc_tf32(128, 64), id2 = idesc_tf32(128, 48);
+
+    const int R = p.R;
+    const long long total = (long long)p.n * R;
+    const long long groups = (total + 3) >> 2;
+    const float scale = 2.f / p.box_warp;
+    uint32_t ph0 = 0, ph1 = 0;
+    int lmin = 0x7f800000, lmax = 0;
+    bool ok = true;
+
+    for (long long grp = blockIdx.x; grp < groups && ok; grp += gridDim.x) {
+        const long long ray = grp * 4 + warp;
+        const bool live = ray < total;
+        const long long rr = live ? ray : total - 1;                    // dead warps shadow the last ray (no stores)
+        const float* pl = p.planes + (size_t)(rr / R) * p.plane_bs;
+        Ray r;
+        r.ox = p.origins[rr * 3]; r.oy = p.origins[rr * 3 + 1]; r.oz = p.origins[rr * 3 + 2];
+        r.dx = p.dirs[rr * 3]; r.dy = p.dirs[rr * 3 + 1]; r.dz = p.dirs[rr * 3 + 2];
+        const int rounds = df > 0 ? 2 : 1;
+        for (int round = 0; round < rounds; round++) {
+            // ---- sample positions + gather
+            float d = 0.f;
+            bool valid;
+            if (round == 0) {
+                valid = lane < dc;
+                if (valid) { d = coarse_depth(p, lane, p.jitter[rr * dc + lane]); dcs[lane] = d; }
+            } else {
+                valid = lane < df;
+                if (valid) d = fine[lane];
+            }
+            gather_rows(pl, p.W, p.H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, valid, a_hi, a_lo, warp * 32, g_ow, lane);
+            fence_async_smem();
+            fence_before();
+            __syncthreads();
+            // ---- layer 1 on the tensor core
+            if (tid == 0) {
+                fence_after();
+                uint32_t acc = 0;
+#pragma unroll
+                for (int pass = 0; pass < 3; pass++) {
+                    const uint32_t a = smem_u32(pass == 1 ? a_lo : a_hi), wq = smem_u32(pass == 2 ? w1_lo : w1_hi);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) { mma_ss(tm + TM_H_HI, desc_sw128(a + ks * 32), desc_sw128(wq + ks * 32), id1, acc); acc = 1; }
+                }
+                commit(&bars[0]);
+            }
+            if (!mbar_wait_bounded(&bars[0], ph0)) { atomicExch(err, 1); ok = false; }
+            ph0 ^= 1;
+            fence_after();
+            // ---- bias + softplus, hi / lo halves back into TMEM (H_hi overwrites D1 in place)
+#pragma unroll
+            for (int half = 0; half < 2; half++) {
+                float v[32];
+                uint32_t hh[32], hl[32];
+                tmem_ld32(tlane + TM_H_HI + half * 32, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 32; c++) split(mma::softplus_fast(v[c] + b1s[half * 32 + c]), hh[c], hl[c]);
+                tmem_st32(tlane + TM_H_HI + half * 32, hh);
+                tmem_st32(tlane + TM_H_LO + half * 32, hl);
+            }
+            tmem_wait_st();
+            fence_before();
+            __syncthreads();
+            // ---- layer 2, A from tensor memory
+            if (tid == 0) {
+                fence_after();
+                uint32_t acc = 0;
+                const uint32_t dcol = tm + TM_D2 + round * TM_D2_STRIDE;
+#pragma unroll
+                for (int pass = 0; pass < 3; pass++) {
+                    const uint32_t a = tm + (pass == 1 ? TM_H_LO : TM_H_HI), wq = smem_u32(pass == 2 ? w2_lo : w2_hi);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ks++) {
+                        mma_ts(dcol, a + ks * 8, desc_sw128(wq + (ks >> 2) * W2_SLAB + (ks & 3) * 32), id2, acc);
+                        acc = 1;
+                    }
+                }
+                commit(&bars[1]);
+            }
+            if (!mbar_wait_bounded(&bars[1], ph1)) { atomicExch(err, 2); ok = false; }
+            ph1 ^= 1;
+            fence_after();
+            float sg;
+            tmem_ld1(tlane + TM_D2 + round * TM_D2_STRIDE + 32, sg);
+            tmem_wait_ld();
+            sg += b2s[32];
+            if (round == 0) {
+                sigc[lane] = sg;
+                __syncwarp();
+                if (df > 0) {
+                    warp_weights(dcs, sigc, dc, w, lane);
+                    warp_importance(dcs, w, dc, p.u + rr * df, df, cdf, fine, nullptr, lane);
+                    warp_merge_ranks(dcs, dc, fine, df, pos_c, pos_f, lane);
+                }
+            } else {
+                sigf[lane] = sg;
+                __syncwarp();
+            }
+        }
+        // ---- merged order, final weights, colour coefficients
+        if (df > 0) {
+            for (int i = lane; i < dc; i += 32) { sigm[pos_c[i]] = sigc[i]; dall[pos_c[i]] = dcs[i]; }
+            for (int j = lane; j < df; j += 32) { sigm[pos_f[j]] = sigf[j]; dall[pos_f[j]] = fine[j]; }
+        } else {
+            for (int i = lane; i < dc; i += 32) { sigm[i] = sigc[i]; dall[i] = dcs[i]; pos_c[i] = i; }
+        }
+        __syncwarp();
+        float depth, wsum;
+        warp_weights(dall, sigm, D, w, lane);
+        warp_finalize(dall, w, D, depth, wsum, lane);          // w[] now holds the colour coefficients a_q
+        // ---- composite: colours straight from TMEM
+        float feat = 0.f;
+        for (int round = 0; round < rounds; round++) {
+            float v[32];
+            tmem_ld32(tlane + TM_D2 + round * TM_D2_STRIDE, v);
+            tmem_wait_ld();
+            const bool valid = round == 0 ? lane < dc : lane < df;
+            const float a = valid ? w[round == 0 ? pos_c[lane] : pos_f[lane]] : 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; c++) v[c] = a * mma::rgb_act_fast(v[c] + b2s[c]);
+            feat += transpose_reduce(v, lane);
+        }
+        if (live) {
+            p.feat[ray * NF + lane] = feat * 2.f - 1.f;                  // rgb*2-1 (ray_marcher.py:55)
+            for (int i = lane; i < D; i += 32) {
+                const float dd = dall[i];
+                lmin = min(lmin, float_as_ordered(dd)); lmax = max(lmax, float_as_ordered(dd));
+                if (p.depths_all) p.depths_all[ray * D + i] = dd;
+                if (p.sigma_all) p.sigma_all[ray * D + i] = sigm[i];
+            }
+            if (lane == 0) { p.depth[ray] = depth; p.wsum[ray] = wsum; }
+        }
+        // the next group's MMAs overwrite D2: every warp must be done reading it
+        fence_before();
+        __syncthreads();
+        fence_after();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o)); lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o)); }
+    if (lane == 0 && lmax != 0) { atomicMin(p.minmax, lmin); atomicMax(p.minmax + 1, lmax); }
+    fence_before();
+    __syncthreads();
+    if (warp == 0) { __syncwarp(); tmem_dealloc(tm, TM_COLS); }
+}
+
+}  // namespace tcr
