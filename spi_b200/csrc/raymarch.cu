@@ -1006,6 +1006,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_fwd_mma_kernel(RenderParams
 }
 
 #include "raymarch_tc.cuh"
+#include "raymarch_tc_bwd.cuh"
 
 // scatter of a 32-row feature-gradient tile (row stride mma::FS); lane = row; `valid` rows only
 __device__ __forceinline__ void warp_scatter_tile(float* __restrict__ gp, const float* dft, int* s_off, float* s_w, int W, int H, float x,
@@ -1321,11 +1322,21 @@ extern "C" int spi_render_backward(const float* planes, const float* origins, co
     SPI_CHECK_ARG(depths_all && minmax && g_feat, "render_backward: null pointer");
     if (n == 0) return SPI_OK;
     const bool simt = getenv("SPI_RENDER_SIMT") != nullptr;
+    long long rays = (long long)n * rays_per_image;
+    // tcgen05 kernel: hidden layer and outputs of both 32-sample rounds resident in tensor memory (<= 64 merged samples per ray)
+    if (!simt && getenv("SPI_RENDER_MMA") == nullptr && dc + df <= 64) {
+        cudaFuncSetAttribute(tcb::render_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::SMEM_BYTES);
+        long long groups = (rays + 3) / 4, cap = spi_num_sms();
+        int grid = (int)(groups < cap ? groups : cap);
+        tcb::render_bwd_tc_kernel<<<grid, tcb::THREADS, tcb::SMEM_BYTES, stream>>>(p, spi_tc_err_flag());
+        SPI_COUNT_LAUNCH(1);
+        SPI_LAUNCH_CHECK("render_backward");
+        return SPI_OK;
+    }
     size_t smem = simt ? bwd_smem_bytes(dc + df) : bwd2_smem_bytes(dc + df);
     SPI_CHECK_ARG(smem <= 227 * 1024, "render_backward: %d samples per ray need %zu B of shared memory (> 227 KB)", dc + df, smem);
     auto kern = simt ? render_bwd_kernel : render_bwd_mma_kernel;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    long long rays = (long long)n * rays_per_image;
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WARPS * 32, smem);
     if (occ < 1) occ = 1;

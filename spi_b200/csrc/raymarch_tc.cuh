@@ -40,12 +40,6 @@ __host__ __device__ inline size_t warp_floats(int dc, int df) {
 }
 __host__ __device__ inline size_t smem_bytes(int dc, int df) { return OFF_WARP + 4 * warp_floats(dc, df) * sizeof(float) + 1024; }
 
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, float& v) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-    v = __uint_as_float(r);
-}
-
 // Warp-cooperative gather of this warp's 32 samples into rows row0 .. row0+31 of the A tiles (hi / lo halves, swizzled).
 // Every lane publishes its own sample's 12 (texel offset, weight) pairs; then 8 lanes serve one sample, each owning 4 of the 32
 // channels, so a texel read is one coalesced 128-byte line.  Out-of-range corners read texel 0 with weight 0 (grid_sample's
