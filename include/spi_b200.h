@@ -170,6 +170,14 @@ int spi_noise_reg_backward(const void* table, int count, int max_size, const flo
                            cudaStream_t stream);
 int spi_noise_renorm(const void* table, int count, cudaStream_t stream);
 
+/* ---- one LPIPS feature tap: spi/criteria/lpips/lpips.py:50-71 + utils.normalize_activation, fused.
+ * x: raw VGG features of the generated image, channels-last fp32 [n, hw, c]; yn: unit-normalised target features [ny, hw, c]
+ * (ny = n or 1, constant); lin: 1x1 lin-layer weights [c].  forward ACCUMULATES out[0] += sum_n mean_hw sum_c lin_c (xn_c - yn_c)^2
+ * with xn = x / (sqrt(sum_c x^2) + 1e-10); backward writes dx = gout[0] * d(tap)/dx. */
+int spi_lpips_tap_forward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, float* out, cudaStream_t stream);
+int spi_lpips_tap_backward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, const float* gout, float* dx,
+                           cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,8 +72,59 @@ class LPIPS(nn.Module):
         assert self.num_scales == 1, 'multi-scale LPIPS is not used by SPI and not built'
         n_samples = x.shape[0]
         resize = x.shape[-1] > 256                     # lpips.py:37-39: both images follow x's size test
-        feat_x = self.net(self._resize(x) if resize else x)
         feat_y = self._target_feats(y, resize)
+        xin = self._resize(x) if resize else x
+        if _fusable(feat_y, y):
+            # normalise + difference + lin + spatial mean of all five taps in one pass each (spi_lpips_tap_forward/backward)
+            feat_x = self.net(xin, normalize=False)
+            lins = [l[1].weight.reshape(-1) for l in self.lin]
+            return _LpipsTail.apply(len(feat_x), *feat_x, *feat_y, *lins) / n_samples
+        feat_x = self.net(xin)
         diff = [(fx - fy) ** 2 for fx, fy in zip(feat_x, feat_y)]
         res = [l(d).mean((2, 3), True) for d, l in zip(diff, self.lin)]
         return torch.sum(torch.cat(res, 0)) / n_samples
+
+
+def _fusable(feat_y, y):
+    return (not y.requires_grad) and all((not f.requires_grad) and f.dtype == torch.float32 and f.shape[1] % 4 == 0 and f.shape[1] <= 512
+                                         for f in feat_y)
+
+
+class _LpipsTail(torch.autograd.Function):
+    """sum over taps of sum_n mean_hw sum_c lin_c (x_c/(|x|+1e-10) - yn_c)^2 (lpips.py:50-71); gradients flow to the x taps only."""
+
+    @staticmethod
+    def forward(ctx, k, *args):
+        from ... import _lib
+        xs = [a.contiguous(memory_format=torch.channels_last) for a in args[:k]]
+        ys = [a.contiguous(memory_format=torch.channels_last) for a in args[k:2 * k]]
+        lins = [a.contiguous() for a in args[2 * k:]]
+        out = torch.zeros((), device=xs[0].device)
+        lib = _lib.load()
+        for fx, fy, w in zip(xs, ys, lins):
+            n, c, h, wd = fx.shape
+            assert fy.shape[1:] == fx.shape[1:] and fy.shape[0] in (1, n)
+            _lib.check(lib.spi_lpips_tap_forward(_lib.ptr(fx), _lib.ptr(fy), _lib.ptr(w), n, h * wd, c, fy.shape[0], _lib.ptr(out), _lib.stream()))
+        ctx.k = k
+        ctx.save_for_backward(*xs, *ys, *lins)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        from ... import _lib
+        k = ctx.k
+        saved = ctx.saved_tensors
+        xs, ys, lins = saved[:k], saved[k:2 * k], saved[2 * k:]
+        gout = gout.contiguous().float()
+        lib = _lib.load()
+        grads = []
+        for i, (fx, fy, w) in enumerate(zip(xs, ys, lins)):
+            if not ctx.needs_input_grad[1 + i]:
+                grads.append(None)
+                continue
+            n, c, h, wd = fx.shape
+            dx = torch.empty_like(fx)
+            _lib.check(lib.spi_lpips_tap_backward(_lib.ptr(fx), _lib.ptr(fy), _lib.ptr(w), n, h * wd, c, fy.shape[0], _lib.ptr(gout), _lib.ptr(dx),
+                                                  _lib.stream()))
+            grads.append(dx)
+        return (None, *grads, *([None] * (2 * k)))

@@ -50,9 +50,18 @@ class BaseNet(nn.Module):
     def z_score(self, x):
         return (x - self.mean) / self.std
 
-    def forward(self, x):
+    def _weights_channels_last(self):
+        """The conv engine consumes channels-last weights; the (frozen) VGG weights are converted once instead of on every call
+        (14.7 M parameters = a 59 MB copy per LPIPS evaluation otherwise).  load_state_dict() copies into the converted tensors."""
+        for layer in self.layers:
+            if isinstance(layer, nn.Conv2d) and not layer.weight.is_contiguous(memory_format=torch.channels_last):
+                layer.weight.data = layer.weight.data.contiguous(memory_format=torch.channels_last)
+
+    def forward(self, x, normalize=True):
+        """Feature taps; `normalize=False` returns them raw (the fused LPIPS tail normalises on the fly)."""
         if not x.is_cuda:
             raise RuntimeError('spi_b200 LPIPS: tensors must reside on a CUDA device (no CPU path in this build)')
+        self._weights_channels_last()
         x = self.z_score(x).contiguous(memory_format=torch.channels_last)
         output = []
         fused_relu = False
@@ -65,7 +74,7 @@ class BaseNet(nn.Module):
             else:
                 x = layer(x)
             if i in self.target_layers:
-                output.append(normalize_activation(x))
+                output.append(normalize_activation(x) if normalize else x)
             if len(output) == len(self.target_layers):
                 break
         return output
