@@ -144,7 +144,10 @@ class KernelTimer:
             return None
         ms = [a.elapsed_time(b) for a, b, _ in sp]
         units = [u for _, _, u in sp]
-        return {'launches': len(sp), 'ms_total': float(sum(ms)), 'ms_per_unit': float(sum(ms) / sum(units)), 'units': int(sum(units))}
+        per = sorted(m / max(u, 1) for m, u in zip(ms, units))
+        # median over launches: one descheduled launch on a shared box must not move the figure
+        return {'launches': len(sp), 'ms_total': float(sum(ms)), 'ms_per_unit': float(per[len(per) // 2]), 'ms_per_unit_mean': float(sum(ms) / sum(units)),
+                'units': int(sum(units))}
 
 
 def measured_peaks():

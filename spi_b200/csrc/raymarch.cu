@@ -296,10 +296,13 @@ __device__ __forceinline__ void warp_importance(const float* d, const float* w, 
     }
     float total = warp_sum(lsum);
     __syncwarp();
+    // pdf = a / total in parallel, then the SEQUENTIAL cumsum of torch (the order of the additions decides the searchsorted indices)
+    for (int k = lane; k < ns; k += 32) cdf[k + 1] = cdf[k + 1] / total;
+    __syncwarp();
     if (lane == 0) {
         float run = 0.f;
         cdf[0] = 0.f;
-        for (int k = 0; k < ns; k++) { run += cdf[k + 1] / total; cdf[k + 1] = run; }
+        for (int k = 0; k < ns; k++) { run += cdf[k + 1]; cdf[k + 1] = run; }
     }
     __syncwarp();
     for (int t = lane; t < Df; t += 32) {

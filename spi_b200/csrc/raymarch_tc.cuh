@@ -2,7 +2,8 @@
 // namespace (uses RenderParams, Ray, corners / plane_coords, the per-ray warp stages and the MUFU activations).
 //
 // Same arithmetic as render_fwd_mma_kernel (renderer.py:88-253, ray_marcher.py:25-57, triplane.py:123-135), different machine
-// mapping.  A CTA of 4 warps owns 4 rays at a time, one ray per warp, one sample per lane, so the 4 x 32 samples of a "round"
+// mapping.  A CTA of 8 warps owns 4 rays at a time -- warps q and q+4 share ray slot q (both may touch TMEM lanes 32q..32q+31) and
+// split its gather, its activation columns, the merge ranks and the two composite rounds -- one sample per lane, so the 4 x 32 samples of a "round"
 // (coarse samples, then importance samples) form ONE M = 128 decoder tile:
 //
 //   gather     8 lanes per texel line (128 B), features -> hi / lo TF32 halves -> shared memory, SWIZZLE_128B K-major rows
@@ -22,7 +23,7 @@ namespace tcr {
 
 using namespace tc05;
 
-constexpr int TC_THREADS = 128;
+constexpr int TC_THREADS = 256;                   // 8 warps: warps q and q + 4 share ray slot q (TMEM lanes 32q .. 32q+31)
 constexpr int A_TILE = 128 * 128;                 // bytes of one 128 x 32 fp32 operand tile
 constexpr int W1_TILE = 64 * 128;
 constexpr int W2_SLAB = 48 * 128;                 // one K slab (32 hidden units) of W2
@@ -30,40 +31,47 @@ constexpr int OFF_A_HI = 0, OFF_A_LO = A_TILE, OFF_W1_HI = 2 * A_TILE, OFF_W1_LO
 constexpr int OFF_W2_HI = OFF_W1_LO + W1_TILE, OFF_W2_LO = OFF_W2_HI + 2 * W2_SLAB;
 constexpr int OFF_BIAS = OFF_W2_LO + 2 * W2_SLAB;  // b1[64], b2 permuted [48]
 constexpr int OFF_BARS = OFF_BIAS + (64 + 48) * 4;
-constexpr int OFF_WARP = OFF_BARS + 64;            // per-warp scratch starts here (16-byte aligned)
+constexpr int OFF_OW = OFF_BARS + 64;              // per-slot (texel offset, weight) tables: 4 x 384 int2
+constexpr int OFF_SLOT = OFF_OW + 4 * 384 * 8;     // per-slot float scratch starts here
 constexpr uint32_t TM_COLS = 256, TM_D2 = 0, TM_D2_STRIDE = 64, TM_H_HI = 128, TM_H_LO = 192;
 
-__host__ __device__ inline size_t warp_floats(int dc, int df) {
+__host__ __device__ inline size_t slot_floats(int dc, int df) {
     const int D = dc + df;
-    size_t f = (size_t)dc /*dcs*/ + 32 /*sigc*/ + 32 /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall, sigm, w*/ + dc + df /*pos*/ + 2 * 32 * 12 + 2 /*int2 alignment*/;
+    size_t f = (size_t)dc /*dcs*/ + 32 /*sigc*/ + 32 /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall, sigm, w*/ + dc + df /*pos*/ + 64 /*feat halves*/;
     return (f + 3) & ~(size_t)3;
 }
-__host__ __device__ inline size_t smem_bytes(int dc, int df) { return OFF_WARP + 4 * warp_floats(dc, df) * sizeof(float) + 1024; }
+__host__ __device__ inline size_t smem_bytes(int dc, int df) { return OFF_SLOT + 4 * slot_floats(dc, df) * sizeof(float) + 1024; }
 
-// Warp-cooperative gather of this warp's 32 samples into rows row0 .. row0+31 of the A tiles (hi / lo halves, swizzled).
-// Every lane publishes its own sample's 12 (texel offset, weight) pairs; then 8 lanes serve one sample, each owning 4 of the 32
-// channels, so a texel read is one coalesced 128-byte line.  Out-of-range corners read texel 0 with weight 0 (grid_sample's
-// zeros padding) so the inner loop has no branches and all 12 loads of a sample are in flight together.
-__device__ __forceinline__ void gather_rows(const float* __restrict__ pl, int W, int H, float x, float y, float z, float scale, bool valid,
-                                            uint8_t* a_hi, uint8_t* a_lo, int row0, int2* s_ow, int lane) {
+__device__ __forceinline__ void pair_sync(int slot) { slot_bar_sync<64>(slot); }
+
+// Every lane publishes its own sample's (texel offset, weight) pairs into the slot's table -- the first warp of the pair writes
+// planes 0 and 1, the second plane 2 -- then (after pair_sync) 8 lanes serve one sample, each owning 4 of the 32 channels, so a
+// texel read is one coalesced 128-byte line.  Out-of-range corners read texel 0 with weight 0 (grid_sample's zeros padding): the
+// inner loop has no branches and all 12 loads of a sample are in flight together.
+__device__ __forceinline__ void publish_corners(int W, int H, float x, float y, float z, float scale, bool valid, int2* s_ow, int lane, int half) {
     float gc[3][2];
     plane_coords(x, y, z, scale, gc);
 #pragma unroll
     for (int pp = 0; pp < 3; pp++) {
-        Corner c;
-        corners(gc[pp][0], gc[pp][1], W, H, c);
+        if ((pp < 2) == (half == 0)) {
+            Corner c;
+            corners(gc[pp][0], gc[pp][1], W, H, c);
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const bool in = valid && c.off[q] >= 0;
-            s_ow[lane * 12 + pp * 4 + q] = make_int2(in ? c.off[q] + pp * NF : 0, __float_as_int(in ? c.w[q] * (1.f / 3.f) : 0.f));
+            for (int q = 0; q < 4; q++) {
+                const bool in = valid && c.off[q] >= 0;
+                s_ow[lane * 12 + pp * 4 + q] = make_int2(in ? c.off[q] + pp * NF : 0, __float_as_int(in ? c.w[q] * (1.f / 3.f) : 0.f));
+            }
         }
     }
-    __syncwarp();
+}
+
+// this warp's 16 samples (rows row0 + 16 half ...) of the A tiles, hi / lo halves, swizzled
+__device__ __forceinline__ void gather_rows(const float* __restrict__ pl, const int2* s_ow, uint8_t* a_hi, uint8_t* a_lo, int row0, int lane, int half) {
     const int sub = lane & 7, grp = lane >> 3;
     const float4* pls = reinterpret_cast<const float4*>(pl) + sub;
 #pragma unroll 2
-    for (int k = 0; k < 8; k++) {
-        const int smp = grp + 4 * k;
+    for (int k = 0; k < 4; k++) {
+        const int smp = grp + 4 * (k + 4 * half);
         float4 v[12];
         float ww[12];
 #pragma unroll
@@ -83,7 +91,6 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ pl, int W,
         *reinterpret_cast<uint4*>(a_hi + o) = h;
         *reinterpret_cast<uint4*>(a_lo + o) = l;
     }
-    __syncwarp();
 }
 
 // v[c] (c = 0..31) per lane -> lane c returns sum over the 32 lanes of v[c]  (31 shuffles)
@@ -113,8 +120,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + OFF_BARS);
     uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 2);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = warp & 3, half = warp >> 2;
     const int dc = p.dc, df = p.df, D = dc + df;
-    float* b = reinterpret_cast<float*>(sm + OFF_WARP) + warp * warp_floats(dc, df);
+    int2* g_ow = reinterpret_cast<int2*>(sm + OFF_OW) + q * 384;
+    float* b = reinterpret_cast<float*>(sm + OFF_SLOT) + q * slot_floats(dc, df);
     float* dcs = b; b += dc;
     float* sigc = b; b += 32;
     float* sigf = b; b += 32;
@@ -125,7 +134,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     float* w = b; b += D;
     int* pos_c = (int*)b; b += dc;
     int* pos_f = (int*)b; b += df;
-    int2* g_ow = reinterpret_cast<int2*>((reinterpret_cast<uintptr_t>(b) + 7) & ~(uintptr_t)7);
+    float* featp = b;                                   // [2][32] partial composites of the two warps
 
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
     if (warp == 0) { __syncwarp(); tmem_alloc(slot, TM_COLS); }
@@ -154,7 +163,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     __syncthreads();
     fence_after();
     const uint32_t tm = *slot;
-    const uint32_t tlane = tm + ((uint32_t)(warp * 32) << 16);
+    const uint32_t tlane = tm + ((uint32_t)(q * 32) << 16);
     const uint32_t id1 = idesc_tf32(128, 64), id2 = idesc_tf32(128, 48);
 
     const int R = p.R;
@@ -163,29 +172,30 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     const float scale = 2.f / p.box_warp;
     uint32_t ph0 = 0, ph1 = 0;
     int lmin = 0x7f800000, lmax = 0;
-    bool ok = true;
+    const int rounds = df > 0 ? 2 : 1;
 
-    for (long long grp = blockIdx.x; grp < groups && ok; grp += gridDim.x) {
-        const long long ray = grp * 4 + warp;
+    for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const long long ray = grp * 4 + q;
         const bool live = ray < total;
-        const long long rr = live ? ray : total - 1;                    // dead warps shadow the last ray (no stores)
+        const long long rr = live ? ray : total - 1;                    // dead slots shadow the last ray (no stores)
         const float* pl = p.planes + (size_t)(rr / R) * p.plane_bs;
         Ray r;
         r.ox = p.origins[rr * 3]; r.oy = p.origins[rr * 3 + 1]; r.oz = p.origins[rr * 3 + 2];
         r.dx = p.dirs[rr * 3]; r.dy = p.dirs[rr * 3 + 1]; r.dz = p.dirs[rr * 3 + 2];
-        const int rounds = df > 0 ? 2 : 1;
         for (int round = 0; round < rounds; round++) {
             // ---- sample positions + gather
             float d = 0.f;
             bool valid;
             if (round == 0) {
                 valid = lane < dc;
-                if (valid) { d = coarse_depth(p, lane, p.jitter[rr * dc + lane]); dcs[lane] = d; }
+                if (valid) { d = coarse_depth(p, lane, p.jitter[rr * dc + lane]); if (half == 0) dcs[lane] = d; }
             } else {
                 valid = lane < df;
                 if (valid) d = fine[lane];
             }
-            gather_rows(pl, p.W, p.H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, valid, a_hi, a_lo, warp * 32, g_ow, lane);
+            publish_corners(p.W, p.H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, valid, g_ow, lane, half);
+            pair_sync(q);
+            gather_rows(pl, g_ow, a_hi, a_lo, q * 32, lane, half);
             fence_async_smem();
             fence_before();
             __syncthreads();
@@ -201,20 +211,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                 }
                 commit(&bars[0]);
             }
-            if (!mbar_wait_bounded(&bars[0], ph0)) { atomicExch(err, 1); ok = false; }
+            if (!mbar_wait_bounded(&bars[0], ph0)) atomicExch(err, 1);
             ph0 ^= 1;
             fence_after();
-            // ---- bias + softplus, hi / lo halves back into TMEM (H_hi overwrites D1 in place)
+            // ---- bias + softplus of this warp's 32 hidden columns, hi / lo halves back into TMEM (H_hi overwrites D1 in place)
 #pragma unroll
-            for (int half = 0; half < 2; half++) {
-                float v[32];
-                uint32_t hh[32], hl[32];
-                tmem_ld32(tlane + TM_H_HI + half * 32, v);
+            for (int ch = 0; ch < 2; ch++) {
+                const int c0 = half * 32 + ch * 16;
+                float v[16];
+                uint32_t hh[16], hl[16];
+                tmem_ld16(tlane + TM_H_HI + c0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 32; c++) split(mma::softplus_fast(v[c] + b1s[half * 32 + c]), hh[c], hl[c]);
-                tmem_st32(tlane + TM_H_HI + half * 32, hh);
-                tmem_st32(tlane + TM_H_LO + half * 32, hl);
+                for (int c = 0; c < 16; c++) split(mma::softplus_fast(v[c] + b1s[c0 + c]), hh[c], hl[c]);
+                tmem_st16(tlane + TM_H_HI + c0, hh);
+                tmem_st16(tlane + TM_H_LO + c0, hl);
             }
             tmem_wait_st();
             fence_before();
@@ -235,51 +246,73 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                 }
                 commit(&bars[1]);
             }
-            if (!mbar_wait_bounded(&bars[1], ph1)) { atomicExch(err, 2); ok = false; }
+            if (!mbar_wait_bounded(&bars[1], ph1)) atomicExch(err, 2);
             ph1 ^= 1;
             fence_after();
-            float sg;
-            tmem_ld1(tlane + TM_D2 + round * TM_D2_STRIDE + 32, sg);
-            tmem_wait_ld();
-            sg += b2s[32];
-            if (round == 0) {
-                sigc[lane] = sg;
-                __syncwarp();
-                if (df > 0) {
-                    warp_weights(dcs, sigc, dc, w, lane);
-                    warp_importance(dcs, w, dc, p.u + rr * df, df, cdf, fine, nullptr, lane);
-                    warp_merge_ranks(dcs, dc, fine, df, pos_c, pos_f, lane);
+            if (half == 0) {
+                float sg;
+                tmem_ld1(tlane + TM_D2 + round * TM_D2_STRIDE + 32, sg);
+                tmem_wait_ld();
+                sg += b2s[32];
+                if (round == 0) {
+                    sigc[lane] = sg;
+                    __syncwarp();
+                    if (df > 0) {
+                        warp_weights(dcs, sigc, dc, w, lane);
+                        warp_importance(dcs, w, dc, p.u + rr * df, df, cdf, fine, nullptr, lane);
+                    }
+                } else {
+                    sigf[lane] = sg;
+                    __syncwarp();
+                }
+            }
+            pair_sync(q);                               // fine[] (round 0) / sigf[] (round 1) visible to both warps
+        }
+        // ---- merged order (ranks split between the two warps), final weights, colour coefficients
+        if (df > 0) {
+            if (half == 0) {
+                for (int i = lane; i < dc; i += 32) {
+                    const float v = dcs[i];
+                    int rk = 0;
+                    for (int k = 0; k < dc; k++) rk += (dcs[k] < v) || (dcs[k] == v && k < i);
+                    for (int k = 0; k < df; k++) rk += (fine[k] < v);
+                    pos_c[i] = rk; sigm[rk] = sigc[i]; dall[rk] = v;
                 }
             } else {
-                sigf[lane] = sg;
-                __syncwarp();
+                for (int j = lane; j < df; j += 32) {
+                    const float v = fine[j];
+                    int rk = 0;
+                    for (int k = 0; k < dc; k++) rk += (dcs[k] <= v);
+                    for (int k = 0; k < df; k++) rk += (fine[k] < v) || (fine[k] == v && k < j);
+                    pos_f[j] = rk; sigm[rk] = sigf[j]; dall[rk] = v;
+                }
             }
-        }
-        // ---- merged order, final weights, colour coefficients
-        if (df > 0) {
-            for (int i = lane; i < dc; i += 32) { sigm[pos_c[i]] = sigc[i]; dall[pos_c[i]] = dcs[i]; }
-            for (int j = lane; j < df; j += 32) { sigm[pos_f[j]] = sigf[j]; dall[pos_f[j]] = fine[j]; }
-        } else {
+        } else if (half == 0) {
             for (int i = lane; i < dc; i += 32) { sigm[i] = sigc[i]; dall[i] = dcs[i]; pos_c[i] = i; }
         }
-        __syncwarp();
-        float depth, wsum;
-        warp_weights(dall, sigm, D, w, lane);
-        warp_finalize(dall, w, D, depth, wsum, lane);          // w[] now holds the colour coefficients a_q
-        // ---- composite: colours straight from TMEM
-        float feat = 0.f;
-        for (int round = 0; round < rounds; round++) {
+        pair_sync(q);
+        float depth = 0.f, wsum = 0.f;
+        if (half == 0) {
+            warp_weights(dall, sigm, D, w, lane);
+            warp_finalize(dall, w, D, depth, wsum, lane);          // w[] now holds the colour coefficients a_q
+        }
+        pair_sync(q);
+        // ---- composite: colours straight from TMEM, one round per warp of the pair
+        if (half < rounds) {
             float v[32];
-            tmem_ld32(tlane + TM_D2 + round * TM_D2_STRIDE, v);
+            tmem_ld32(tlane + TM_D2 + half * TM_D2_STRIDE, v);
             tmem_wait_ld();
-            const bool valid = round == 0 ? lane < dc : lane < df;
-            const float a = valid ? w[round == 0 ? pos_c[lane] : pos_f[lane]] : 0.f;
+            const bool valid = half == 0 ? lane < dc : lane < df;
+            const float a = valid ? w[half == 0 ? pos_c[lane] : pos_f[lane]] : 0.f;
 #pragma unroll
             for (int c = 0; c < 32; c++) v[c] = a * mma::rgb_act_fast(v[c] + b2s[c]);
-            feat += transpose_reduce(v, lane);
+            featp[half * 32 + lane] = transpose_reduce(v, lane);
+        } else {
+            featp[half * 32 + lane] = 0.f;
         }
-        if (live) {
-            p.feat[ray * NF + lane] = feat * 2.f - 1.f;                  // rgb*2-1 (ray_marcher.py:55)
+        pair_sync(q);
+        if (half == 0 && live) {
+            p.feat[ray * NF + lane] = (featp[lane] + featp[32 + lane]) * 2.f - 1.f;        // rgb*2-1 (ray_marcher.py:55)
             for (int i = lane; i < D; i += 32) {
                 const float dd = dall[i];
                 lmin = min(lmin, float_as_ordered(dd)); lmax = max(lmax, float_as_ordered(dd));
@@ -288,7 +321,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
             }
             if (lane == 0) { p.depth[ray] = depth; p.wsum[ray] = wsum; }
         }
-        // the next group's MMAs overwrite D2: every warp must be done reading it
+        // the next group's MMAs overwrite D2 and the slot scratch: every warp must be done with them
         fence_before();
         __syncthreads();
         fence_after();

@@ -46,7 +46,7 @@ __device__ __forceinline__ uint32_t tm_h_lo(int r) { return (uint32_t)(r * 128 +
 __device__ __forceinline__ uint32_t tm_d2(int r) { return (uint32_t)(256 + r * 64); }
 constexpr uint32_t TM_DOUT_LO = 384, TM_D3 = 448;
 
-__device__ __forceinline__ void quad_sync(int slot) { named_bar_sync(1 + slot, 32 * NPART); }
+__device__ __forceinline__ void quad_sync(int slot) { slot_bar_sync<32 * NPART>(slot); }
 
 // publish (texel offset, weight) of this lane's sample into the slot's table: warp `part` (< 3) of the quad writes plane `part`;
 // out-of-range corners point at texel 0 with weight 0.  Callers quad_sync() before reading the table.

@@ -211,3 +211,16 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                  : "memory");
 }
 }  // namespace tc05
+
+namespace tc05 {
+// named barrier 1 + slot (slot 0..3) over NT threads, with compile-time barrier ids so that ptxas reserves 5 barriers, not 16
+template <int NT>
+__device__ __forceinline__ void slot_bar_sync(int slot) {
+    switch (slot) {
+        case 0: asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); break;
+        case 1: asm volatile("bar.sync 2, %0;" ::"n"(NT) : "memory"); break;
+        case 2: asm volatile("bar.sync 3, %0;" ::"n"(NT) : "memory"); break;
+        default: asm volatile("bar.sync 4, %0;" ::"n"(NT) : "memory"); break;
+    }
+}
+}  // namespace tc05
