@@ -6,7 +6,8 @@
                     reference pickle in an environment that has the reference's `legacy`/`persistence` loaders);
   * `synthetic[:seed]`  FFHQ-512 architecture with default-initialised weights under `torch.manual_seed(seed)`
                     (SURVEY.md §8d: no checkpoint exists offline);
-  * `*.pkl`         not readable here (source-carrying pickle, eg3d/legacy.py:23) -> NotImplementedError.
+  * `*.pkl`         the reference's source-carrying pickle (eg3d/legacy.py:23), read by `spi_b200.legacy.load_network_pkl`
+                    without executing the embedded source.
 """
 import copy
 
@@ -57,8 +58,12 @@ def load_eg3d(reload_modules=True, device=None, network_pkl=None):
             blob = torch.load(network_pkl, map_location='cpu')
             _template[network_pkl] = (blob.get('init_kwargs', FFHQ512_KWARGS), blob['G'])
         else:
-            raise NotImplementedError(f'{network_pkl}: source-carrying EG3D pickles need the reference loader (eg3d/legacy.py); convert '
-                                      'once with tools/convert_pkl.py -- see INTEGRATION.md')
+            from .. import legacy                 # source-carrying pickle (eg3d/legacy.py:23) read without executing its source
+            with open(network_pkl, 'rb') as f:
+                G = legacy.load_network_pkl(f)['G_ema']
+            kw = dict(G.init_kwargs)
+            assert not G.init_args, 'TriPlaneGenerator pickles carry keyword arguments only'
+            _template[network_pkl] = (kw, {k: v.clone() for k, v in G.state_dict().items()})
     kw, sd = _template[network_pkl]
     return build_generator(kw, sd, device=device)
 
