@@ -73,14 +73,19 @@ def test_ray_marcher_golden(golden):
     assert rel_l2(rgb, g['rm_rgb']) < 1e-5 and rel_l2(depth, g['rm_depth']) < 1e-5 and rel_l2(w, g['rm_w']) < 1e-5
 
 
-def test_render_backward_vs_oracle(gen_sd):
+@pytest.mark.parametrize('n,r,dc,df', [
+    (2, 160, 16, 16),      # tcgen05 kernels, full 4-ray groups
+    (1, 37, 32, 32),       # tcgen05 kernels, ragged last group (dead ray slots), both 32-sample rounds full
+    (1, 30, 24, 20),       # tcgen05 kernels, partially filled rounds in both passes
+    (1, 24, 40, 40),       # more than 64 merged samples: mma.sync kernels
+])
+def test_render_backward_vs_oracle(gen_sd, n, r, dc, df):
     """Gradients w.r.t. planes and the four decoder tensors against autograd through the CPU oracle."""
     from spi_b200.training.volumetric_rendering.renderer import ImportanceRenderer
     gen = torch.Generator().manual_seed(11)
-    n, r, dc, df = 2, 160, 16, 16
     rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=dc, depth_resolution_importance=df)
     planes = torch.randn(n, 3, 32, 48, 48, generator=gen)
-    cam = torch.cat([weights.canonical_camera(0.3), weights.canonical_camera(-0.2, 0.1)], 0)
+    cam = torch.cat([weights.canonical_camera(0.3), weights.canonical_camera(-0.2, 0.1)], 0)[:n]
     o, d = OG.ray_sampler(cam[:, :16].reshape(-1, 4, 4), cam[:, 16:].reshape(-1, 3, 3), 128)
     sel = torch.arange(r) * 97 + 700
     o, d = o[:, sel].contiguous(), d[:, sel].contiguous()
