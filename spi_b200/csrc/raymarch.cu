@@ -1277,11 +1277,13 @@ extern "C" int spi_render_forward(const float* planes, const float* origins, con
     if (n == 0) return SPI_OK;
     const bool simt = getenv("SPI_RENDER_SIMT") != nullptr;      // v1 SIMT kernels kept for A/B comparison
     long long rays = (long long)n * rays_per_image;
-    // tcgen05 kernel: one 128-sample decoder tile per round, D2 of both rounds resident in tensor memory (<= 32 + 32 samples per ray)
-    if (!simt && getenv("SPI_RENDER_MMA") == nullptr && dc <= 32 && df <= 32) {
+    // tcgen05 kernel: one 128-sample decoder tile per 32-sample round, D2 of every round resident in tensor memory (<= 6 rounds)
+    const int tc_rounds = tcr::rounds_of(dc) + tcr::rounds_of(df);
+    if (!simt && getenv("SPI_RENDER_MMA") == nullptr && tc_rounds <= tcr::MAX_ROUNDS) {
         const size_t smem_tc = tcr::smem_bytes(dc, df);
         cudaFuncSetAttribute(tcr::render_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc);
-        long long groups = (rays + 3) / 4, cap = 2LL * spi_num_sms();
+        // up to 2 rounds: 256 TMEM columns per CTA, two CTAs per SM; more: all 512 columns, one CTA per SM
+        long long groups = (rays + 3) / 4, cap = (tc_rounds <= 2 ? 2LL : 1LL) * spi_num_sms();
         int grid = (int)(groups < cap ? groups : cap);
         minmax_init_kernel<<<1, 1, 0, stream>>>(minmax);
         tcr::render_fwd_tc_kernel<<<grid, tcr::TC_THREADS, smem_tc, stream>>>(p, spi_tc_err_flag());

@@ -33,11 +33,14 @@ constexpr int OFF_BIAS = OFF_W2_LO + 2 * W2_SLAB;  // b1[64], b2 permuted [48]
 constexpr int OFF_BARS = OFF_BIAS + (64 + 48) * 4;
 constexpr int OFF_OW = OFF_BARS + 64;              // per-slot (texel offset, weight) tables: 4 x 384 int2
 constexpr int OFF_SLOT = OFF_OW + 4 * 384 * 8;     // per-slot float scratch starts here
-constexpr uint32_t TM_COLS = 256, TM_D2 = 0, TM_D2_STRIDE = 64, TM_H_HI = 128, TM_H_LO = 192;
+constexpr uint32_t TM_D2 = 0, TM_D2_STRIDE = 64;   // D2 of round r at columns [64 r, 64 r + 48); H_hi / H_lo behind the last round
+constexpr int MAX_ROUNDS = 6;                      // 64 * rounds + 128 <= 512 tensor-memory columns
+__host__ __device__ inline int rounds_of(int d) { return (d + 31) >> 5; }
 
 __host__ __device__ inline size_t slot_floats(int dc, int df) {
     const int D = dc + df;
-    size_t f = (size_t)dc /*dcs*/ + 32 /*sigc*/ + 32 /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall, sigm, w*/ + dc + df /*pos*/ + 64 /*feat halves*/;
+    size_t f = (size_t)dc /*dcs*/ + 32 * rounds_of(dc) /*sigc*/ + 32 * rounds_of(df) /*sigf*/ + df /*fine*/ + dc /*cdf*/ + 3 * (size_t)D /*dall, sigm, w*/ +
+               dc + df /*pos*/ + 64 /*feat halves*/;
     return (f + 3) & ~(size_t)3;
 }
 __host__ __device__ inline size_t smem_bytes(int dc, int df) { return OFF_SLOT + 4 * slot_floats(dc, df) * sizeof(float) + 1024; }
@@ -125,8 +128,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     int2* g_ow = reinterpret_cast<int2*>(sm + OFF_OW) + q * 384;
     float* b = reinterpret_cast<float*>(sm + OFF_SLOT) + q * slot_floats(dc, df);
     float* dcs = b; b += dc;
-    float* sigc = b; b += 32;
-    float* sigf = b; b += 32;
+    const int RC = rounds_of(dc), RF = rounds_of(df), RT = RC + RF;
+    float* sigc = b; b += 32 * RC;
+    float* sigf = b; b += 32 * RF;
     float* fine = b; b += df;
     float* cdf = b; b += dc;
     float* dall = b; b += D;
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     float* featp = b;                                   // [2][32] partial composites of the two warps
 
     if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); fence_mbar_init(); }
+    const uint32_t TM_H_HI = (uint32_t)(RT < 2 ? 2 : RT) * TM_D2_STRIDE, TM_H_LO = TM_H_HI + 64;
+    const uint32_t TM_COLS = TM_H_HI + 128 <= 256 ? 256u : 512u;
     if (warp == 0) { __syncwarp(); tmem_alloc(slot, TM_COLS); }
     // decoder -> shared memory: gains folded, hi / lo split, canonical K-major SWIZZLE_128B rows
     for (int i = tid; i < 64 * 32; i += TC_THREADS) {
@@ -172,7 +178,6 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
     const float scale = 2.f / p.box_warp;
     uint32_t ph0 = 0, ph1 = 0;
     int lmin = 0x7f800000, lmax = 0;
-    const int rounds = df > 0 ? 2 : 1;
 
     for (long long grp = blockIdx.x; grp < groups; grp += gridDim.x) {
         const long long ray = grp * 4 + q;
@@ -182,16 +187,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
         Ray r;
         r.ox = p.origins[rr * 3]; r.oy = p.origins[rr * 3 + 1]; r.oz = p.origins[rr * 3 + 2];
         r.dx = p.dirs[rr * 3]; r.dy = p.dirs[rr * 3 + 1]; r.dz = p.dirs[rr * 3 + 2];
-        for (int round = 0; round < rounds; round++) {
-            // ---- sample positions + gather
+        for (int round = 0; round < RT; round++) {
+            // ---- sample positions + gather (coarse rounds first, then the importance rounds)
+            const bool coarse = round < RC;
+            const int idx = (coarse ? round : round - RC) * 32 + lane;
             float d = 0.f;
             bool valid;
-            if (round == 0) {
-                valid = lane < dc;
-                if (valid) { d = coarse_depth(p, lane, p.jitter[rr * dc + lane]); if (half == 0) dcs[lane] = d; }
+            if (coarse) {
+                valid = idx < dc;
+                if (valid) { d = coarse_depth(p, idx, p.jitter[rr * dc + idx]); if (half == 0) dcs[idx] = d; }
             } else {
-                valid = lane < df;
-                if (valid) d = fine[lane];
+                valid = idx < df;
+                if (valid) d = fine[idx];
             }
             publish_corners(p.W, p.H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, valid, g_ow, lane, half);
             pair_sync(q);
@@ -254,19 +261,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                 tmem_ld1(tlane + TM_D2 + round * TM_D2_STRIDE + 32, sg);
                 tmem_wait_ld();
                 sg += b2s[32];
-                if (round == 0) {
-                    sigc[lane] = sg;
-                    __syncwarp();
-                    if (df > 0) {
-                        warp_weights(dcs, sigc, dc, w, lane);
-                        warp_importance(dcs, w, dc, p.u + rr * df, df, cdf, fine, nullptr, lane);
-                    }
-                } else {
-                    sigf[lane] = sg;
-                    __syncwarp();
+                (coarse ? sigc : sigf)[idx] = sg;
+                __syncwarp();
+                if (round == RC - 1 && df > 0) {            // all coarse sigmas known: importance sampling
+                    warp_weights(dcs, sigc, dc, w, lane);
+                    warp_importance(dcs, w, dc, p.u + rr * df, df, cdf, fine, nullptr, lane);
                 }
             }
-            pair_sync(q);                               // fine[] (round 0) / sigf[] (round 1) visible to both warps
+            pair_sync(q);                               // fine[] / sigma arrays visible to both warps
         }
         // ---- merged order (ranks split between the two warps), final weights, colour coefficients
         if (df > 0) {
@@ -297,18 +299,22 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
             warp_finalize(dall, w, D, depth, wsum, lane);          // w[] now holds the colour coefficients a_q
         }
         pair_sync(q);
-        // ---- composite: colours straight from TMEM, one round per warp of the pair
-        if (half < rounds) {
-            float v[32];
-            tmem_ld32(tlane + TM_D2 + half * TM_D2_STRIDE, v);
-            tmem_wait_ld();
-            const bool valid = half == 0 ? lane < dc : lane < df;
-            const float a = valid ? w[half == 0 ? pos_c[lane] : pos_f[lane]] : 0.f;
+        // ---- composite: colours straight from TMEM, the rounds alternate between the two warps of the pair
+        {
+            float feat = 0.f;
+            for (int round = half; round < RT; round += 2) {
+                float v[32];
+                tmem_ld32(tlane + TM_D2 + round * TM_D2_STRIDE, v);
+                tmem_wait_ld();
+                const bool coarse = round < RC;
+                const int idx = (coarse ? round : round - RC) * 32 + lane;
+                const bool valid = coarse ? idx < dc : idx < df;
+                const float a = valid ? w[coarse ? pos_c[idx] : pos_f[idx]] : 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; c++) v[c] = a * mma::rgb_act_fast(v[c] + b2s[c]);
-            featp[half * 32 + lane] = transpose_reduce(v, lane);
-        } else {
-            featp[half * 32 + lane] = 0.f;
+                for (int c = 0; c < 32; c++) v[c] = a * mma::rgb_act_fast(v[c] + b2s[c]);
+                feat += transpose_reduce(v, lane);
+            }
+            featp[half * 32 + lane] = feat;
         }
         pair_sync(q);
         if (half == 0 && live) {
