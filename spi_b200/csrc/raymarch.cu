@@ -1328,8 +1328,8 @@ extern "C" int spi_render_backward(const float* planes, const float* origins, co
     if (n == 0) return SPI_OK;
     const bool simt = getenv("SPI_RENDER_SIMT") != nullptr;
     long long rays = (long long)n * rays_per_image;
-    // tcgen05 kernel: hidden layer and outputs of both 32-sample rounds resident in tensor memory (<= 64 merged samples per ray)
-    if (!simt && getenv("SPI_RENDER_MMA") == nullptr && dc + df <= 64) {
+    // tcgen05 kernel: hidden layer and outputs of the last two 32-sample rounds resident in tensor memory (<= 128 merged samples per ray)
+    if (!simt && getenv("SPI_RENDER_MMA") == nullptr && dc + df <= tcb::MAXD) {
         cudaFuncSetAttribute(tcb::render_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tcb::SMEM_BYTES);
         long long groups = (rays + 3) / 4, cap = spi_num_sms();
         int grid = (int)(groups < cap ? groups : cap);

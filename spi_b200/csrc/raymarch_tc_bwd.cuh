@@ -13,8 +13,9 @@
 //                   dPre = dH (1 - exp(-H)) -> TMEM over H in place -> MMA4: dF = dPre W1 -> smem -> RED.v4 scatter into the
 //                   12 texel lines of every sample (8 lanes per line)
 //
-// Nothing is recomputed between B1 and B3: the hidden layer and the outputs of both rounds stay in tensor memory (512 columns,
-// one CTA per SM).  All four GEMMs are 3xTF32 (hi*hi + lo*hi + hi*lo) with fp32 accumulation, like the forward pass.
+// The hidden layer and the outputs of the last two rounds stay in tensor memory between B1 and B3 (512 columns, one CTA per SM):
+// with up to 64 merged samples per ray nothing is recomputed; longer rays (up to 128 samples) re-run the forward part of their
+// older rounds in B3.  All four GEMMs are 3xTF32 (hi*hi + lo*hi + hi*lo) with fp32 accumulation, like the forward pass.
 // Decoder weight gradients: when requested the per-sample rows f | hid | dpre | dout are written to the scratch tensors and
 // reduced by two TF32 GEMMs on the host side (unchanged contract of spi_render_backward).
 #pragma once
@@ -24,6 +25,7 @@ namespace tcb {
 using namespace tc05;
 
 constexpr int THREADS = 512, NPART = 4;
+constexpr int MAXD = 128;                          // merged samples per ray (4 rounds of 32)
 constexpr int OFF_A_HI = 0, OFF_A_LO = 16384;
 constexpr int OFF_W1_HI = 32768, OFF_W1_LO = OFF_W1_HI + 8192;
 constexpr int W2_SLAB = 48 * 128;
@@ -36,7 +38,7 @@ constexpr int OFF_BIAS = OFF_W1T_LO + 2 * W1T_SLAB;             // b1[64], b2 pe
 constexpr int OFF_BARS = OFF_BIAS + (64 + 48) * 4;
 constexpr int OFF_SLOT = OFF_BARS + 64;
 constexpr int DFS = 36;                                          // row stride of the dF tile (floats)
-constexpr int SLOT_FLOATS = 11 * 64 + 32 + 32 * DFS;             // dall sig w pd[4] alpha Tarr gmid spare | gfe | dF tile
+constexpr int SLOT_FLOATS = 10 * MAXD + 32 + 32 * DFS;           // dall sig w pd[4] alpha Tarr gmid | gfe | dF tile
 constexpr int OFF_OW = OFF_SLOT + 4 * SLOT_FLOATS * 4;           // per-slot (offset, weight) tables: 4 x 384 int2
 constexpr int SMEM_BYTES = OFF_OW + 4 * 384 * 8 + 1024;
 // tensor memory columns
@@ -78,8 +80,8 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = warp & 3, part = warp >> 2;
     float* sb = reinterpret_cast<float*>(sm + OFF_SLOT) + q * SLOT_FLOATS;
-    float* dall = sb; float* sig = sb + 64; float* w = sb + 128; float* pd = sb + 192;          // pd[4][64]: per-warp partial <g_rgb, rgb>
-    float* alpha = sb + 448; float* Tarr = sb + 512; float* gmid = sb + 576; float* gfe = sb + 704; float* DFt = sb + 736;
+    float* dall = sb; float* sig = sb + MAXD; float* w = sb + 2 * MAXD; float* pd = sb + 3 * MAXD;      // pd[4][MAXD]: per-warp partial <g_rgb, rgb>
+    float* alpha = sb + 7 * MAXD; float* Tarr = sb + 8 * MAXD; float* gmid = sb + 9 * MAXD; float* gfe = sb + 10 * MAXD; float* DFt = gfe + 32;
     int2* s_ow = reinterpret_cast<int2*>(sm + OFF_OW) + q * 384;
 
     if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
@@ -146,11 +148,11 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
         r.ox = p.origins[rr * 3]; r.oy = p.origins[rr * 3 + 1]; r.oz = p.origins[rr * 3 + 2];
         r.dx = p.dirs[rr * 3]; r.dy = p.dirs[rr * 3 + 1]; r.dz = p.dirs[rr * 3 + 2];
         if (part == 0) gfe[lane] = p.g_feat[rr * NF + lane] * 2.f;
-        if (part >= 2) { const int i = (part - 2) * 32 + lane; dall[i] = i < D ? p.depths_all[rr * D + i] : 0.f; }
+        for (int i = part * 32 + lane; i < MAXD; i += 32 * NPART) dall[i] = i < D ? p.depths_all[rr * D + i] : 0.f;
         quad_sync(q);
 
-        // ================================================================ B1
-        for (int rd = 0; rd < rounds; rd++) {
+        // forward part of round rd into TMEM slot sl: gather -> MMA1 -> softplus -> H[sl] -> MMA2 -> D2[sl]
+        auto fwd_round = [&](const int rd, const int sl, const bool first) {
             const int i = rd * 32 + lane;
             const bool valid = i < D;
             const float d = dall[min(i, D - 1)];
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 const uint32_t o = swz(q * 32 + smp, sub);
                 *reinterpret_cast<uint4*>(a_hi + o) = hi;
                 *reinterpret_cast<uint4*>(a_lo + o) = lo;
-                if (p.sc_f && live && rd * 32 + smp < D) *reinterpret_cast<float4*>(p.sc_f + (ray * D + rd * 32 + smp) * NF + 4 * sub) = acc;
+                if (first && p.sc_f && live && rd * 32 + smp < D) *reinterpret_cast<float4*>(p.sc_f + (ray * D + rd * 32 + smp) * NF + 4 * sub) = acc;
             }
             fence_async_smem();
             fence_before();
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 for (int pass = 0; pass < 3; pass++) {
                     const uint32_t a = smem_u32(pass == 1 ? a_lo : a_hi), wq = smem_u32(sm + (pass == 2 ? OFF_W1_LO : OFF_W1_HI));
 #pragma unroll
-                    for (int ks = 0; ks < 4; ks++) { mma_ss(tm + tm_h_hi(rd), desc_sw128(a + ks * 32), desc_sw128(wq + ks * 32), id64, acc); acc = 1; }
+                    for (int ks = 0; ks < 4; ks++) { mma_ss(tm + tm_h_hi(sl), desc_sw128(a + ks * 32), desc_sw128(wq + ks * 32), id64, acc); acc = 1; }
                 }
                 commit(bar);
             }
@@ -200,13 +202,13 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
             {   // +b1, softplus; this warp's 16 of the 64 hidden columns
                 float v[16];
                 uint32_t hh[16], hl[16];
-                tmem_ld16(tlane + tm_h_hi(rd) + part * 16, v);
+                tmem_ld16(tlane + tm_h_hi(sl) + part * 16, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int c = 0; c < 16; c++) { v[c] = mma::softplus_fast(v[c] + b1s[part * 16 + c]); split(v[c], hh[c], hl[c]); }
-                tmem_st16(tlane + tm_h_hi(rd) + part * 16, hh);
-                tmem_st16(tlane + tm_h_lo(rd) + part * 16, hl);
-                if (p.sc_hid && live && valid) {
+                tmem_st16(tlane + tm_h_hi(sl) + part * 16, hh);
+                tmem_st16(tlane + tm_h_lo(sl) + part * 16, hl);
+                if (first && p.sc_hid && live && valid) {
                     float4* dst = reinterpret_cast<float4*>(p.sc_hid + (ray * D + i) * NH + part * 16);
 #pragma unroll
                     for (int c = 0; c < 4; c++) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
@@ -220,25 +222,32 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; pass++) {
-                    const uint32_t a = tm + (pass == 1 ? tm_h_lo(rd) : tm_h_hi(rd)), wq = smem_u32(sm + (pass == 2 ? OFF_W2_LO : OFF_W2_HI));
+                    const uint32_t a = tm + (pass == 1 ? tm_h_lo(sl) : tm_h_hi(sl)), wq = smem_u32(sm + (pass == 2 ? OFF_W2_LO : OFF_W2_HI));
 #pragma unroll
-                    for (int ks = 0; ks < 8; ks++) { mma_ts(tm + tm_d2(rd), a + ks * 8, desc_sw128(wq + (ks >> 2) * W2_SLAB + (ks & 3) * 32), id48, acc); acc = 1; }
+                    for (int ks = 0; ks < 8; ks++) { mma_ts(tm + tm_d2(sl), a + ks * 8, desc_sw128(wq + (ks >> 2) * W2_SLAB + (ks & 3) * 32), id48, acc); acc = 1; }
                 }
                 commit(bar);
             }
             if (!mbar_wait_bounded(bar, ph)) atomicExch(err, 12);
             ph ^= 1;
             fence_after();
+        };
+
+        // ================================================================ B1: sigma_i and p_i of every round; the last two rounds stay resident
+        for (int rd = 0; rd < rounds; rd++) {
+            const int sl = rd & 1;
+            const int i = rd * 32 + lane;
+            fwd_round(rd, sl, true);
             {   // p_i = <g_rgb, rgb_i>: 8 colour columns per warp of the quad; sigma by the first warp
                 float v[8];
-                tmem_ld8(tlane + tm_d2(rd) + part * 8, v);
+                tmem_ld8(tlane + tm_d2(sl) + part * 8, v);
                 float sg = 0.f;
-                if (part == 0) tmem_ld1(tlane + tm_d2(rd) + 32, sg);
+                if (part == 0) tmem_ld1(tlane + tm_d2(sl) + 32, sg);
                 tmem_wait_ld();
                 float pdv = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; c++) pdv = fmaf(gfe[part * 8 + c], mma::rgb_act_fast(v[c] + b2s[part * 8 + c]), pdv);
-                pd[part * 64 + i] = pdv;
+                pd[part * MAXD + i] = pdv;
                 if (part == 0) sig[i] = sg + b2s[32];
             }
         }
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
         // ================================================================ B2: compositing adjoint (first warp of the pair)
         if (part == 0) {
             float* pd0 = pd;
-            for (int i = lane; i < D; i += 32) pd0[i] = (pd[i] + pd[64 + i]) + (pd[128 + i] + pd[192 + i]);
+            for (int i = lane; i < D; i += 32) pd0[i] = (pd[i] + pd[MAXD + i]) + (pd[2 * MAXD + i] + pd[3 * MAXD + i]);
             __syncwarp();
             for (int i = lane; i < D - 1; i += 32) {
                 float delta = dall[i + 1] - dall[i];
@@ -309,8 +318,10 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
             __syncwarp();
         }
         quad_sync(q);
-        // ================================================================ B3
-        for (int rd = 0; rd < rounds; rd++) {
+        // ================================================================ B3: the two resident rounds first, older rounds are recomputed
+        for (int rd = rounds - 1; rd >= 0; rd--) {
+            const int sl = rd & 1;
+            if (rd < rounds - 2) fwd_round(rd, sl, false);
             const int i = rd * 32 + lane;
             const bool valid = i < D;
             float gs = 0.f, a = 0.f;
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
             {   // dOut: colours [8 part, 8 part + 8) (+ sigma and the zero padding by the first warp), hi over D2 in place
                 float v[8];
                 uint32_t hh[16], hl[16];
-                tmem_ld8(tlane + tm_d2(rd) + part * 8, v);
+                tmem_ld8(tlane + tm_d2(sl) + part * 8, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                     v[c] = valid ? gfe[part * 8 + c] * a * (1.f + 2.f * 0.001f) * so * (1.f - so) : 0.f;
                     split(v[c], hh[c], hl[c]);
                 }
-                tmem_st8(tlane + tm_d2(rd) + part * 8, hh);
+                tmem_st8(tlane + tm_d2(sl) + part * 8, hh);
                 tmem_st8(tlane + TM_DOUT_LO + part * 8, hl);
                 if (p.sc_dout && live && valid) {
                     float* dst = p.sc_dout + (ray * D + i) * 36;
@@ -342,7 +353,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
 #pragma unroll
                     for (int c = 0; c < 16; c++) { hh[c] = 0u; hl[c] = 0u; }
                     split(gs, hh[0], hl[0]);
-                    tmem_st16(tlane + tm_d2(rd) + 32, hh);
+                    tmem_st16(tlane + tm_d2(sl) + 32, hh);
                     tmem_st16(tlane + TM_DOUT_LO + 32, hl);
                 }
             }
@@ -354,7 +365,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 uint32_t acc = 0;
 #pragma unroll
                 for (int pass = 0; pass < 3; pass++) {
-                    const uint32_t at = tm + (pass == 1 ? TM_DOUT_LO : tm_d2(rd)), wq = smem_u32(sm + (pass == 2 ? OFF_W2T_LO : OFF_W2T_HI));
+                    const uint32_t at = tm + (pass == 1 ? TM_DOUT_LO : tm_d2(sl)), wq = smem_u32(sm + (pass == 2 ? OFF_W2T_LO : OFF_W2T_HI));
 #pragma unroll
                     for (int ks = 0; ks < 6; ks++) { mma_ts(tm + TM_D3, at + ks * 8, desc_sw128(wq + (ks >> 2) * W2T_SLAB + (ks & 3) * 32), id64, acc); acc = 1; }
                 }
@@ -368,16 +379,16 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 float dh[16], h1[16], h2[16];
                 uint32_t hh[16], hl[16];
                 tmem_ld16(tlane + TM_D3 + c0, dh);
-                tmem_ld16(tlane + tm_h_hi(rd) + c0, h1);
-                tmem_ld16(tlane + tm_h_lo(rd) + c0, h2);
+                tmem_ld16(tlane + tm_h_hi(sl) + c0, h1);
+                tmem_ld16(tlane + tm_h_lo(sl) + c0, h2);
                 tmem_wait_ld();
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
                     dh[c] *= (1.f - mma::ex2_ftz(-1.4426950408889634f * (h1[c] + h2[c])));
                     split(dh[c], hh[c], hl[c]);
                 }
-                tmem_st16(tlane + tm_h_hi(rd) + c0, hh);
-                tmem_st16(tlane + tm_h_lo(rd) + c0, hl);
+                tmem_st16(tlane + tm_h_hi(sl) + c0, hh);
+                tmem_st16(tlane + tm_h_lo(sl) + c0, hl);
                 if (p.sc_dpre && live && valid) {
                     float4* dst = reinterpret_cast<float4*>(p.sc_dpre + (ray * D + i) * NH + c0);
 #pragma unroll
@@ -393,7 +404,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                     uint32_t acc = 0;
 #pragma unroll
                     for (int pass = 0; pass < 3; pass++) {
-                        const uint32_t at = tm + (pass == 1 ? tm_h_lo(rd) : tm_h_hi(rd)), wq = smem_u32(sm + (pass == 2 ? OFF_W1T_LO : OFF_W1T_HI));
+                        const uint32_t at = tm + (pass == 1 ? tm_h_lo(sl) : tm_h_hi(sl)), wq = smem_u32(sm + (pass == 2 ? OFF_W1T_LO : OFF_W1T_HI));
 #pragma unroll
                         for (int ks = 0; ks < 8; ks++) { mma_ts(tm + TM_D3, at + ks * 8, desc_sw128(wq + (ks >> 2) * W1T_SLAB + (ks & 3) * 32), id32, acc); acc = 1; }
                     }

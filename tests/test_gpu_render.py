@@ -77,7 +77,8 @@ def test_ray_marcher_golden(golden):
     (2, 160, 16, 16),      # tcgen05 kernels, full 4-ray groups
     (1, 37, 32, 32),       # tcgen05 kernels, ragged last group (dead ray slots), both 32-sample rounds full
     (1, 30, 24, 20),       # tcgen05 kernels, partially filled rounds in both passes
-    (1, 24, 40, 40),       # more than 64 merged samples: mma.sync kernels
+    (1, 24, 40, 40),       # 80 merged samples = 3 rounds: tcgen05 backward re-runs the forward part of its oldest round
+    (1, 12, 72, 72),       # 144 merged samples: tcgen05 forward (6 rounds), mma.sync backward
 ])
 def test_render_backward_vs_oracle(gen_sd, n, r, dc, df):
     """Gradients w.r.t. planes and the four decoder tensors against autograd through the CPU oracle."""
