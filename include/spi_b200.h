@@ -178,6 +178,10 @@ int spi_lpips_tap_forward(const float* x, const float* yn, const float* lin, int
 int spi_lpips_tap_backward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, const float* gout, float* dx,
                            cudaStream_t stream);
 
+/* out[c] = sum over rows of x[row, c]; x row-major [rows, cols] fp32, cols a multiple of 4 (<= 128).  Used for the decoder bias
+ * gradients db1 = sum dpre, db2 = sum dout over the per-sample rows of spi_render_backward (triplane.py:123-135). */
+int spi_column_sums(const float* x, long long rows, int cols, float* out, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -394,12 +394,49 @@ __global__ void __launch_bounds__(256) epilogue_grad_reduce_kernel(const float* 
     if (dstrength && lane == 0 && ds != 0.f) atomicAdd(dstrength, ds);
 }
 
+// db only, for channel counts that are not a multiple of 4 (the RGB outputs of the toRGB layers, C = 3): the flat [pixels*C]
+// array is read as float4 vectors; the grid-stride is a multiple of C vectors, so each of a thread's 4 accumulators always sees
+// the same channel ((4 v + k) mod C is invariant), and the block combines them through shared memory.
+__global__ void __launch_bounds__(256) bias_grad_smallc_kernel(const float* __restrict__ dx, long long nvec, int C, float* __restrict__ db) {
+    __shared__ float sm[8];
+    if (threadIdx.x < 8) sm[threadIdx.x] = 0.f;
+    __syncthreads();
+    const long long T = (long long)gridDim.x * blockDim.x;            // host guarantees T % C == 0
+    const long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long v = v0; v < nvec; v += T) {
+        const float4 x = ldg_stream(reinterpret_cast<const float4*>(dx) + v);
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+    }
+    const int c0 = (int)((4 * v0) % C);
+    atomicAdd(sm + c0, acc.x);
+    atomicAdd(sm + (c0 + 1) % C, acc.y);
+    atomicAdd(sm + (c0 + 2) % C, acc.z);
+    atomicAdd(sm + (c0 + 3) % C, acc.w);
+    __syncthreads();
+    if (threadIdx.x < C) atomicAdd(db + threadIdx.x, sm[threadIdx.x]);
+}
+
 }  // namespace
 
 extern "C" int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,
                                         float* dstrength, cudaStream_t stream) {
-    SPI_CHECK_ARG(dx && pixels >= 0 && c >= 4 && c % 4 == 0 && c <= 4 * 32 * RG_MAXG, "epilogue_grad_reduce: C must be a multiple of 4, <= 1024");
+    SPI_CHECK_ARG(dx && pixels >= 0 && c >= 1, "epilogue_grad_reduce: bad argument");
     SPI_CHECK_ARG(((uintptr_t)dx & 15) == 0, "epilogue_grad_reduce: dx must be 16-byte aligned");
+    if (c % 4 != 0) {      // small channel counts (RGB): bias gradient only
+        SPI_CHECK_ARG(c <= 8 && db && !dpix && !dstrength && (pixels * c) % 4 == 0, "epilogue_grad_reduce: C %% 4 != 0 supports db only, C <= 8, numel %% 4 == 0");
+        cudaMemsetAsync(db, 0, sizeof(float) * c, stream);
+        if (pixels == 0) return SPI_OK;
+        const long long nvec = pixels * c / 4;
+        long long blocks = (nvec + 256 * 8 - 1) / (256 * 8), capb = (long long)spi_num_sms() * 8;
+        long long grid = blocks < capb ? blocks : capb;
+        grid = (grid + c - 1) / c * c;                          // grid * 256 vectors per sweep: a multiple of C
+        bias_grad_smallc_kernel<<<(unsigned)grid, 256, 0, stream>>>(dx, nvec, c, db);
+        SPI_COUNT_LAUNCH(1);
+        SPI_LAUNCH_CHECK("epilogue_grad_reduce");
+        return SPI_OK;
+    }
+    SPI_CHECK_ARG(c >= 4 && c <= 4 * 32 * RG_MAXG, "epilogue_grad_reduce: C must be <= 1024");
     SPI_CHECK_ARG(!dstrength || noise, "epilogue_grad_reduce: noise map required for dstrength");
     if (hw <= 0) hw = 1;
     SPI_CHECK_ARG(pixels % hw == 0 && pixels / hw <= 2147483647LL && pixels * c <= (1LL << 40), "epilogue_grad_reduce: pixels must be n * hw");

@@ -52,7 +52,9 @@ __global__ void __launch_bounds__(256) demod_coef_kernel(const float* __restrict
 // elementwise in OUTPUT memory order (coalesced stores for every layout): out = W * s * d
 __global__ void __launch_bounds__(256) modulate_apply_kernel(const float* __restrict__ W, const float* __restrict__ s,
                                                              const float* __restrict__ dcoef, float* __restrict__ out, int N, int O,
-                                                             int I, int KK, int layout) {
+                                                             int I, int KK, int layout_flags) {
+    const int layout = layout_flags & 3;
+    const bool flip = (layout_flags & 4) != 0;      // taps written in reverse order: out[.., k] = W[.., KK-1-k] (= w.flip([3, 4]))
     const long long total = (long long)N * O * I * KK;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long long)gridDim.x * blockDim.x) {
         int n, o, i, k;
@@ -60,7 +62,7 @@ __global__ void __launch_bounds__(256) modulate_apply_kernel(const float* __rest
         if (layout == 0) { k = (int)(r % KK); r /= KK; i = (int)(r % I); r /= I; o = (int)(r % O); n = (int)(r / O); }
         else if (layout == 1) { i = (int)(r % I); r /= I; k = (int)(r % KK); r /= KK; o = (int)(r % O); n = (int)(r / O); }
         else { o = (int)(r % O); r /= O; k = (int)(r % KK); r /= KK; i = (int)(r % I); n = (int)(r / I); }
-        float v = W[((size_t)o * I + i) * KK + k] * s[(size_t)n * I + i];
+        float v = W[((size_t)o * I + i) * KK + (flip ? KK - 1 - k : k)] * s[(size_t)n * I + i];
         if (dcoef) v *= dcoef[(size_t)n * O + o];
         out[q] = v;
     }
@@ -69,8 +71,10 @@ __global__ void __launch_bounds__(256) modulate_apply_kernel(const float* __rest
 // grid (O), block 256: loops over n; dW written (no atomics), ds accumulated with atomics across o
 __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restrict__ W, const float* __restrict__ s, const float* __restrict__ dcoef,
                                                            const float* __restrict__ g, float* __restrict__ dW, float* __restrict__ ds,
-                                                           int N, int O, int I, int KK, int demod, int layout) {
+                                                           int N, int O, int I, int KK, int demod, int layout_flags) {
     __shared__ float sh[32];
+    const int layout = layout_flags & 3;
+    const bool flip = (layout_flags & 4) != 0;      // g holds the gradient of the tap-reversed weights
     const int o = blockIdx.x;
     const int len = I * KK;
     const float* w = W + (size_t)o * len;
@@ -83,7 +87,7 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
             float acc = 0.f;
             for (int q = threadIdx.x; q < len; q += blockDim.x) {      // q walks g's memory order for layouts 0 and 1
                 const int i = (layout == 1) ? q % I : q / KK, k = (layout == 1) ? q / I : q % KK;
-                acc += g[widx(layout, n, o, i, k, O, I, KK)] * w[i * KK + k] * sn[i];
+                acc += g[widx(layout, n, o, i, k, O, I, KK)] * w[i * KK + (flip ? KK - 1 - k : k)] * sn[i];
             }
             A = block_sum(acc, sh);
         }
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
             for (int k = 0; k < KK; k++) {
                 const int e = i * KK + k;
                 const float ws = w[e] * si;
-                const float ge = g[widx(layout, n, o, i, k, O, I, KK)];
+                const float ge = g[widx(layout, n, o, i, flip ? KK - 1 - k : k, O, I, KK)];
                 const float t = demod ? d * (ge - dA * ws) : ge;
                 if (dw) dw[e] = (n == 0 ? 0.f : dw[e]) + si * t;
                 dsi += w[e] * t;
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
 
 extern "C" int spi_modulate_weights(const float* weight, const float* styles, float* out, float* dcoef, int n, int o, int i, int kk,
                                     int demodulate, int layout, cudaStream_t stream) {
-    SPI_CHECK_ARG(layout >= 0 && layout <= 2, "modulate_weights: layout must be 0 (OIK), 1 (OKI) or 2 (IKO)");
+    SPI_CHECK_ARG(layout >= 0 && (layout & 3) <= 2 && layout < 8, "modulate_weights: layout must be 0 (OIK), 1 (OKI) or 2 (IKO), +4 to reverse the taps");
     SPI_CHECK_ARG(weight && styles && out, "modulate_weights: null pointer");
     SPI_CHECK_ARG(n >= 1 && o >= 1 && i >= 1 && kk >= 1 && n <= 65535, "modulate_weights: bad shape");
     SPI_CHECK_ARG(!demodulate || dcoef, "modulate_weights: dcoef buffer required when demodulating");

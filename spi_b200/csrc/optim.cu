@@ -105,3 +105,54 @@ extern "C" int spi_downsample2x(const float* x, float* y, long long planes, int 
     SPI_LAUNCH_CHECK("downsample2x");
     return SPI_OK;
 }
+
+// Column sums of a tall row-major matrix x [rows, cols] (cols % 4 == 0, <= 128): the bias gradients of the OSG decoder,
+// db1 = sum_rows dpre, db2 = sum_rows dout (rows = millions of samples).  HBM-streaming: a warp reads whole rows with 128-bit
+// loads (32 / (cols/4) rows per instruction), 4 loads in flight per lane; per-lane partials are combined through shared memory
+// and one atomicAdd per column per CTA.
+namespace {
+
+__global__ void __launch_bounds__(256) column_sums_kernel(const float* __restrict__ x, long long rows, int cols, float* __restrict__ out) {
+    __shared__ float sm[128];
+    if (threadIdx.x < 128) sm[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int c4 = cols >> 2;
+    const long long nvec = rows * c4;
+    const long long T = (long long)gridDim.x * blockDim.x;            // host guarantees T % c4 == 0: a thread's column never changes
+    const long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    long long v = v0;
+    for (; v + 3 * T < nvec; v += 4 * T) {
+        const float4 a = ldg_stream(reinterpret_cast<const float4*>(x) + v), b = ldg_stream(reinterpret_cast<const float4*>(x) + v + T);
+        const float4 c = ldg_stream(reinterpret_cast<const float4*>(x) + v + 2 * T), d = ldg_stream(reinterpret_cast<const float4*>(x) + v + 3 * T);
+        acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+        acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; v < nvec; v += T) {
+        const float4 a = ldg_stream(reinterpret_cast<const float4*>(x) + v);
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    const int col = (int)(v0 % c4) * 4;
+    atomicAdd(sm + col, acc.x); atomicAdd(sm + col + 1, acc.y); atomicAdd(sm + col + 2, acc.z); atomicAdd(sm + col + 3, acc.w);
+    __syncthreads();
+    if (threadIdx.x < cols) atomicAdd(out + threadIdx.x, sm[threadIdx.x]);
+}
+
+}  // namespace
+
+extern "C" int spi_column_sums(const float* x, long long rows, int cols, float* out, cudaStream_t stream) {
+    SPI_CHECK_ARG(x && out && rows >= 0 && cols >= 4 && cols % 4 == 0 && cols <= 128, "column_sums: cols must be a multiple of 4, <= 128");
+    SPI_CHECK_ARG(((uintptr_t)x & 15) == 0, "column_sums: x must be 16-byte aligned");
+    cudaMemsetAsync(out, 0, sizeof(float) * cols, stream);
+    if (rows == 0) return SPI_OK;
+    const int c4 = cols / 4;
+    long long nvec = rows * c4, blocks = (nvec + 256 * 16 - 1) / (256 * 16), cap = (long long)spi_num_sms() * 8;
+    long long grid = blocks < cap ? blocks : cap;
+    int need = c4, r256 = 256;                                   // grid * 256 must be a multiple of c4
+    while (need % 2 == 0 && r256 % 2 == 0) { need /= 2; r256 /= 2; }
+    grid = (grid + need - 1) / need * need;
+    column_sums_kernel<<<(unsigned)grid, 256, 0, stream>>>(x, rows, cols, out);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("column_sums");
+    return SPI_OK;
+}

@@ -8,10 +8,12 @@ import torch
 from .. import _lib
 
 LAYOUTS = {'oihw': 0, 'ohwi': 1, 'ihwo': 2}
+FLIP = 4          # + FLIP: the taps are written reversed (the result equals w.flip([3, 4])), see modulate.cu
 
 
 def _alloc(n, o, i, kh, kw, layout, device):
     """Logical [N,O,I,kh,kw] tensor whose memory order is the requested layout."""
+    layout &= 3
     if layout == 0:
         return torch.empty(n, o, i, kh, kw, device=device)
     if layout == 1:
@@ -39,7 +41,8 @@ class _Modulate(torch.autograd.Function):
         o, i, kh, kw = weight.shape
         n = styles.shape[0]
         ref = _alloc(n, o, i, kh, kw, ctx.layout, weight.device)
-        if g.stride() != ref.stride():          # re-lay the incoming gradient only if autograd handed it over differently
+        same = all(gs == rs for gs, rs, sz in zip(g.stride(), ref.stride(), g.shape) if sz > 1)
+        if not same:                            # re-lay the incoming gradient only if autograd handed it over differently
             ref.copy_(g)
             g = ref
         gw = torch.empty_like(weight) if ctx.needs_input_grad[0] else None
@@ -50,8 +53,10 @@ class _Modulate(torch.autograd.Function):
         return gw, gs, None, None
 
 
-def modulate_weights(weight, styles, demodulate=True, layout='oihw'):
-    """weight [O,I,kh,kw], styles [N,I] -> per-sample weights, logical shape [N,O,I,kh,kw], memory order `layout`."""
+def modulate_weights(weight, styles, demodulate=True, layout='oihw', flip=False):
+    """weight [O,I,kh,kw], styles [N,I] -> per-sample weights, logical shape [N,O,I,kh,kw], memory order `layout`; `flip=True`
+    returns them with the taps reversed (what `_conv2d_wrapper(..., flip_weight=False)` would build with `w.flip([2, 3])`,
+    conv2d_resample.py:38-40) at no extra pass."""
     if not weight.is_cuda:
         raise RuntimeError('spi_b200.modulate_weights: tensors must reside on a CUDA device (no CPU path in this build)')
-    return _Modulate.apply(weight.float(), styles.float(), bool(demodulate), LAYOUTS[layout])
+    return _Modulate.apply(weight.float(), styles.float(), bool(demodulate), LAYOUTS[layout] | (FLIP if flip else 0))

@@ -34,10 +34,17 @@ def _dense_like(x):
 
 def _fused_reductions(dx, want_db, noise=None, want_dpix=False, want_ds=False):
     """db / per-pixel sum / dstrength from one pass over a channels-last fp32 dx; None when the fast path does not apply."""
-    if not (dx.ndim == 4 and dx.dtype == torch.float32 and dx.shape[1] % 4 == 0 and 4 <= dx.shape[1] <= 1024
-            and dx.is_contiguous(memory_format=torch.channels_last) and dx.data_ptr() % 16 == 0):
+    if not (dx.ndim == 4 and dx.dtype == torch.float32 and dx.is_contiguous(memory_format=torch.channels_last) and dx.data_ptr() % 16 == 0):
         return None
     n, c, h, w = dx.shape
+    if c % 4 != 0:          # RGB outputs of the toRGB layers: bias gradient only (small-C kernel)
+        if not (c <= 8 and want_db and not want_dpix and not want_ds and dx.numel() % 4 == 0 and dx.numel() > 0):
+            return None
+        db = torch.empty(c, device=dx.device)
+        _lib.check(_lib.load().spi_epilogue_grad_reduce(_lib.ptr(dx), n * h * w, c, h * w, None, _lib.ptr(db), None, None, _lib.stream()))
+        return db, None, None
+    if not 4 <= c <= 1024:
+        return None
     if want_db and want_ds:                      # packed so the library zero-fills both with one memset
         buf = torch.empty(c + 1, device=dx.device)
         db, ds = buf[:c], buf[c]

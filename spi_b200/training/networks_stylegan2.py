@@ -50,9 +50,17 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     assert styles.ndim == 2 and styles.shape[1] == in_channels and styles.shape[0] in (1, batch_size)     # 1: one style shared by the batch
     if fused_modconv and x.dtype == torch.float32:
         # one launch: w[n,o,i,k] = W*s (*rsqrt(sum (W s)^2 + 1e-8))  (spi_modulate_weights)
-        w = modulate_weights(weight, styles, demodulate, layout='ohwi')
         assert down == 1
-        x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
+        kh, kw = weight.shape[2:]
+        if up == 2:
+            # the stride-2 transposed convolution consumes [I,O,kh,kw] channels-last weights with the taps reversed when
+            # flip_weight is set (conv2d_resample.py:38-40,117): modulate_weights writes them like that directly
+            pre = bool(flip_weight) and (kh > 1 or kw > 1)
+            w = modulate_weights(weight, styles, demodulate, layout='ihwo', flip=pre)
+            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight and not pre)
+        else:
+            w = modulate_weights(weight, styles, demodulate, layout='ohwi')
+            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
         if noise is not None:
             x = x + noise
         return x

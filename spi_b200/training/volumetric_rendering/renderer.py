@@ -60,8 +60,13 @@ def _decoder_grads(sc, n_rows, lr_mul):
         dw2 = torch.bmm(dout[:n_rows].view(chunks, k, -1).transpose(1, 2), hid[:n_rows].view(chunks, k, -1)).sum(0)[:33] * g2
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    db1 = dpre[:n_rows].sum(0) * lr_mul
-    db2 = dout[:n_rows, :33].sum(0) * lr_mul
+    # column sums of the tall scratch matrices at HBM speed (`spi_column_sums`; ATen's strided column reduction ran at 1.3 TB/s)
+    lib = _lib.load()
+    s1, s2 = torch.empty(64, device=f.device), torch.empty(36, device=f.device)
+    _lib.check(lib.spi_column_sums(_lib.ptr(dpre), n_rows, 64, _lib.ptr(s1), _lib.stream()))
+    _lib.check(lib.spi_column_sums(_lib.ptr(dout), n_rows, 36, _lib.ptr(s2), _lib.stream()))
+    db1 = s1 * lr_mul
+    db2 = s2[:33] * lr_mul
     return dw1, db1, dw2, db2
 
 

@@ -219,3 +219,18 @@ def test_bias_act_noise_vs_oracle(P):
         yg.backward(dy.cuda())
         for a, r in ((xg.grad, xo.grad), (bg.grad, bo.grad), (ng.grad, no.grad), (sg.grad, so.grad)):
             assert rel_l2(a, r) < 1e-5
+
+
+@pytest.mark.parametrize('shape', [(2, 3, 16, 24), (1, 3, 64, 64), (4, 6, 8, 10), (1, 5, 4, 4)])
+def test_bias_gradient_small_channel_counts_channels_last(P, shape):
+    """toRGB outputs are channels-last with C = 3: the bias gradient goes through the small-C reduction kernel."""
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=gen)
+    b = torch.randn(shape[1], generator=gen)
+    dy = torch.randn(*shape, generator=gen)
+    xo, bo = x.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    O.bias_act(xo, bo, act='linear', clamp=1.0).backward(dy)
+    xg = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bg = b.cuda().requires_grad_(True)
+    P.bias_act.bias_act(xg, bg, act='linear', clamp=1.0).backward(dy.cuda().contiguous(memory_format=torch.channels_last))
+    assert rel_l2(xg.grad, xo.grad) < TOL and rel_l2(bg.grad, bo.grad) < 1e-5
