@@ -1,8 +1,8 @@
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 900 python bench.py --gpus 1 --steps 24 --warmup 6 --no-cpu-baseline > gpurun_out/bench5.json 2> gpurun_out/bench5.err
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 24 --warmup 6 > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "rc=$?" >> gpurun_out/bench_n2.err
 python - <<'PY'
 import json
-d=json.load(open('gpurun_out/bench5.json'))
-print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'])
+for l in open('gpurun_out/bench_n2.json'):
+    if l.startswith('{'):
+        d=json.loads(l); print({k:d[k] for k in ('value','n_gpus','ms_per_step','gpu_launches')}, d['e2e']['value'], d['clocks'])
 PY
-timeout 300 python tools/profile_step.py > gpurun_out/profile_eager.txt 2>&1
+tail -1 gpurun_out/bench_n2.err
