@@ -87,6 +87,23 @@ int spi_render_backward(const float* planes, const float* origins, const float* 
                         const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, const float* g_feat,
                         const float* g_depth, float* g_planes, float* sc_f, float* sc_hid, float* sc_dpre, float* sc_dout, int n,
                         int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream);
+/* Same pair with the forward pass KEEPING its decoder activations for the backward pass (tcgen05 kernels; 180 GB of HBM make the
+ * ~0.5 GB per image cheaper than re-gathering 12 texel lines per sample and re-running layers 1-2): sv_h [S,64] hidden layer,
+ * sv_o [S,36] pre-activation outputs incl. bias (32 colours, sigma, 3 pad), sv_f [S,32] gathered features (NULL unless decoder
+ * weight gradients are wanted), sv_src [n,R,dc+df] uint8 storage index of every merged sample; S = n*R*(dc+df), rows in storage
+ * order (coarse i -> i, importance j -> dc + j).  The backward pass then writes sc_dpre / sc_dout in the same row order, so that
+ * dW1 = sc_dpre^T sv_f and dW2 = sc_dout^T sv_h.  spi_render_keeps_activations(dc, df) = 1 when these entry points apply. */
+int spi_render_keeps_activations(int dc, int df);
+int spi_render_forward_keep(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
+                            const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat, float* depth,
+                            float* wsum, float* depths_all, int* minmax, int n, int rays_per_image, long long plane_batch_stride,
+                            int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end, float box_warp, int disparity,
+                            float* sv_h, float* sv_o, float* sv_f, unsigned char* sv_src, cudaStream_t stream);
+int spi_render_backward_kept(const float* planes, const float* origins, const float* dirs, const float* depths_all, const int* minmax,
+                             const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, const float* g_feat,
+                             const float* g_depth, float* g_planes, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
+                             long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, const float* sv_h,
+                             const float* sv_o, const unsigned char* sv_src, cudaStream_t stream);
 /* ImportanceRenderer.run_model (renderer.py:142-149) on arbitrary points: coords [n, m, 3] -> rgb [n, m, 32],
  * sigma [n, m]; used by TriPlaneGenerator.sample / sample_mixed (triplane.py:91-102). */
 int spi_points_forward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,

@@ -71,6 +71,10 @@ struct RenderParams {
     float* g_planes;           // [N, H, W, 96]  (accumulated)
     float* sc_f; float* sc_hid; float* sc_dpre; float* sc_dout;   // per-sample [S,32] [S,64] [S,64] [S,36] rows for the decoder
                                // weight-gradient GEMMs; null when the decoder is frozen (stage 1)
+    // activations kept by the forward pass for the backward pass (tcgen05 kernels only; rows in STORAGE order: coarse sample i ->
+    // i, importance sample j -> dc + j): hidden layer [S,64], pre-activation outputs incl. bias [S,36] (32 colours, sigma, 3 pad),
+    // gathered features [S,32] (optional), and the storage index of every merged sample [n,R,D]
+    float* sv_h; float* sv_o; float* sv_f; unsigned char* sv_src;
 };
 
 __device__ __forceinline__ void load_decoder(Decoder* s, const RenderParams& p) {
@@ -1260,13 +1264,14 @@ int check_render(const RenderParams& p) {
     p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w1_gain = lr_mul * 0.17677669529663687f; p.w2_gain = lr_mul * 0.125f; \
     p.b_gain = lr_mul;
 
-extern "C" int spi_render_forward(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
-                                  const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
-                                  float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n,
-                                  int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end,
-                                  float box_warp, int disparity, cudaStream_t stream) {
+static int render_forward_impl(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
+                               const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
+                               float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n,
+                               int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end,
+                               float box_warp, int disparity, float* sv_h, float* sv_o, float* sv_f, unsigned char* sv_src, cudaStream_t stream) {
     RenderParams p;
     memset(&p, 0, sizeof(p));
+    p.sv_h = sv_h; p.sv_o = sv_o; p.sv_f = sv_f; p.sv_src = sv_src;
     p.planes = planes; p.origins = origins; p.dirs = dirs; p.jitter = jitter; p.u = u; FILL_DECODER(p);
     p.feat = feat; p.depth = depth; p.wsum = wsum; p.depths_all = depths_all; p.sigma_all = sigma_all; p.minmax = minmax;
     p.n = n; p.R = rays_per_image; p.H = plane_h; p.W = plane_w; p.dc = dc; p.df = df; p.plane_bs = plane_batch_stride;
@@ -1310,13 +1315,44 @@ extern "C" int spi_render_forward(const float* planes, const float* origins, con
     return SPI_OK;
 }
 
-extern "C" int spi_render_backward(const float* planes, const float* origins, const float* dirs, const float* depths_all,
-                                   const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
-                                   float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_f,
-                                   float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
-                                   long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream) {
+// 1 when spi_render_forward_keep / spi_render_backward_kept run on the tcgen05 kernels for these depth resolutions
+extern "C" int spi_render_keeps_activations(int dc, int df) {
+    return (getenv("SPI_RENDER_SIMT") == nullptr && getenv("SPI_RENDER_MMA") == nullptr && getenv("SPI_RENDER_RECOMPUTE") == nullptr &&
+            tcr::rounds_of(dc) + tcr::rounds_of(df) <= tcr::MAX_ROUNDS && dc + df <= tcb::MAXD) ? 1 : 0;
+}
+
+extern "C" int spi_render_forward(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
+                                  const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
+                                  float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n,
+                                  int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end,
+                                  float box_warp, int disparity, cudaStream_t stream) {
+    return render_forward_impl(planes, origins, dirs, jitter, u, w1, b1, w2, b2, lr_mul, feat, depth, wsum, depths_all, sigma_all, minmax, n,
+                               rays_per_image, plane_batch_stride, plane_h, plane_w, dc, df, ray_start, ray_end, box_warp, disparity, nullptr, nullptr,
+                               nullptr, nullptr, stream);
+}
+
+extern "C" int spi_render_forward_keep(const float* planes, const float* origins, const float* dirs, const float* jitter, const float* u,
+                                       const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, float* feat,
+                                       float* depth, float* wsum, float* depths_all, int* minmax, int n, int rays_per_image,
+                                       long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end,
+                                       float box_warp, int disparity, float* sv_h, float* sv_o, float* sv_f, unsigned char* sv_src,
+                                       cudaStream_t stream) {
+    SPI_CHECK_ARG(sv_h && sv_o && sv_src, "render_forward_keep: null activation buffer");
+    SPI_CHECK_ARG(spi_render_keeps_activations(dc, df), "render_forward_keep: %d+%d samples per ray are outside the tcgen05 kernels' range", dc, df);
+    return render_forward_impl(planes, origins, dirs, jitter, u, w1, b1, w2, b2, lr_mul, feat, depth, wsum, depths_all, nullptr, minmax, n,
+                               rays_per_image, plane_batch_stride, plane_h, plane_w, dc, df, ray_start, ray_end, box_warp, disparity, sv_h, sv_o, sv_f,
+                               sv_src, stream);
+}
+
+static int render_backward_impl(const float* planes, const float* origins, const float* dirs, const float* depths_all,
+                                const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
+                                float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_f,
+                                float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
+                                long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, const float* sv_h,
+                                const float* sv_o, const unsigned char* sv_src, cudaStream_t stream) {
     RenderParams p;
     memset(&p, 0, sizeof(p));
+    p.sv_h = (float*)sv_h; p.sv_o = (float*)sv_o; p.sv_src = (unsigned char*)sv_src;
     p.planes = planes; p.origins = origins; p.dirs = dirs; FILL_DECODER(p);
     p.depths_all = (float*)depths_all; p.minmax = (int*)minmax; p.g_feat = g_feat; p.g_depth = g_depth; p.g_planes = g_planes;
     p.sc_f = sc_f; p.sc_hid = sc_hid; p.sc_dpre = sc_dpre; p.sc_dout = sc_dout;
@@ -1352,6 +1388,27 @@ extern "C" int spi_render_backward(const float* planes, const float* origins, co
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("render_backward");
     return SPI_OK;
+}
+
+extern "C" int spi_render_backward(const float* planes, const float* origins, const float* dirs, const float* depths_all,
+                                   const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
+                                   float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_f,
+                                   float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
+                                   long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream) {
+    return render_backward_impl(planes, origins, dirs, depths_all, minmax, w1, b1, w2, b2, lr_mul, g_feat, g_depth, g_planes, sc_f, sc_hid, sc_dpre,
+                                sc_dout, n, rays_per_image, plane_batch_stride, plane_h, plane_w, dc, df, box_warp, nullptr, nullptr, nullptr, stream);
+}
+
+extern "C" int spi_render_backward_kept(const float* planes, const float* origins, const float* dirs, const float* depths_all,
+                                        const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
+                                        float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_dpre,
+                                        float* sc_dout, int n, int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w,
+                                        int dc, int df, float box_warp, const float* sv_h, const float* sv_o, const unsigned char* sv_src,
+                                        cudaStream_t stream) {
+    SPI_CHECK_ARG(sv_h && sv_o && sv_src, "render_backward_kept: null activation buffer");
+    SPI_CHECK_ARG(spi_render_keeps_activations(dc, df), "render_backward_kept: %d+%d samples per ray are outside the tcgen05 kernels' range", dc, df);
+    return render_backward_impl(planes, origins, dirs, depths_all, minmax, w1, b1, w2, b2, lr_mul, g_feat, g_depth, g_planes, nullptr, nullptr, sc_dpre,
+                                sc_dout, n, rays_per_image, plane_batch_stride, plane_h, plane_w, dc, df, box_warp, sv_h, sv_o, sv_src, stream);
 }
 
 extern "C" int spi_points_forward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,

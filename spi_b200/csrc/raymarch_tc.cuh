@@ -69,7 +69,8 @@ __device__ __forceinline__ void publish_corners(int W, int H, float x, float y, 
 }
 
 // this warp's 16 samples (rows row0 + 16 half ...) of the A tiles, hi / lo halves, swizzled
-__device__ __forceinline__ void gather_rows(const float* __restrict__ pl, const int2* s_ow, uint8_t* a_hi, uint8_t* a_lo, int row0, int lane, int half) {
+__device__ __forceinline__ void gather_rows(const float* __restrict__ pl, const int2* s_ow, uint8_t* a_hi, uint8_t* a_lo, int row0, int lane, int half,
+                                            float* frows, int nvalid) {
     const int sub = lane & 7, grp = lane >> 3;
     const float4* pls = reinterpret_cast<const float4*>(pl) + sub;
 #pragma unroll 2
@@ -93,6 +94,7 @@ __device__ __forceinline__ void gather_rows(const float* __restrict__ pl, const 
         const uint32_t o = swz(row0 + smp, sub);
         *reinterpret_cast<uint4*>(a_hi + o) = h;
         *reinterpret_cast<uint4*>(a_lo + o) = l;
+        if (frows && smp < nvalid) *reinterpret_cast<float4*>(frows + smp * NF + 4 * sub) = acc;      // kept for the decoder weight gradients
     }
 }
 
@@ -200,9 +202,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                 valid = idx < df;
                 if (valid) d = fine[idx];
             }
+            // storage row of this lane's sample in the tensors kept for the backward pass
+            const int st0 = coarse ? round * 32 : dc + (round - RC) * 32;
+            const long long srow = ray * D + st0 + lane;
+            const int nvalid = live ? min(32, (coarse ? dc : dc + df) - st0) : 0;
             publish_corners(p.W, p.H, r.ox + d * r.dx, r.oy + d * r.dy, r.oz + d * r.dz, scale, valid, g_ow, lane, half);
             pair_sync(q);
-            gather_rows(pl, g_ow, a_hi, a_lo, q * 32, lane, half);
+            gather_rows(pl, g_ow, a_hi, a_lo, q * 32, lane, half, p.sv_f ? p.sv_f + (ray * D + st0) * NF : nullptr, nvalid);
             fence_async_smem();
             fence_before();
             __syncthreads();
@@ -230,9 +236,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                 tmem_ld16(tlane + TM_H_HI + c0, v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int c = 0; c < 16; c++) split(mma::softplus_fast(v[c] + b1s[c0 + c]), hh[c], hl[c]);
+                for (int c = 0; c < 16; c++) { v[c] = mma::softplus_fast(v[c] + b1s[c0 + c]); split(v[c], hh[c], hl[c]); }
                 tmem_st16(tlane + TM_H_HI + c0, hh);
                 tmem_st16(tlane + TM_H_LO + c0, hl);
+                if (p.sv_h && lane < nvalid) {
+                    float4* dst = reinterpret_cast<float4*>(p.sv_h + srow * NH + c0);
+#pragma unroll
+                    for (int c = 0; c < 4; c++) dst[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+                }
             }
             tmem_wait_st();
             fence_before();
@@ -256,11 +267,24 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
             if (!mbar_wait_bounded(&bars[1], ph1)) atomicExch(err, 2);
             ph1 ^= 1;
             fence_after();
+            if (p.sv_o) {          // pre-activation colours (+bias) of this warp's 16 columns, kept for the backward pass
+                float v[16];
+                tmem_ld16(tlane + TM_D2 + round * TM_D2_STRIDE + half * 16, v);
+                tmem_wait_ld();
+                if (lane < nvalid) {
+                    float4* dst = reinterpret_cast<float4*>(p.sv_o + srow * 36 + half * 16);
+#pragma unroll
+                    for (int c = 0; c < 4; c++)
+                        dst[c] = make_float4(v[4 * c] + b2s[half * 16 + 4 * c], v[4 * c + 1] + b2s[half * 16 + 4 * c + 1], v[4 * c + 2] + b2s[half * 16 + 4 * c + 2],
+                                             v[4 * c + 3] + b2s[half * 16 + 4 * c + 3]);
+                }
+            }
             if (half == 0) {
                 float sg;
                 tmem_ld1(tlane + TM_D2 + round * TM_D2_STRIDE + 32, sg);
                 tmem_wait_ld();
                 sg += b2s[32];
+                if (p.sv_o && lane < nvalid) p.sv_o[srow * 36 + 32] = sg;
                 (coarse ? sigc : sigf)[idx] = sg;
                 __syncwarp();
                 if (round == RC - 1 && df > 0) {            // all coarse sigmas known: importance sampling
@@ -279,6 +303,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                     for (int k = 0; k < dc; k++) rk += (dcs[k] < v) || (dcs[k] == v && k < i);
                     for (int k = 0; k < df; k++) rk += (fine[k] < v);
                     pos_c[i] = rk; sigm[rk] = sigc[i]; dall[rk] = v;
+                    if (p.sv_src && live) p.sv_src[ray * D + rk] = (unsigned char)i;
                 }
             } else {
                 for (int j = lane; j < df; j += 32) {
@@ -287,10 +312,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) render_fwd_tc_kernel(RenderPara
                     for (int k = 0; k < dc; k++) rk += (dcs[k] <= v);
                     for (int k = 0; k < df; k++) rk += (fine[k] < v) || (fine[k] == v && k < j);
                     pos_f[j] = rk; sigm[rk] = sigf[j]; dall[rk] = v;
+                    if (p.sv_src && live) p.sv_src[ray * D + rk] = (unsigned char)(dc + j);
                 }
             }
         } else if (half == 0) {
-            for (int i = lane; i < dc; i += 32) { sigm[i] = sigc[i]; dall[i] = dcs[i]; pos_c[i] = i; }
+            for (int i = lane; i < dc; i += 32) { sigm[i] = sigc[i]; dall[i] = dcs[i]; pos_c[i] = i; if (p.sv_src && live) p.sv_src[ray * D + i] = (unsigned char)i; }
         }
         pair_sync(q);
         float depth = 0.f, wsum = 0.f;

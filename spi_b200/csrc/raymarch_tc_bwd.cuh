@@ -18,6 +18,9 @@
 // older rounds in B3.  All four GEMMs are 3xTF32 (hi*hi + lo*hi + hi*lo) with fp32 accumulation, like the forward pass.
 // Decoder weight gradients: when requested the per-sample rows f | hid | dpre | dout are written to the scratch tensors and
 // reduced by two TF32 GEMMs on the host side (unchanged contract of spi_render_backward).
+// When the forward pass kept its activations (RenderParams::sv_*: hidden layer, pre-activation outputs, merged -> storage index)
+// B1 shrinks to one 144-byte row read per sample and B3 reads H from global memory: no gather, no layers 1-2, half the MMA
+// round-trips; dpre / dout rows are then written in storage order so that they pair with the kept f / hid rows.
 #pragma once
 
 namespace tcb {
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
     const float dlo = __int_as_float(p.minmax[0]), dhi = __int_as_float(p.minmax[1]);
     uint32_t ph = 0;
     const int sub = lane & 7, grp = lane >> 3;
+    const bool saved = p.sv_h != nullptr;          // hidden layer / outputs kept by the forward pass: no gather, no layers 1-2 here
 
     for (long long group = blockIdx.x; group < groups; group += gridDim.x) {
         const long long ray = group * 4 + q;
@@ -237,18 +241,29 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
         for (int rd = 0; rd < rounds; rd++) {
             const int sl = rd & 1;
             const int i = rd * 32 + lane;
-            fwd_round(rd, sl, true);
-            {   // p_i = <g_rgb, rgb_i>: 8 colour columns per warp of the quad; sigma by the first warp
-                float v[8];
+            float v[8];
+            float sg = 0.f;
+            if (saved) {      // pre-activation outputs (bias included) straight from the forward pass, storage-order rows
+                const long long row = rr * D + (i < D ? p.sv_src[rr * D + i] : 0);
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.sv_o + row * 36 + part * 8));
+                const float4 b = __ldg(reinterpret_cast<const float4*>(p.sv_o + row * 36 + part * 8) + 1);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                if (part == 0) sg = __ldg(p.sv_o + row * 36 + 32);
+            } else {
+                fwd_round(rd, sl, true);
                 tmem_ld8(tlane + tm_d2(sl) + part * 8, v);
-                float sg = 0.f;
                 if (part == 0) tmem_ld1(tlane + tm_d2(sl) + 32, sg);
                 tmem_wait_ld();
+#pragma unroll
+                for (int c = 0; c < 8; c++) v[c] += b2s[part * 8 + c];
+                sg += b2s[32];
+            }
+            {   // p_i = <g_rgb, rgb_i>: 8 colour columns per warp of the quad; sigma by the first warp
                 float pdv = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; c++) pdv = fmaf(gfe[part * 8 + c], mma::rgb_act_fast(v[c] + b2s[part * 8 + c]), pdv);
+                for (int c = 0; c < 8; c++) pdv = fmaf(gfe[part * 8 + c], mma::rgb_act_fast(v[c]), pdv);
                 pd[part * MAXD + i] = pdv;
-                if (part == 0) sig[i] = sg + b2s[32];
+                if (part == 0) sig[i] = sg;
             }
         }
         quad_sync(q);
@@ -321,9 +336,11 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
         // ================================================================ B3: the two resident rounds first, older rounds are recomputed
         for (int rd = rounds - 1; rd >= 0; rd--) {
             const int sl = rd & 1;
-            if (rd < rounds - 2) fwd_round(rd, sl, false);
+            if (!saved && rd < rounds - 2) fwd_round(rd, sl, false);
             const int i = rd * 32 + lane;
             const bool valid = i < D;
+            // row of this sample in the per-sample tensors: storage order when the forward pass kept its activations, merged order otherwise
+            const long long row = rr * D + (saved ? (valid ? p.sv_src[rr * D + i] : 0) : min(i, D - 1));
             float gs = 0.f, a = 0.f;
             if (valid) {
                 gs = 0.5f * ((i > 0 ? gmid[i - 1] : 0.f) + (i < D - 1 ? gmid[i] : 0.f));
@@ -332,18 +349,26 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
             {   // dOut: colours [8 part, 8 part + 8) (+ sigma and the zero padding by the first warp), hi over D2 in place
                 float v[8];
                 uint32_t hh[16], hl[16];
-                tmem_ld8(tlane + tm_d2(sl) + part * 8, v);
-                tmem_wait_ld();
+                if (saved) {
+                    const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.sv_o + row * 36 + part * 8));
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.sv_o + row * 36 + part * 8) + 1);
+                    v[0] = a4.x; v[1] = a4.y; v[2] = a4.z; v[3] = a4.w; v[4] = b4.x; v[5] = b4.y; v[6] = b4.z; v[7] = b4.w;
+                } else {
+                    tmem_ld8(tlane + tm_d2(sl) + part * 8, v);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int c = 0; c < 8; c++) v[c] += b2s[part * 8 + c];
+                }
 #pragma unroll
                 for (int c = 0; c < 8; c++) {
-                    const float so = mma::sigmoid_fast(v[c] + b2s[part * 8 + c]);
+                    const float so = mma::sigmoid_fast(v[c]);
                     v[c] = valid ? gfe[part * 8 + c] * a * (1.f + 2.f * 0.001f) * so * (1.f - so) : 0.f;
                     split(v[c], hh[c], hl[c]);
                 }
                 tmem_st8(tlane + tm_d2(sl) + part * 8, hh);
                 tmem_st8(tlane + TM_DOUT_LO + part * 8, hl);
                 if (p.sc_dout && live && valid) {
-                    float* dst = p.sc_dout + (ray * D + i) * 36;
+                    float* dst = p.sc_dout + row * 36;
 #pragma unroll
                     for (int c = 0; c < 8; c++) dst[1 + part * 8 + c] = v[c];
                     if (part == 0) dst[0] = gs;
@@ -379,8 +404,17 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 float dh[16], h1[16], h2[16];
                 uint32_t hh[16], hl[16];
                 tmem_ld16(tlane + TM_D3 + c0, dh);
-                tmem_ld16(tlane + tm_h_hi(sl) + c0, h1);
-                tmem_ld16(tlane + tm_h_lo(sl) + c0, h2);
+                if (saved) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        const float4 h4 = __ldg(reinterpret_cast<const float4*>(p.sv_h + row * NH + c0) + c);
+                        h1[4 * c] = h4.x; h1[4 * c + 1] = h4.y; h1[4 * c + 2] = h4.z; h1[4 * c + 3] = h4.w;
+                        h2[4 * c] = 0.f; h2[4 * c + 1] = 0.f; h2[4 * c + 2] = 0.f; h2[4 * c + 3] = 0.f;
+                    }
+                } else {
+                    tmem_ld16(tlane + tm_h_hi(sl) + c0, h1);
+                    tmem_ld16(tlane + tm_h_lo(sl) + c0, h2);
+                }
                 tmem_wait_ld();
 #pragma unroll
                 for (int c = 0; c < 16; c++) {
@@ -390,7 +424,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
                 tmem_st16(tlane + tm_h_hi(sl) + c0, hh);
                 tmem_st16(tlane + tm_h_lo(sl) + c0, hl);
                 if (p.sc_dpre && live && valid) {
-                    float4* dst = reinterpret_cast<float4*>(p.sc_dpre + (ray * D + i) * NH + c0);
+                    float4* dst = reinterpret_cast<float4*>(p.sc_dpre + row * NH + c0);
 #pragma unroll
                     for (int c = 0; c < 4; c++) dst[c] = make_float4(dh[4 * c], dh[4 * c + 1], dh[4 * c + 2], dh[4 * c + 3]);
                 }

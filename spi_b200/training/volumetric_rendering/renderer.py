@@ -13,6 +13,7 @@ from ... import _lib
 from .ray_marcher import MipRayMarcher2
 
 SCRATCH_COLS = (32, 64, 64, 36)
+KEEP_ACTIVATIONS = True       # forward keeps hidden layer / outputs / features for backward when decoder gradients are wanted (tcgen05 kernels)
 KERNEL_TIMER = None      # bench.py installs an object with .start(tag) / .stop(tag) that records CUDA events on the launch stream
 
 
@@ -85,17 +86,35 @@ class _RenderFn(torch.autograd.Function):
         wsum = torch.empty(n, r, 1, device=dev)
         depths_all = torch.empty(n, r, dc + df, device=dev)
         minmax = torch.empty(2, dtype=torch.int32, device=dev)
+        # Keeping activations pays when the decoder is being trained (the backward pass would otherwise write the same f / hid rows
+        # for the weight-gradient GEMMs: measured 0.31 + 1.31 -> 0.42 + 1.10 ms/img); with frozen decoder weights the forward
+        # pass's extra 0.4 GB/img of stores cost what the backward pass saves (its floor is the L2 atomic traffic of the scatter)
+        keep = any(ctx.needs_input_grad[1:5]) and KEEP_ACTIVATIONS and bool(lib.spi_render_keeps_activations(dc, df))
+        kept = None
+        if keep:
+            # the forward pass keeps hidden layer / outputs (/ features) of every sample for the backward pass: ~0.5 GB per image
+            rows = n * r * (dc + df)
+            need_dec = any(ctx.needs_input_grad[1:5])
+            kept = (torch.empty(rows, 64, device=dev), torch.empty(rows, 36, device=dev),
+                    torch.empty(rows, 32, device=dev) if need_dec else None, torch.empty(n, r, dc + df, dtype=torch.uint8, device=dev))
         if KERNEL_TIMER is not None:
             KERNEL_TIMER.start('render_fwd', n)
-        _lib.check(lib.spi_render_forward(
-            _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(jitter), _lib.ptr(u), _lib.ptr(w1), _lib.ptr(b1),
-            _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(feat), _lib.ptr(depth), _lib.ptr(wsum), _lib.ptr(depths_all),
-            None, _lib.ptr(minmax), n, r, plane_bs, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
-            int(opts['disparity']), _lib.stream()))
+        if keep:
+            _lib.check(lib.spi_render_forward_keep(
+                _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(jitter), _lib.ptr(u), _lib.ptr(w1), _lib.ptr(b1),
+                _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(feat), _lib.ptr(depth), _lib.ptr(wsum), _lib.ptr(depths_all),
+                _lib.ptr(minmax), n, r, plane_bs, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
+                int(opts['disparity']), _lib.ptr(kept[0]), _lib.ptr(kept[1]), _lib.ptr(kept[2]), _lib.ptr(kept[3]), _lib.stream()))
+        else:
+            _lib.check(lib.spi_render_forward(
+                _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(jitter), _lib.ptr(u), _lib.ptr(w1), _lib.ptr(b1),
+                _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(feat), _lib.ptr(depth), _lib.ptr(wsum), _lib.ptr(depths_all),
+                None, _lib.ptr(minmax), n, r, plane_bs, h, w, dc, df, opts['ray_start'], opts['ray_end'], opts['box_warp'],
+                int(opts['disparity']), _lib.stream()))
         if KERNEL_TIMER is not None:
             KERNEL_TIMER.stop('render_fwd')
         ctx.save_for_backward(planes, w1, b1, w2, b2, origins, dirs, depths_all, minmax)
-        ctx.opts, ctx.plane_bs = opts, plane_bs
+        ctx.opts, ctx.plane_bs, ctx.kept = opts, plane_bs, kept
         ctx.mark_non_differentiable(wsum)
         return feat, depth, wsum
 
@@ -116,7 +135,26 @@ class _RenderFn(torch.autograd.Function):
         gw = None
         if KERNEL_TIMER is not None:
             KERNEL_TIMER.start('render_bwd', n)
-        if need_dec:
+        kept = ctx.kept
+        if kept is not None:
+            rows = n * r * (dc + df)
+            sc_dpre = torch.empty(rows, 64, device=planes.device) if need_dec else None
+            sc_dout = torch.empty(rows, 36, device=planes.device) if need_dec else None
+            _lib.check(lib.spi_render_backward_kept(
+                _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
+                _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
+                _lib.ptr(g_planes), _lib.ptr(sc_dpre), _lib.ptr(sc_dout), n, r, plane_bs, h, w, dc, df, opts['box_warp'],
+                _lib.ptr(kept[0]), _lib.ptr(kept[1]), _lib.ptr(kept[3]), _lib.stream()))
+            if KERNEL_TIMER is not None:
+                KERNEL_TIMER.stop('render_bwd')
+            gw = (None, None, None, None)
+            if need_dec:
+                if KERNEL_TIMER is not None:
+                    KERNEL_TIMER.start('render_dec_grads', n)
+                gw = _decoder_grads((kept[2], kept[0], sc_dpre, sc_dout), rows, opts['lr_mul'])
+                if KERNEL_TIMER is not None:
+                    KERNEL_TIMER.stop('render_dec_grads')
+        elif need_dec:
             # all images in one launch: the per-sample rows (784 B/sample) of the whole batch feed two TF32 GEMMs
             rows = n * r * (dc + df)
             sc = [torch.empty(rows, c, device=planes.device) for c in SCRATCH_COLS]
