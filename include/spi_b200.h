@@ -80,13 +80,15 @@ int spi_render_forward(const float* planes, const float* origins, const float* d
                        float* depth, float* wsum, float* depths_all, float* sigma_all, int* minmax, int n, int rays_per_image,
                        long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float ray_start, float ray_end, float box_warp, int disparity,
                        cudaStream_t stream);
-/* Backward of the above w.r.t. planes (accumulated into g_planes, may be NULL) and, when the sc_* buffers are
+/* Backward of the above w.r.t. planes (accumulated into g_planes, may be NULL; batch stride grad_batch_stride, which may be a full
+ * plane set even when the planes themselves are shared by all views: per-view gradient planes keep the views' REDs apart) and, when the sc_* buffers are
  * given, the per-sample rows [S,32] [S,64] [S,64] [S,36] from which the decoder weight gradients are formed
  * (dW1 = dpre^T f, dW2 = dout^T hid; S = n*R*(dc+df)). */
 int spi_render_backward(const float* planes, const float* origins, const float* dirs, const float* depths_all, const int* minmax,
                         const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, const float* g_feat,
                         const float* g_depth, float* g_planes, float* sc_f, float* sc_hid, float* sc_dpre, float* sc_dout, int n,
-                        int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream);
+                        int rays_per_image, long long plane_batch_stride, long long grad_batch_stride, int plane_h, int plane_w, int dc, int df,
+                        float box_warp, cudaStream_t stream);
 /* Same pair with the forward pass KEEPING its decoder activations for the backward pass (tcgen05 kernels; 180 GB of HBM make the
  * ~0.5 GB per image cheaper than re-gathering 12 texel lines per sample and re-running layers 1-2): sv_h [S,64] hidden layer,
  * sv_o [S,36] pre-activation outputs incl. bias (32 colours, sigma, 3 pad), sv_f [S,32] gathered features (NULL unless decoder
@@ -102,8 +104,8 @@ int spi_render_forward_keep(const float* planes, const float* origins, const flo
 int spi_render_backward_kept(const float* planes, const float* origins, const float* dirs, const float* depths_all, const int* minmax,
                              const float* w1, const float* b1, const float* w2, const float* b2, float lr_mul, const float* g_feat,
                              const float* g_depth, float* g_planes, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
-                             long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, const float* sv_h,
-                             const float* sv_o, const unsigned char* sv_src, cudaStream_t stream);
+                             long long plane_batch_stride, long long grad_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp,
+                             const float* sv_h, const float* sv_o, const unsigned char* sv_src, cudaStream_t stream);
 /* ImportanceRenderer.run_model (renderer.py:142-149) on arbitrary points: coords [n, m, 3] -> rgb [n, m, 32],
  * sigma [n, m]; used by TriPlaneGenerator.sample / sample_mixed (triplane.py:91-102). */
 int spi_points_forward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,

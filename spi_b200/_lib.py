@@ -22,10 +22,10 @@ _SIGS = {
     'spi_filtered_lrelu': [c_void_p] * 6 + [c_int] * 5 + [c_void_p, c_void_p] + [c_int] * 14 + [c_float] * 3 + [c_int, c_int, c_void_p],
     'spi_filtered_lrelu_act': [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 4 + [c_float] * 3 + [c_int, c_void_p],
     'spi_render_forward': [c_void_p] * 9 + [c_float] + [c_void_p] * 6 + [c_int, c_int, c_ll] + [c_int] * 4 + [c_float] * 3 + [c_int, c_void_p],
-    'spi_render_backward': [c_void_p] * 9 + [c_float] + [c_void_p] * 7 + [c_int, c_int, c_ll] + [c_int] * 4 + [c_float, c_void_p],
+    'spi_render_backward': [c_void_p] * 9 + [c_float] + [c_void_p] * 7 + [c_int, c_int, c_ll, c_ll] + [c_int] * 4 + [c_float, c_void_p],
     'spi_render_keeps_activations': [c_int, c_int],
     'spi_render_forward_keep': [c_void_p] * 9 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_ll] + [c_int] * 4 + [c_float] * 3 + [c_int] + [c_void_p] * 4 + [c_void_p],
-    'spi_render_backward_kept': [c_void_p] * 9 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_ll] + [c_int] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p],
+    'spi_render_backward_kept': [c_void_p] * 9 + [c_float] + [c_void_p] * 5 + [c_int, c_int, c_ll, c_ll] + [c_int] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p],
     'spi_points_forward': [c_void_p] * 6 + [c_float] + [c_void_p] * 2 + [c_int] * 4 + [c_float, c_void_p],
     'spi_points_backward': [c_void_p] * 6 + [c_float] + [c_void_p] * 7 + [c_int] * 4 + [c_float, c_void_p],
     'spi_ray_sampler': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],

@@ -62,7 +62,8 @@ struct RenderParams {
     float* sigma_all;          // optional debug output [N, R, D]
     int* minmax;               // 2 ints: ordered-int min / max of all sample depths (ray_marcher.py:50)
     int n, R, H, W, dc, df;    // R = rays per image
-    long long plane_bs;        // batch stride of planes / g_planes in floats (0: one tri-plane set shared by all n views)
+    long long plane_bs;        // batch stride of planes in floats (0: one tri-plane set shared by all n views)
+    long long gplane_bs;       // batch stride of g_planes (may differ: per-view gradient planes for shared planes avoid RED contention)
     float ray_start, ray_end, box_warp;
     int disparity;
     // backward
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_kernel(RenderParams p) 
     for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
         const int n = (int)(ray / R);
         const float* pl = p.planes + (size_t)n * p.plane_bs;
-        float* gpl = p.g_planes + (size_t)n * p.plane_bs;
+        float* gpl = p.g_planes + (size_t)n * p.gplane_bs;
         Ray r;
         r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
         r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
@@ -1068,7 +1069,7 @@ __global__ void __launch_bounds__(WARPS * 32) render_bwd_mma_kernel(RenderParams
     for (long long ray = (long long)blockIdx.x * WARPS + warp; ray < total; ray += (long long)gridDim.x * WARPS) {
         const int n = (int)(ray / R);
         const float* pl = p.planes + (size_t)n * p.plane_bs;
-        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.plane_bs : nullptr;
+        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.gplane_bs : nullptr;
         Ray r;
         r.ox = p.origins[ray * 3]; r.oy = p.origins[ray * 3 + 1]; r.oz = p.origins[ray * 3 + 2];
         r.dx = p.dirs[ray * 3]; r.dy = p.dirs[ray * 3 + 1]; r.dz = p.dirs[ray * 3 + 2];
@@ -1348,11 +1349,12 @@ static int render_backward_impl(const float* planes, const float* origins, const
                                 const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
                                 float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_f,
                                 float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
-                                long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, const float* sv_h,
-                                const float* sv_o, const unsigned char* sv_src, cudaStream_t stream) {
+                                long long plane_batch_stride, long long grad_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp,
+                                const float* sv_h, const float* sv_o, const unsigned char* sv_src, cudaStream_t stream) {
     RenderParams p;
     memset(&p, 0, sizeof(p));
     p.sv_h = (float*)sv_h; p.sv_o = (float*)sv_o; p.sv_src = (unsigned char*)sv_src;
+    p.gplane_bs = grad_batch_stride;
     p.planes = planes; p.origins = origins; p.dirs = dirs; FILL_DECODER(p);
     p.depths_all = (float*)depths_all; p.minmax = (int*)minmax; p.g_feat = g_feat; p.g_depth = g_depth; p.g_planes = g_planes;
     p.sc_f = sc_f; p.sc_hid = sc_hid; p.sc_dpre = sc_dpre; p.sc_dout = sc_dout;
@@ -1394,21 +1396,24 @@ extern "C" int spi_render_backward(const float* planes, const float* origins, co
                                    const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
                                    float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_f,
                                    float* sc_hid, float* sc_dpre, float* sc_dout, int n, int rays_per_image,
-                                   long long plane_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp, cudaStream_t stream) {
+                                   long long plane_batch_stride, long long grad_batch_stride, int plane_h, int plane_w, int dc, int df, float box_warp,
+                                   cudaStream_t stream) {
     return render_backward_impl(planes, origins, dirs, depths_all, minmax, w1, b1, w2, b2, lr_mul, g_feat, g_depth, g_planes, sc_f, sc_hid, sc_dpre,
-                                sc_dout, n, rays_per_image, plane_batch_stride, plane_h, plane_w, dc, df, box_warp, nullptr, nullptr, nullptr, stream);
+                                sc_dout, n, rays_per_image, plane_batch_stride, grad_batch_stride, plane_h, plane_w, dc, df, box_warp, nullptr, nullptr,
+                                nullptr, stream);
 }
 
 extern "C" int spi_render_backward_kept(const float* planes, const float* origins, const float* dirs, const float* depths_all,
                                         const int* minmax, const float* w1, const float* b1, const float* w2, const float* b2,
                                         float lr_mul, const float* g_feat, const float* g_depth, float* g_planes, float* sc_dpre,
-                                        float* sc_dout, int n, int rays_per_image, long long plane_batch_stride, int plane_h, int plane_w,
-                                        int dc, int df, float box_warp, const float* sv_h, const float* sv_o, const unsigned char* sv_src,
-                                        cudaStream_t stream) {
+                                        float* sc_dout, int n, int rays_per_image, long long plane_batch_stride, long long grad_batch_stride,
+                                        int plane_h, int plane_w, int dc, int df, float box_warp, const float* sv_h, const float* sv_o,
+                                        const unsigned char* sv_src, cudaStream_t stream) {
     SPI_CHECK_ARG(sv_h && sv_o && sv_src, "render_backward_kept: null activation buffer");
     SPI_CHECK_ARG(spi_render_keeps_activations(dc, df), "render_backward_kept: %d+%d samples per ray are outside the tcgen05 kernels' range", dc, df);
     return render_backward_impl(planes, origins, dirs, depths_all, minmax, w1, b1, w2, b2, lr_mul, g_feat, g_depth, g_planes, nullptr, nullptr, sc_dpre,
-                                sc_dout, n, rays_per_image, plane_batch_stride, plane_h, plane_w, dc, df, box_warp, sv_h, sv_o, sv_src, stream);
+                                sc_dout, n, rays_per_image, plane_batch_stride, grad_batch_stride, plane_h, plane_w, dc, df, box_warp, sv_h, sv_o, sv_src,
+                                stream);
 }
 
 extern "C" int spi_points_forward(const float* planes, const float* coords, const float* w1, const float* b1, const float* w2,

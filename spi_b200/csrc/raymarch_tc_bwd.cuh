@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(THREADS, 1) render_bwd_tc_kernel(RenderParams 
         const long long rr = live ? ray : total - 1;
         const int n = (int)(rr / R);
         const float* pl = p.planes + (size_t)n * p.plane_bs;
-        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.plane_bs : nullptr;
+        float* gpl = p.g_planes ? p.g_planes + (size_t)n * p.gplane_bs : nullptr;
         Ray r;
         r.ox = p.origins[rr * 3]; r.oy = p.origins[rr * 3 + 1]; r.oz = p.origins[rr * 3 + 2];
         r.dx = p.dirs[rr * 3]; r.dy = p.dirs[rr * 3 + 1]; r.dz = p.dirs[rr * 3 + 2];

@@ -13,6 +13,8 @@ from ... import _lib
 from .ray_marcher import MipRayMarcher2
 
 SCRATCH_COLS = (32, 64, 64, 36)
+PER_VIEW_GRADIENT_PLANES = False   # shared planes, n views: one gradient plane set per view, summed after the kernel (measured: no gain,
+                                   # the views' REDs do not contend noticeably; kept as a switch)
 KEEP_ACTIVATIONS = True       # forward keeps hidden layer / outputs / features for backward when decoder gradients are wanted (tcgen05 kernels)
 KERNEL_TIMER = None      # bench.py installs an object with .start(tag) / .stop(tag) that records CUDA events on the launch stream
 
@@ -131,7 +133,13 @@ class _RenderFn(torch.autograd.Function):
         need_dec = any(ctx.needs_input_grad[1:5])
         g_feat = g_feat.contiguous()
         g_depth = g_depth.contiguous() if g_depth is not None else None
-        g_planes = torch.zeros_like(planes) if need_planes else None       # channels-last arena, accumulated with RED
+        # channels-last gradient arena, accumulated with RED (optionally one plane set per view, see PER_VIEW_GRADIENT_PLANES)
+        per_view = need_planes and plane_bs == 0 and n > 1 and PER_VIEW_GRADIENT_PLANES
+        gplane_bs = h * w * 96 if per_view else plane_bs
+        g_planes = None
+        if need_planes:
+            g_planes = (torch.empty(n, *planes.shape[1:], device=planes.device, memory_format=torch.channels_last).zero_() if per_view
+                        else torch.zeros_like(planes))
         gw = None
         if KERNEL_TIMER is not None:
             KERNEL_TIMER.start('render_bwd', n)
@@ -143,7 +151,7 @@ class _RenderFn(torch.autograd.Function):
             _lib.check(lib.spi_render_backward_kept(
                 _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
                 _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
-                _lib.ptr(g_planes), _lib.ptr(sc_dpre), _lib.ptr(sc_dout), n, r, plane_bs, h, w, dc, df, opts['box_warp'],
+                _lib.ptr(g_planes), _lib.ptr(sc_dpre), _lib.ptr(sc_dout), n, r, plane_bs, gplane_bs, h, w, dc, df, opts['box_warp'],
                 _lib.ptr(kept[0]), _lib.ptr(kept[1]), _lib.ptr(kept[3]), _lib.stream()))
             if KERNEL_TIMER is not None:
                 KERNEL_TIMER.stop('render_bwd')
@@ -161,7 +169,7 @@ class _RenderFn(torch.autograd.Function):
             _lib.check(lib.spi_render_backward(
                 _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
                 _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
-                _lib.ptr(g_planes), _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]), _lib.ptr(sc[3]), n, r, plane_bs, h, w, dc, df,
+                _lib.ptr(g_planes), _lib.ptr(sc[0]), _lib.ptr(sc[1]), _lib.ptr(sc[2]), _lib.ptr(sc[3]), n, r, plane_bs, gplane_bs, h, w, dc, df,
                 opts['box_warp'], _lib.stream()))
             if KERNEL_TIMER is not None:
                 KERNEL_TIMER.stop('render_bwd')
@@ -173,10 +181,12 @@ class _RenderFn(torch.autograd.Function):
             _lib.check(lib.spi_render_backward(
                 _lib.ptr(planes), _lib.ptr(origins), _lib.ptr(dirs), _lib.ptr(depths_all), _lib.ptr(minmax), _lib.ptr(w1),
                 _lib.ptr(b1), _lib.ptr(w2), _lib.ptr(b2), opts['lr_mul'], _lib.ptr(g_feat), _lib.ptr(g_depth),
-                _lib.ptr(g_planes), None, None, None, None, n, r, plane_bs, h, w, dc, df, opts['box_warp'], _lib.stream()))
+                _lib.ptr(g_planes), None, None, None, None, n, r, plane_bs, gplane_bs, h, w, dc, df, opts['box_warp'], _lib.stream()))
             gw = (None, None, None, None)
             if KERNEL_TIMER is not None:
                 KERNEL_TIMER.stop('render_bwd')
+        if per_view:
+            g_planes = g_planes.sum(0, keepdim=True)
         return (g_planes, *gw, None, None, None, None, None)
 
 
