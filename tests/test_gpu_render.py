@@ -111,6 +111,37 @@ def test_render_backward_vs_oracle(gen_sd, n, r, dc, df):
         assert rel_l2(got[k], sd[k].grad) < 1e-3, k
 
 
+def test_render_backward_recompute_mode_matches_kept_mode(gen_sd):
+    """Decoder gradients with the forward pass keeping its activations (default) and with the backward pass recomputing them
+    (KEEP_ACTIVATIONS = False: per-sample rows written in merged order by the backward kernel) agree."""
+    from spi_b200.training.volumetric_rendering import renderer as RM
+    gen = torch.Generator().manual_seed(21)
+    n, r, dc, df = 1, 50, 32, 32
+    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=dc, depth_resolution_importance=df)
+    planes = torch.randn(n, 3, 32, 48, 48, generator=gen)
+    cam = weights.canonical_camera(0.3)
+    o, d = OG.ray_sampler(cam[:, :16].reshape(-1, 4, 4), cam[:, 16:].reshape(-1, 3, 3), 128)
+    sel = torch.arange(r) * 131 + 900
+    o, d = o[:, sel].contiguous().cuda(), d[:, sel].contiguous().cuda()
+    jit, u = torch.rand(n, r, dc, 1, generator=gen).cuda(), torch.rand(n * r, df, generator=gen).cuda()
+    g_rgb, g_depth = torch.randn(n, r, 32, generator=gen).cuda(), torch.randn(n, r, 1, generator=gen).cuda()
+    res = {}
+    for keep in (True, False):
+        RM.KEEP_ACTIVATIONS = keep
+        try:
+            dec = decoder_module(gen_sd).requires_grad_(True)
+            pg = planes.cuda().requires_grad_(True)
+            R = RM.ImportanceRenderer()
+            R.inject_noise(jit, u)
+            rgb, depth, _ = R(pg, dec, o, d, rk)
+            ((rgb * g_rgb).sum() + (depth * g_depth).sum()).backward()
+            res[keep] = [pg.grad] + [p.grad for p in dec.parameters()]
+        finally:
+            RM.KEEP_ACTIVATIONS = True
+    for a, b in zip(res[True], res[False]):
+        assert rel_l2(a, b) < 2e-4
+
+
 def test_run_model_vs_oracle(gen_sd):
     from spi_b200.training.volumetric_rendering.renderer import ImportanceRenderer
     gen = torch.Generator().manual_seed(12)
