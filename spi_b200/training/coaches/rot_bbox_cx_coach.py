@@ -97,7 +97,16 @@ class RotBboxCoach(BaseCoach):
                 # only image_depth is consumed here (:133-139): the super-resolution network is dead code for this branch
                 sample_depth = self.G.synthesis(new_ws, new_camera, noise_mode='const', need_image=not share, **kw)['image_depth']
                 with torch.no_grad():
-                    stable_depth = self.original_G.synthesis(new_ws, new_camera, noise_mode='const', need_image=not share)['image_depth']
+                    if share:
+                        # original_G is frozen and w_pivot is constant during this stage: its camera-independent tri-planes are the
+                        # same in every iteration, so they are synthesised once per image (identical results)
+                        key = (w_pivot.data_ptr(), w_pivot._version, id(self.original_G))
+                        hit = getattr(self, '_stable_key', None) == key and self.original_G._last_planes is not None
+                        stable_depth = self.original_G.synthesis(new_ws, new_camera, noise_mode='const', need_image=False, cache_backbone=not hit,
+                                                                 use_cached_backbone=hit)['image_depth']
+                        self._stable_key = key
+                    else:
+                        stable_depth = self.original_G.synthesis(new_ws, new_camera, noise_mode='const', need_image=True)['image_depth']
                 loss_depth = l2_loss(stable_depth, sample_depth) * hp.pt_depth_lambda
                 if share:
                     loss = loss + loss_depth
