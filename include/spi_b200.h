@@ -201,6 +201,11 @@ int spi_lpips_tap_backward(const float* x, const float* yn, const float* lin, in
  * gradients db1 = sum dpre, db2 = sum dout over the per-sample rows of spi_render_backward (triplane.py:123-135). */
 int spi_column_sums(const float* x, long long rows, int cols, float* out, cudaStream_t stream);
 
+/* 2x2 / stride-2 max pooling of channels-last fp32 activations [n, h, w, c] (VGG feature extractors of the losses,
+ * spi/criteria/lpips/networks.py:75-80, bbox_cx_loss.py:79-87).  backward = 0: out [n, h/2, w/2, c] = max over the window;
+ * backward = 1: out [n, h, w, c] = dy routed to the first maximum of every window (torch's arg-max rule), zeros elsewhere. */
+int spi_maxpool2x2(const float* x, const float* dy, float* out, int n, int h, int w, int c, int backward, cudaStream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,7 +8,7 @@ import torch.nn.functional as F
 from torchvision.ops import roi_align
 
 from ..ops import conv as conv_engine
-from ..ops.resize import downsample2x
+from ..ops.resize import downsample2x, maxpool2x2
 from ..torch_utils.ops import bias_act
 
 
@@ -67,7 +67,7 @@ class VGG19(torch.nn.Module):
                 X = bias_act.bias_act(conv_engine.conv2d(X, m.weight, padding=1), m.bias, act=('relu' if relu else 'linear'), gain=1)
                 k += 2 if relu else 1
             else:
-                X = m(X)
+                X = maxpool2x2(X) if isinstance(m, torch.nn.MaxPool2d) else m(X)
                 k += 1
         return X
 

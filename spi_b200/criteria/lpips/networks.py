@@ -7,6 +7,7 @@ import torch
 import torch.nn as nn
 
 from ...ops import conv as conv_engine
+from ...ops.resize import maxpool2x2
 from ...torch_utils.ops import bias_act
 from .utils import normalize_activation
 
@@ -72,7 +73,7 @@ class BaseNet(nn.Module):
             elif isinstance(layer, nn.ReLU) and fused_relu:
                 fused_relu = False
             else:
-                x = layer(x)
+                x = maxpool2x2(x) if isinstance(layer, nn.MaxPool2d) else layer(x)
             if i in self.target_layers:
                 output.append(normalize_activation(x) if normalize else x)
             if len(output) == len(self.target_layers):

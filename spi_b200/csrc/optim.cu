@@ -156,3 +156,57 @@ extern "C" int spi_column_sums(const float* x, long long rows, int cols, float* 
     SPI_LAUNCH_CHECK("column_sums");
     return SPI_OK;
 }
+
+// 2x2 / stride-2 max pooling for channels-last fp32 activations (the VGG16 / VGG19 feature extractors of the losses,
+// spi/criteria/lpips/networks.py:75-80, bbox_cx_loss.py:79-87).  Forward: one read of x, one write of y (ATen's NHWC kernel also
+// writes an int64 index per output).  Backward recomputes the arg-max from x (first maximum in row-major window order, like
+// torch) and writes every dx element exactly once: read x + dy/4, write dx.
+namespace {
+
+__global__ void __launch_bounds__(256) maxpool2_cl_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ out, int n,
+                                                          int h, int w, int c4, int backward) {
+    const int oh = h >> 1, ow = w >> 1;
+    const long long total = (long long)n * oh * ow * c4;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(idx % c4); long long r = idx / c4;
+        const int ox = (int)(r % ow); r /= ow;
+        const int oy = (int)(r % oh); const int nn = (int)(r / oh);
+        const float4* xp = reinterpret_cast<const float4*>(x) + (((long long)nn * h + 2 * oy) * w + 2 * ox) * c4 + cv;
+        const float4 a = __ldg(xp), b = __ldg(xp + c4), c = __ldg(xp + (long long)w * c4), d = __ldg(xp + (long long)w * c4 + c4);
+        if (!backward) {
+            float4 m;
+            m.x = fmaxf(fmaxf(a.x, b.x), fmaxf(c.x, d.x)); m.y = fmaxf(fmaxf(a.y, b.y), fmaxf(c.y, d.y));
+            m.z = fmaxf(fmaxf(a.z, b.z), fmaxf(c.z, d.z)); m.w = fmaxf(fmaxf(a.w, b.w), fmaxf(c.w, d.w));
+            reinterpret_cast<float4*>(out)[idx] = m;
+        } else {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + idx);
+            float4 ga = make_float4(0.f, 0.f, 0.f, 0.f), gb = ga, gc = ga, gd = ga;
+#define ROUTE(f)                                                                                   \
+            {                                                                                      \
+                int k = 0; float m = a.f;                                                          \
+                if (b.f > m) { m = b.f; k = 1; }                                                   \
+                if (c.f > m) { m = c.f; k = 2; }                                                   \
+                if (d.f > m) { k = 3; }                                                            \
+                if (k == 0) ga.f = g.f; else if (k == 1) gb.f = g.f; else if (k == 2) gc.f = g.f; else gd.f = g.f; \
+            }
+            ROUTE(x) ROUTE(y) ROUTE(z) ROUTE(w)
+#undef ROUTE
+            float4* op = reinterpret_cast<float4*>(out) + (((long long)nn * h + 2 * oy) * w + 2 * ox) * c4 + cv;
+            op[0] = ga; op[c4] = gb; op[(long long)w * c4] = gc; op[(long long)w * c4 + c4] = gd;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int spi_maxpool2x2(const float* x, const float* dy, float* out, int n, int h, int w, int c, int backward, cudaStream_t stream) {
+    SPI_CHECK_ARG(x && out && (!backward || dy), "maxpool2x2: null pointer");
+    SPI_CHECK_ARG(n >= 1 && h >= 2 && w >= 2 && h % 2 == 0 && w % 2 == 0 && c >= 4 && c % 4 == 0, "maxpool2x2: even H, W and C %% 4 == 0 required");
+    SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)out | (uintptr_t)dy) & 15) == 0, "maxpool2x2: tensors must be 16-byte aligned");
+    const long long total = (long long)n * (h / 2) * (w / 2) * (c / 4);
+    long long blocks = (total + 255) / 256, cap = (long long)spi_num_sms() * 16;
+    maxpool2_cl_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, stream>>>(x, dy, out, n, h, w, c / 4, backward);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("maxpool2x2");
+    return SPI_OK;
+}

@@ -23,3 +23,18 @@ def test_column_sums_rejects_bad_shapes(lib):
     x = torch.zeros(8, 6, device='cuda')
     with pytest.raises(RuntimeError):
         _lib.check(lib.spi_column_sums(_lib.ptr(x), 8, 6, _lib.ptr(torch.empty(6, device='cuda')), _lib.stream()))
+
+
+@pytest.mark.parametrize('shape', [(1, 64, 32, 32), (2, 128, 16, 24), (1, 512, 4, 4)])
+def test_maxpool2x2_matches_torch_including_ties(lib, shape):
+    from spi_b200.ops.resize import maxpool2x2
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.relu(torch.randn(*shape, generator=gen))            # post-ReLU activations: windows of all zeros tie
+    dy = torch.randn(shape[0], shape[1], shape[2] // 2, shape[3] // 2, generator=gen)
+    xo = x.clone().requires_grad_(True)
+    yo = torch.nn.functional.max_pool2d(xo, 2, 2)
+    yo.backward(dy)
+    xg = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    yg = maxpool2x2(xg)
+    yg.backward(dy.cuda())
+    assert torch.equal(yg.cpu(), yo) and torch.equal(xg.grad.cpu(), xo.grad)
