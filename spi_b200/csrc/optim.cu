@@ -210,3 +210,63 @@ extern "C" int spi_maxpool2x2(const float* x, const float* dy, float* out, int n
     SPI_LAUNCH_CHECK("maxpool2x2");
     return SPI_OK;
 }
+
+// Multi-tensor Adam over a device pointer table: rows of 5 x int64 = {param, grad, exp_avg, exp_avg_sq, numel}.  Parameters and
+// moments live in the flat arenas of FlatAdam; the gradients are whatever tensors autograd produced (no accumulation into a
+// pre-seated gradient arena: that cost one ATen add launch per parameter per iteration).  blockIdx.y = tensor, blockIdx.x strides
+// over its elements.  Same arithmetic and same device-side early exit as adam_kernel.
+namespace {
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __restrict__ table, float lr, float b1, float b2, float eps, float bc1,
+                                                         float bc2, const float* __restrict__ hyper, const float* __restrict__ cond, float cond_thr) {
+    if (cond && cond[0] <= cond_thr) return;
+    if (hyper) { lr = hyper[0]; bc1 = hyper[1]; bc2 = hyper[2]; }
+    const long long* row = table + 5 * (long long)blockIdx.y;
+    float* p = reinterpret_cast<float*>(row[0]);
+    const float* g = reinterpret_cast<const float*>(row[1]);
+    float* m = reinterpret_cast<float*>(row[2]);
+    float* v = reinterpret_cast<float*>(row[3]);
+    const long long n = row[4];
+    const float step_size = lr / bc1;
+    const float rsbc2 = 1.f / sqrtf(bc2);
+    const bool vec = ((row[0] | row[1] | row[2] | row[3]) & 15) == 0;
+    const long long nv = vec ? n / 4 : 0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 pp = ((float4*)p)[i], gg = ldg_stream((const float4*)g + i), mm = ((float4*)m)[i], vv = ((float4*)v)[i];
+        float* P = (float*)&pp; float* G = (float*)&gg; float* M = (float*)&mm; float* V = (float*)&vv;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            M[k] = M[k] + (G[k] - M[k]) * (1.f - b1);
+            V[k] = V[k] * b2 + G[k] * G[k] * (1.f - b2);
+            float denom = sqrtf(V[k]) * rsbc2 + eps;
+            P[k] = P[k] - step_size * (M[k] / denom);
+        }
+        ((float4*)p)[i] = pp; ((float4*)m)[i] = mm; ((float4*)v)[i] = vv;
+    }
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gk = g[i];
+        float mk = m[i] + (gk - m[i]) * (1.f - b1);
+        float vk = v[i] * b2 + gk * gk * (1.f - b2);
+        m[i] = mk; v[i] = vk;
+        p[i] = p[i] - step_size * (mk / (sqrtf(vk) * rsbc2 + eps));
+    }
+}
+
+}  // namespace
+
+extern "C" int spi_adam_step_multi(const void* table, int count, float lr, float beta1, float beta2, float eps, int step, const float* hyper,
+                                   const float* skip_if_le, float skip_threshold, cudaStream_t stream) {
+    SPI_CHECK_ARG(table && count >= 0 && count <= 65535, "adam_step_multi: bad table");
+    SPI_CHECK_ARG(step >= 1 || hyper, "adam_step_multi: step must be >= 1");
+    if (count == 0) return SPI_OK;
+    float bc1 = 1.f, bc2 = 1.f;
+    if (!hyper) {
+        bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+        bc2 = (float)(1.0 - pow((double)beta2, (double)step));
+    }
+    adam_multi_kernel<<<dim3(16, count), 256, 0, stream>>>((const long long*)table, lr, beta1, beta2, eps, bc1, bc2, hyper, skip_if_le, skip_threshold);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("adam_step_multi");
+    return SPI_OK;
+}

@@ -13,7 +13,8 @@ from . import _lib
 
 
 class FlatAdam:
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, steal_grads=False):
+        self.steal = bool(steal_grads)     # leave .grad to autograd (no gradient arena, no per-parameter accumulation launch)
         self.params = [p for p in params]
         assert self.params, 'FlatAdam: empty parameter list'
         dev = self.params[0].device
@@ -22,7 +23,14 @@ class FlatAdam:
         sizes = [(p.numel() + 3) // 4 * 4 for p in self.params]       # keep every view 16-byte aligned
         total = sum(sizes)
         self.arena = torch.zeros(total, device=dev)
-        self.grads = torch.zeros(total, device=dev)
+        self.grads = torch.zeros(0 if self.steal else total, device=dev)
+        self._offsets, off_ = [], 0
+        for sz_ in sizes:
+            self._offsets.append(off_)
+            off_ += sz_
+        self._tables = []            # (pinned host table, device table) pairs; one per captured graph + one reused in eager mode
+        self._eager_table = None
+        self._keep = []
         self.exp_avg = torch.zeros(total, device=dev)
         self.exp_avg_sq = torch.zeros(total, device=dev)
         off = 0
@@ -31,14 +39,28 @@ class FlatAdam:
                 view = self.arena[off:off + p.numel()].view(p.shape)
                 view.copy_(p.data)
                 p.data = view
-                p.grad = self.grads[off:off + p.numel()].view(p.shape)
+                p.grad = None if self.steal else self.grads[off:off + p.numel()].view(p.shape)
                 off += sz
         self.param_groups = [dict(params=self.params, lr=lr, betas=betas, eps=eps)]
         self.steps = 0
         self.hyper = None            # device {lr, bc1, bc2}: enable with use_device_hyper() for CUDA-graph replay
         self.skip_if_le = None       # (device scalar tensor, threshold): device-side early exit
 
+    def flat_grads(self):
+        """Gradients of all parameters as one flat tensor in arena order (zeros where a parameter received none)."""
+        if not self.steal:
+            return self.grads.clone()
+        out = torch.zeros_like(self.arena)
+        for p, off in zip(self.params, self._offsets):
+            if p.grad is not None:
+                out[off:off + p.numel()] = p.grad.reshape(-1)
+        return out
+
     def zero_grad(self, set_to_none=False):
+        if self.steal:
+            for p in self.params:
+                p.grad = None
+            return
         self.grads.zero_()
         for p in self.params:           # autograd may have replaced .grad (e.g. after set_to_none elsewhere): re-seat
             if p.grad is None or p.grad.data_ptr() < self.grads.data_ptr() or p.grad.data_ptr() >= self.grads.data_ptr() + self.grads.numel() * 4:
@@ -46,6 +68,8 @@ class FlatAdam:
                 break
 
     def _reseat(self):
+        if self.steal:
+            return
         off = 0
         for p in self.params:
             sz = (p.numel() + 3) // 4 * 4
@@ -79,8 +103,44 @@ class FlatAdam:
                 self.advance()
         g = self.param_groups[0]
         cond, thr = self.skip_if_le if self.skip_if_le is not None else (None, 0.0)
+        if self.steal:
+            return self._step_multi(g, cond, thr)
         with _lib.timed('adam', self.arena.numel() * 28):
             _lib.check(_lib.load().spi_adam_step(_lib.ptr(self.arena), _lib.ptr(self.grads), _lib.ptr(self.exp_avg), _lib.ptr(self.exp_avg_sq),
                                                  self.arena.numel(), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
                                                  max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None, 0,
                                                  _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))
+
+    def _step_multi(self, g, cond, thr):
+        """One launch over a pointer table {param, grad, m, v, numel} of the parameters that received a gradient."""
+        rows, self._keep = [], []
+        for p, off in zip(self.params, self._offsets):
+            gr = p.grad
+            if gr is None:
+                continue
+            if gr.dtype != torch.float32 or not gr.is_contiguous() or gr.data_ptr() % 4:
+                gr = gr.contiguous().float()
+                self._keep.append(gr)
+            base = off * 4
+            rows.append([self.arena.data_ptr() + base, gr.data_ptr(), self.exp_avg.data_ptr() + base, self.exp_avg_sq.data_ptr() + base, p.numel()])
+        if not rows:
+            return
+        capturing = torch.cuda.is_current_stream_capturing()
+        if capturing or self._eager_table is None:
+            # a captured graph re-uploads ITS table on every replay: it must own the pinned buffer (eager steps in between
+            # would otherwise overwrite the pointers the graph was captured with)
+            pair = (torch.empty(len(self.params), 5, dtype=torch.int64).pin_memory(), torch.empty(len(self.params), 5, dtype=torch.int64, device=self.arena.device))
+            if capturing:
+                self._tables.append(pair)
+            else:
+                self._eager_table = pair
+        else:
+            pair = self._eager_table
+        host, dev = pair
+        host[:len(rows)] = torch.tensor(rows, dtype=torch.int64)
+        dev.copy_(host, non_blocking=True)
+        nbytes = sum(r[4] for r in rows) * 28
+        with _lib.timed('adam', nbytes):
+            _lib.check(_lib.load().spi_adam_step_multi(_lib.ptr(dev), len(rows), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+                                                       max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None,
+                                                       _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))

@@ -93,7 +93,7 @@ class BaseCoach:
 
     def configure_optimizers(self):
         """base_coach.py:132-135: Adam over every G parameter, lr = pti_learning_rate."""
-        return FlatAdam(self.G.parameters(), lr=hyperparameters.pti_learning_rate)
+        return FlatAdam(self.G.parameters(), lr=hyperparameters.pti_learning_rate, steal_grads=True)
 
     def save(self, w, c, G, path):
         torch.save({'w': w.detach().cpu(), 'c': c.detach().cpu(), 'G': {k: v.detach().cpu() for k, v in G.state_dict().items()}}, path)

@@ -60,7 +60,7 @@ class LatentProjector:
         for buf in self.noise_bufs.values():
             buf[:] = rng.randn_like(buf)
             buf.requires_grad = True
-        self.optimizer = FlatAdam([self.w_opt] + list(self.noise_bufs.values()), betas=(0.9, 0.999), lr=initial_learning_rate)
+        self.optimizer = FlatAdam([self.w_opt] + list(self.noise_bufs.values()), betas=(0.9, 0.999), lr=initial_learning_rate, steal_grads=True)
         self.optimizer.use_device_hyper()
         self.w_noise_scale = torch.zeros((), device=device)          # per-step scalar, read on device (graph replay)
         self._scale_host = torch.zeros(()).pin_memory()

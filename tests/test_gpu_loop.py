@@ -273,7 +273,7 @@ def test_shared_backbone_equals_per_view_evaluation(gen_sd, lpips_mod, cx_mod):
             lp, stepped = coach.train_step(0, st, w)
             assert stepped and rng.pending() == 0
             lps.append(float(lp))
-            grads.append((coach.optimizer.grads.clone(), w.grad.clone()))
+            grads.append((coach.optimizer.flat_grads(), w.grad.clone()))
         finally:
             global_config.share_backbone = True
     assert abs(lps[0] / lps[1] - 1) < 1e-4
