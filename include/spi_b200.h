@@ -155,9 +155,10 @@ int spi_adam_step(float* param, const float* grad, float* exp_avg, float* exp_av
                   float beta2, float eps, int step, const float* hyper, int zero_grad, const float* skip_if_le,
                   float skip_threshold, cudaStream_t stream);
 /* Same update over a device table of `count` rows {param, grad, exp_avg, exp_avg_sq, numel} (5 x int64, device pointers): the
- * gradients are read where autograd left them instead of being accumulated into a gradient arena first. */
-int spi_adam_step_multi(const void* table, int count, float lr, float beta1, float beta2, float eps, int step, const float* hyper,
-                        const float* skip_if_le, float skip_threshold, cudaStream_t stream);
+ * gradients are read where autograd left them instead of being accumulated into a gradient arena first.  A row may be a chunk of
+ * a tensor (the caller splits large tensors so that the rows are balanced); blocks_per_row CTAs of 256 threads serve each row. */
+int spi_adam_step_multi(const void* table, int count, int blocks_per_row, float lr, float beta1, float beta2, float eps, int step,
+                        const float* hyper, const float* skip_if_le, float skip_threshold, cudaStream_t stream);
 /* F.interpolate(..., (H/2, W/2), mode='bilinear'|'area') at exactly half size (lpips.py:38-39, bbox_cx_loss.py:161-163,
  * w_projector.py:50,83); contiguous [planes, 2*out_h, 2*out_w] -> [planes, out_h, out_w]; backward != 0 runs the adjoint. */
 int spi_downsample2x(const float* x, float* y, long long planes, int out_h, int out_w, int backward, cudaStream_t stream);

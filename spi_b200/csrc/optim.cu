@@ -255,9 +255,9 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const long long* __rest
 
 }  // namespace
 
-extern "C" int spi_adam_step_multi(const void* table, int count, float lr, float beta1, float beta2, float eps, int step, const float* hyper,
-                                   const float* skip_if_le, float skip_threshold, cudaStream_t stream) {
-    SPI_CHECK_ARG(table && count >= 0 && count <= 65535, "adam_step_multi: bad table");
+extern "C" int spi_adam_step_multi(const void* table, int count, int blocks_per_row, float lr, float beta1, float beta2, float eps, int step,
+                                   const float* hyper, const float* skip_if_le, float skip_threshold, cudaStream_t stream) {
+    SPI_CHECK_ARG(table && count >= 0 && count <= 65535 && blocks_per_row >= 1 && blocks_per_row <= 1024, "adam_step_multi: bad table");
     SPI_CHECK_ARG(step >= 1 || hyper, "adam_step_multi: step must be >= 1");
     if (count == 0) return SPI_OK;
     float bc1 = 1.f, bc2 = 1.f;
@@ -265,7 +265,7 @@ extern "C" int spi_adam_step_multi(const void* table, int count, float lr, float
         bc1 = (float)(1.0 - pow((double)beta1, (double)step));
         bc2 = (float)(1.0 - pow((double)beta2, (double)step));
     }
-    adam_multi_kernel<<<dim3(16, count), 256, 0, stream>>>((const long long*)table, lr, beta1, beta2, eps, bc1, bc2, hyper, skip_if_le, skip_threshold);
+    adam_multi_kernel<<<dim3(blocks_per_row, count), 256, 0, stream>>>((const long long*)table, lr, beta1, beta2, eps, bc1, bc2, hyper, skip_if_le, skip_threshold);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("adam_step_multi");
     return SPI_OK;

@@ -13,6 +13,7 @@ from . import _lib
 
 
 class FlatAdam:
+    CHUNK = 32768          # elements per table row of the multi-tensor step (one CTA each)
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, steal_grads=False):
         self.steal = bool(steal_grads)     # leave .grad to autograd (no gradient arena, no per-parameter accumulation launch)
         self.params = [p for p in params]
@@ -28,6 +29,7 @@ class FlatAdam:
         for sz_ in sizes:
             self._offsets.append(off_)
             off_ += sz_
+        self._max_rows = sum((p.numel() + self.CHUNK - 1) // self.CHUNK for p in self.params)
         self._tables = []            # (pinned host table, device table) pairs; one per captured graph + one reused in eager mode
         self._eager_table = None
         self._keep = []
@@ -121,15 +123,18 @@ class FlatAdam:
             if gr.dtype != torch.float32 or not gr.is_contiguous() or gr.data_ptr() % 4:
                 gr = gr.contiguous().float()
                 self._keep.append(gr)
-            base = off * 4
-            rows.append([self.arena.data_ptr() + base, gr.data_ptr(), self.exp_avg.data_ptr() + base, self.exp_avg_sq.data_ptr() + base, p.numel()])
+            # rows are chunks of at most CHUNK elements so that every CTA has the same amount of work
+            for c0 in range(0, p.numel(), self.CHUNK):
+                base = (off + c0) * 4
+                rows.append([self.arena.data_ptr() + base, gr.data_ptr() + c0 * 4, self.exp_avg.data_ptr() + base, self.exp_avg_sq.data_ptr() + base,
+                             min(self.CHUNK, p.numel() - c0)])
         if not rows:
             return
         capturing = torch.cuda.is_current_stream_capturing()
         if capturing or self._eager_table is None:
             # a captured graph re-uploads ITS table on every replay: it must own the pinned buffer (eager steps in between
             # would otherwise overwrite the pointers the graph was captured with)
-            pair = (torch.empty(len(self.params), 5, dtype=torch.int64).pin_memory(), torch.empty(len(self.params), 5, dtype=torch.int64, device=self.arena.device))
+            pair = (torch.empty(self._max_rows, 5, dtype=torch.int64).pin_memory(), torch.empty(self._max_rows, 5, dtype=torch.int64, device=self.arena.device))
             if capturing:
                 self._tables.append(pair)
             else:
@@ -141,6 +146,6 @@ class FlatAdam:
         dev.copy_(host, non_blocking=True)
         nbytes = sum(r[4] for r in rows) * 28
         with _lib.timed('adam', nbytes):
-            _lib.check(_lib.load().spi_adam_step_multi(_lib.ptr(dev), len(rows), float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
+            _lib.check(_lib.load().spi_adam_step_multi(_lib.ptr(dev), len(rows), 1, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
                                                        max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None,
                                                        _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))
