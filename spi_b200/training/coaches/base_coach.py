@@ -13,6 +13,8 @@ from ...optim import FlatAdam
 from ...utils import load_utils
 from ...utils.camera_utils import cal_mirror_c
 from ...utils.log_utils import log_image_from_w
+from ...utils.metric_utils import Metric, format_metric_log, gather_metric_dic
+from ...utils.video_utils import gen_interp_video
 from ..projectors import mirror_projector, w_plus_projector, w_projector
 
 
@@ -30,7 +32,7 @@ def fix_seed():
 
 
 class BaseCoach:
-    def __init__(self, data_loader, use_wandb, lpips_loss=None, vgg16=None):
+    def __init__(self, data_loader, use_wandb, lpips_loss=None, vgg16=None, metric=None):
         self.use_wandb = use_wandb
         self.data_loader = data_loader
         self.w_pivots = {}
@@ -40,6 +42,14 @@ class BaseCoach:
         self.lpips_loss = lpips_loss if lpips_loss is not None else LPIPS(net_type='vgg').to(global_config.device).eval()
         self.restart_training()
         self.vgg16 = vgg16 if vgg16 is not None else load_utils.load_sg_vgg().to(global_config.device)
+        self._metric = metric
+
+    @property
+    def metric(self):
+        """base_coach.py:43 builds `Metric()` (IR-SE50 + LPIPS) eagerly; here on first use: only `use_wandb` runs need it."""
+        if self._metric is None:
+            self._metric = Metric(lpips_loss=self.lpips_loss)
+        return self._metric
 
     def restart_training(self):
         """base_coach.py:53-60: fresh G and original_G per image, new optimiser, then fix_seed()."""
@@ -59,9 +69,11 @@ class BaseCoach:
             w_pivot = self.calc_inversions(image_name, image, camera, fg_mask)
         torch.save(w_pivot, f'{embedding_dir}/{image_name}.pt')
         w_pivot = w_pivot.to(global_config.device)
-        if self.use_wandb:
-            log_image_from_w(w_pivot, camera, self.G, f'{image_name}_w_inv')
-            log_image_from_w(w_pivot, cal_mirror_c(camera), self.G, f'{image_name}_w_inv_m')
+        if self.use_wandb:                       # base_coach.py:77-83
+            w_inv = log_image_from_w(w_pivot, camera, self.G, f'{image_name}_w_inv')
+            w_inv_m = log_image_from_w(w_pivot, cal_mirror_c(camera), self.G, f'{image_name}_w_inv_m')
+            self.log_video(w_pivot, self.G, os.path.join(paths_config.experiments_output_dir, f'{image_name}_w_inv.mp4'))
+            self.cal_metric(w_inv, image, 'w_inv', fake_m=w_inv_m)
         return w_pivot
 
     def load_inversions(self, embedding_dir, image_name):
@@ -95,6 +107,39 @@ class BaseCoach:
         """base_coach.py:132-135: Adam over every G parameter, lr = pti_learning_rate."""
         return FlatAdam(self.G.parameters(), lr=hyperparameters.pti_learning_rate, steal_grads=True)
 
+    def cal_metric(self, fake, gt, name, fake_m=None):
+        """base_coach.py:141-154: L2 / LPIPS / ID of a render against the photo, and of the mirrored render against the
+        flipped photo."""
+        d = self.metric_dic.setdefault(name, {'l2': [], 'lpips': [], 'id': [], 'l2_m': [], 'lpips_m': [], 'id_m': []})
+        l2, lpips, id_sim = self.metric.run(gt, fake)
+        d['l2'].append(l2)
+        d['lpips'].append(lpips)
+        d['id'].append(id_sim)
+        if fake_m is not None:
+            l2, lpips, id_sim = self.metric.run(torch.flip(gt, dims=[3]), fake_m)
+            d['l2_m'].append(l2)
+            d['lpips_m'].append(lpips)
+            d['id_m'].append(id_sim)
+
+    def log_metric(self):
+        """base_coach.py:156-198: append the per-image table and the averages to experiments/<coach>/metric_log.txt.  Under
+        torchrun every rank holds the rows of its own dataset block: they are gathered in rank (= block = dataset) order and
+        rank 0 writes the one file a single-process run would have written."""
+        merged, writer = gather_metric_dic(self.metric_dic)
+        if writer:
+            with open(os.path.join(paths_config.experiments_output_dir, 'metric_log.txt'), 'a') as log_file:
+                log_file.write(format_metric_log(self.coach_name, hyperparameters, merged))
+        return merged
+
+    def finish_image(self, w_pivot, image, camera, image_name):
+        """Tail of the per-image loop (pti_coach.py:87-94, rot_bbox_cx_coach.py:160-167)."""
+        if self.use_wandb and hyperparameters.G_1_step > 0:
+            G1_inv = log_image_from_w(w_pivot, camera, self.G, f'{image_name}_G1_inv')
+            G1_inv_m = log_image_from_w(w_pivot, cal_mirror_c(camera), self.G, f'{image_name}_G1_inv_m')
+            self.log_video(w_pivot, self.G, path=os.path.join(paths_config.experiments_output_dir, f'{image_name}_G1_inv.mp4'))
+            self.cal_metric(G1_inv, image, 'G1_inv', fake_m=G1_inv_m)
+        self.post_process(w_pivot, camera, self.G, image_name)
+
     def save(self, w, c, G, path):
         torch.save({'w': w.detach().cpu(), 'c': c.detach().cpu(), 'G': {k: v.detach().cpu() for k, v in G.state_dict().items()}}, path)
 
@@ -118,9 +163,10 @@ class BaseCoach:
         Image.fromarray(img).save(path)
 
     def log_video(self, w, G, path):
-        """The 120-frame orbit video (spi/utils/video_utils.py:74) needs imageio/mrcfile and is post-processing outside the
-        hot path: not built."""
-        return None
+        """base_coach.py:236-237: the 120-frame orbit; one backbone pass for the clip (utils/video_utils.py)."""
+        if len(w.size()) <= 2:
+            w = w.unsqueeze(0)
+        return gen_interp_video(G, {'w': w.detach().clone()}, mp4=path)
 
     def build_name(self):
         """base_coach.py:240-270."""

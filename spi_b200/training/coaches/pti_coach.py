@@ -86,5 +86,7 @@ class SingleIDCoach(BaseCoach):
                     break
                 global_config.training_step += 1
             self.image_counter += 1
-            self.post_process(w_pivot, camera, self.G, image_name)
+            self.finish_image(w_pivot, image, camera, image_name)
         paths_config.experiments_output_dir = output_dir
+        if self.use_wandb:
+            self.log_metric()

@@ -1,0 +1,115 @@
+"""CPU tests of the post-processing rows next to the hot path: orbit-video camera trajectory and
+frame layout against the reference's own outputs (`oracle/make_golden_post.py` -> tests/golden/post.npz), the
+`metric_log.txt` text byte for byte, the two-rank gather of per-image metrics (gloo), and the Motion-JPEG writer."""
+import json
+import os
+import tempfile
+import types
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+
+def test_orbit_cameras_match_reference_frame_by_frame():
+    from spi_b200.utils.video_utils import orbit_cameras
+    gold = np.load(os.path.join(GOLD, 'post.npz'))['orbit_poses']
+    cams, poses = orbit_cameras(120, device='cpu')
+    assert cams.shape == (120, 25) and poses.shape == (120, 4, 4)
+    np.testing.assert_allclose(poses.numpy(), gold, rtol=0, atol=2e-7)          # batched vs one-by-one evaluation
+    np.testing.assert_array_equal(cams[:, :16].numpy(), poses.reshape(120, 16).numpy())
+    np.testing.assert_allclose(cams[:, 16:].numpy(), np.tile(np.float32([4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1]), (120, 1)))
+    # every camera sits on the radius-2.7 sphere around the look-at point's origin
+    np.testing.assert_allclose(np.linalg.norm(poses[:, :3, 3].numpy(), axis=1), 2.7, rtol=1e-6)
+
+
+def test_layout_grid_matches_reference():
+    from spi_b200.utils.video_utils import layout_grid
+    g = np.load(os.path.join(GOLD, 'post.npz'))
+    out = layout_grid(torch.from_numpy(g['grid_in']), grid_w=3, grid_h=2)
+    assert out.dtype == np.uint8
+    np.testing.assert_array_equal(out, g['grid_out'])
+
+
+def test_metric_log_text_is_the_reference_text():
+    from spi_b200.utils.metric_utils import format_metric_log
+    g = json.load(open(os.path.join(GOLD, 'metric_log.json')))
+    hp = types.SimpleNamespace(**g['hyperparameters'])
+    assert format_metric_log(g['coach_name'], hp, g['metric_dic']) == g['text']
+
+
+def _metric_worker(rank, world, port, out_dir):
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from spi_b200.configs import hyperparameters, paths_config
+    from spi_b200.training.coaches.base_coach import BaseCoach
+    g = json.load(open(os.path.join(GOLD, 'metric_log.json')))
+    for k, v in g['hyperparameters'].items():
+        setattr(hyperparameters, k, v)
+    paths_config.experiments_output_dir = out_dir
+    # rank 0 holds images 0-2 (dataset block 1/2 of 5 images: len // W + 1 = 3), rank 1 images 3-4
+    lo, hi = (0, 3) if rank == 0 else (3, 5)
+    part = {mode: {k: v[lo:hi] for k, v in cur.items()} for mode, cur in g['metric_dic'].items()}
+    fake = types.SimpleNamespace(coach_name=g['coach_name'], metric_dic=part)
+    merged = BaseCoach.log_metric(fake)
+    assert merged == g['metric_dic']
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_metric_log_two_ranks_write_the_single_process_file():
+    g = json.load(open(os.path.join(GOLD, 'metric_log.json')))
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_metric_worker, args=(2, 29541, d), nprocs=2, join=True)
+        assert open(os.path.join(d, 'metric_log.txt')).read() == g['text']       # written once, by rank 0
+
+
+def test_cal_metric_rows_and_mirror_flip():
+    from spi_b200.training.coaches.base_coach import BaseCoach
+    calls = []
+
+    class M:
+        def run(self, gt, fake):
+            calls.append((gt.clone(), fake.clone()))
+            return float(len(calls)), 0.5, 0.25
+    fake_self = types.SimpleNamespace(metric_dic={}, metric=M())
+    gt = torch.arange(8.).view(1, 1, 2, 4)
+    BaseCoach.cal_metric(fake_self, gt + 1, gt, 'w_inv', fake_m=gt + 2)
+    assert fake_self.metric_dic['w_inv'] == {'l2': [1.0], 'lpips': [0.5], 'id': [0.25], 'l2_m': [2.0], 'lpips_m': [0.5], 'id_m': [0.25]}
+    assert torch.equal(calls[1][0], torch.flip(gt, dims=[3]))       # the mirrored render is compared with the flipped photo
+
+
+def test_mjpeg_writer_round_trip():
+    from spi_b200.utils.video_utils import MJPEGWriter
+    cv2 = pytest.importorskip('cv2')
+    rs = np.random.RandomState(0)
+    base = np.kron(rs.randint(0, 255, (8, 8, 3)), np.ones((8, 8, 1))).astype(np.uint8)          # blocky: survives JPEG
+    frames = [np.roll(base, 8 * i, axis=1) for i in range(5)]
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'clip.avi')
+        w = MJPEGWriter(path, fps=60)
+        for f in frames:
+            w.append_data(f)
+        w.close()
+        cap = cv2.VideoCapture(path)
+        assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 5
+        assert abs(cap.get(cv2.CAP_PROP_FPS) - 60) < 1e-3
+        for f in frames:
+            ok, got = cap.read()
+            assert ok and got.shape == f.shape
+            assert np.abs(got[..., ::-1].astype(int) - f.astype(int)).mean() < 6
+        cap.release()
+
+
+def test_interpolated_keyframes_are_periodic_and_hit_the_keys():
+    from spi_b200.utils.video_utils import interpolate_keyframes
+    ws = torch.randn(3, 14, 8, generator=torch.Generator().manual_seed(0))
+    assert interpolate_keyframes(ws[:1], 120) is None                        # one keyframe: broadcast, no copies
+    w = interpolate_keyframes(ws, 4)
+    assert w.shape == (12, 14, 8)
+    for k in range(3):
+        torch.testing.assert_close(w[4 * k], ws[k], rtol=1e-5, atol=1e-5)
