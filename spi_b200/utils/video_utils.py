@@ -125,14 +125,19 @@ def render_orbit(G, ws, w_frames=30 * 4, kind='cubic', wraps=2, cfg='FFHQ', imag
     cams, poses = orbit_cameras(n, cfg=cfg, device=device)
     w_all = interpolate_keyframes(ws, w_frames, kind=kind, wraps=wraps)
     frames = []
+    kept = G._last_planes
     for s in range(0, n, batch):
         c = cams[s:s + batch]
         if w_all is None:
-            w = ws[:1].expand(c.shape[0], -1, -1)         # stride-0 batch: `synthesis` evaluates the backbone once per call
+            # constant latent: a stride-0 batch (shared styles in the SR network) and the reference's own backbone cache
+            # (triplane.py:66-71) -- the tri-planes are synthesised by the first batch and re-used by the others
+            w = ws[:1].expand(c.shape[0], -1, -1)
+            cache = dict(cache_backbone=(s == 0), use_cached_backbone=(s > 0))
         else:
             w = w_all[s:s + batch].to(device)
+            cache = {}
         need_image = (image_mode == 'image')
-        img = G.synthesis(ws=w, c=c, noise_mode='const', need_image=need_image)[image_mode]
+        img = G.synthesis(ws=w, c=c, noise_mode='const', need_image=need_image, **cache)[image_mode]
         if image_mode == 'image_depth':                   # per-frame min/max stretch, video_utils.py:174-176
             img = -img
             lo = img.amin(dim=(1, 2, 3), keepdim=True)
@@ -142,6 +147,7 @@ def render_orbit(G, ws, w_frames=30 * 4, kind='cubic', wraps=2, cfg='FFHQ', imag
         if img.shape[1] == 1:
             img = img.expand(-1, 3, -1, -1)
         frames.append(img.permute(0, 2, 3, 1).contiguous())
+    G._last_planes = kept
     return torch.cat(frames), poses
 
 

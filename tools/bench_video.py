@@ -41,7 +41,7 @@ def main():
     print(f'frame by frame (120 generator passes)        {t_ref:8.1f} ms  {t_ref / 120:6.2f} ms/frame', flush=True)
     for b in (4, 8, 16):
         t = timed(lambda: render_orbit(G, ws, w_frames=120, batch=b))
-        print(f'one backbone pass per batch of {b:2d} views        {t:8.1f} ms  {t / 120:6.2f} ms/frame  ({t_ref / t:4.2f}x)', flush=True)
+        print(f'one backbone pass, batches of {b:2d} views         {t:8.1f} ms  {t / 120:6.2f} ms/frame  ({t_ref / t:4.2f}x)', flush=True)
     t = timed(lambda: render_orbit(G, ws, w_frames=120, batch=8, image_mode='image_depth'))
     print(f'depth clip (SR skipped), batch 8                {t:8.1f} ms  {t / 120:6.2f} ms/frame', flush=True)
 
