@@ -1,0 +1,154 @@
+"""CPU tests of the host logic either side of the hot path, against outputs of the reference's own classes
+(`oracle/make_golden_post.py` -> tests/golden/host_logic.json): `PTIDataset` item formats and slicing rules
+(spi/data/images_dataset.py:102-198), coach naming + output tree (base_coach.py:240-270), the CLI surface
+(spi/run_inversion.py:18-56) and the checkpoint format (base_coach.py:204-217)."""
+import json
+import os
+import tempfile
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import toy_dataset
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'host_logic.json')))
+
+
+def _names(ds):
+    return [os.path.dirname(p).split('/')[-1] for p in ds.source_paths]
+
+
+@pytest.fixture(scope='module')
+def toy_root():
+    with tempfile.TemporaryDirectory() as d:
+        toy_dataset.write(d, n=7)
+        yield d
+
+
+def _kw(d):
+    return dict(source_root=os.path.join(d, 'crop'), c_root=os.path.join(d, 'c'), mask_root=os.path.join(d, 'mask'),
+                lm_root=os.path.join(d, 'lm'), mode='png')
+
+
+def test_dataset_items_equal_the_reference_items(toy_root):
+    from spi_b200.data.images_dataset import PTIDataset
+    ds = PTIDataset(**_kw(toy_root))
+    assert len(ds) == 7
+    for gold, i in zip(GOLD['dataset']['items'], (0, 6)):
+        got = toy_dataset.digest(ds[i])
+        for k in ('img_shape', 'c_dtype', 'mask_sum', 'mask_dtype', 'mask_shape', 'lm_dtype', 'name', 'fname', 'c', 'lm'):
+            assert got[k] == gold[k], k
+        np.testing.assert_array_equal(np.float32(got['img_grid']), np.float32(gold['img_grid']))      # ToTensor + Normalize(0.5, 0.5), bit for bit
+        assert got['img_sum'] == gold['img_sum']
+
+
+def test_dataset_slicing_rules(toy_root):
+    from spi_b200.data.images_dataset import PTIDataset
+    kw = _kw(toy_root)
+    g = GOLD['dataset']
+    for block, names in g['blocks'].items():
+        assert _names(PTIDataset(dataset_block=block, **kw)) == names, block
+    assert _names(PTIDataset(select_range=3, **kw)) == g['select_3']
+    assert _names(PTIDataset(filter_index=['00004', '00001'], **kw)) == g['filter']
+    with tempfile.TemporaryDirectory() as out:
+        for nm in ('00000', '00003'):
+            open(os.path.join(out, nm + '.jpg'), 'w').close()
+        assert _names(PTIDataset(output_root=out, **kw)) == g['resume']                           # finished images are skipped
+        assert _names(PTIDataset(output_root=out, dataset_block='2/2', **kw)) == g['resume_block_2_2']
+
+
+def test_every_image_lands_on_exactly_one_rank(toy_root):
+    """The blocks of `len // W + 1` images cover the list without overlap for any world size (trailing ranks may idle)."""
+    from spi_b200.data.images_dataset import PTIDataset
+    kw = _kw(toy_root)
+    for world in (1, 2, 3, 4, 8):
+        got = sum((_names(PTIDataset(dataset_block=f'{r + 1}/{world}', **kw)) for r in range(world)), [])
+        assert got == [f'{i:05d}' for i in range(7)], world
+
+
+def test_coach_names_and_output_tree():
+    from spi_b200.configs import hyperparameters, paths_config
+    from spi_b200.training.coaches.base_coach import BaseCoach
+    saved_hp = {k: getattr(hyperparameters, k) for k in GOLD['coach_names'][0]['hyperparameters']}
+    keys = ('checkpoints_dir', 'embedding_base_dir', 'experiments_output_dir', 'images_output_dir', 'mirror_images_output_dir', 'video_output_dir')
+    saved_paths = {k: getattr(paths_config, k) for k in keys}
+    try:
+        for case in GOLD['coach_names']:
+            with tempfile.TemporaryDirectory() as d:
+                for k in keys:
+                    setattr(paths_config, k, os.path.join(d, k) + '/')
+                for k, v in case['hyperparameters'].items():
+                    setattr(hyperparameters, k, v)
+                fake = types.SimpleNamespace(coach_name='RotBboxCoach')
+                BaseCoach.build_name(fake)
+                assert fake.coach_name == case['coach_name']
+                dirs = sorted(os.path.relpath(os.path.join(r, x), d) for r, dd, _ in os.walk(d) for x in dd)
+                assert dirs == case['dirs']
+    finally:
+        for k, v in saved_hp.items():
+            setattr(hyperparameters, k, v)
+        for k, v in saved_paths.items():
+            setattr(paths_config, k, v)
+
+
+# flag -> (default, type) of spi/run_inversion.py:18-42
+REFERENCE_FLAGS = {
+    'data_root': 'test/dataset/', 'data_mode': 'png', 'output_root': None, 'use_encoder': False, 'use_G_avg': False,
+    'use_adapt_yaw_range': False, 'not_use_wandb': False, 'first_inv_type': 'pti', 'first_inv_steps': 500, 'G_1_step': 500,
+    'G_1_type': 'space', 'G_2_step': 500, 'load_embedding_coach_name': None, 'pt_rot_lambda': 0, 'pt_mirror_rot_lambda': 0,
+    'pt_depth_lambda': 0, 'pt_tv_lambda': 0, 'description': None, 'dataset_block': None, 'select_range': None, 'filter_index': None}
+
+
+def test_cli_surface_defaults_and_config_globals():
+    from spi_b200 import run_inversion
+    from spi_b200.configs import hyperparameters, paths_config
+    keys = ('root', 'checkpoints_dir', 'embedding_base_dir', 'experiments_output_dir', 'images_output_dir', 'mirror_images_output_dir',
+            'video_output_dir', 'EG3D_PATH')
+    saved_paths = {k: getattr(paths_config, k) for k in keys}
+    saved_hp = dict(vars(hyperparameters))
+    try:
+        args = run_inversion.parse_args([])
+        for flag, default in REFERENCE_FLAGS.items():
+            assert getattr(args, flag) == default, flag
+        with tempfile.TemporaryDirectory() as d:
+            out = d + '/'
+            args = run_inversion.parse_args(['--output_root', out, '--first_inv_type', 'mir', '--first_inv_steps', '7', '--G_1_type', 'RotBbox',
+                                             '--G_1_step', '9', '--pt_rot_lambda', '0.1', '--pt_mirror_rot_lambda', '0.05', '--pt_depth_lambda',
+                                             '1', '--not_use_wandb', '--dataset_block', '2/8', '--filter_index', '3,4'])
+            assert (hyperparameters.first_inv_type, hyperparameters.first_inv_steps, hyperparameters.G_1_type, hyperparameters.G_1_step) == ('mir', 7, 'RotBbox', 9)
+            assert (hyperparameters.pt_rot_lambda, hyperparameters.pt_mirror_rot_lambda, hyperparameters.pt_depth_lambda) == (0.1, 0.05, 1.0)
+            assert sorted(os.listdir(d)) == ['checkpoints', 'embedding', 'experiments', 'image', 'image_m', 'video']     # run_inversion.py:60-79
+            assert paths_config.video_output_dir == out + 'video/' and args.dataset_block == '2/8'
+        # the parser defaults are not runnable, as in the reference (run_inversion.py:119-120): both flags are effectively required
+        with tempfile.TemporaryDirectory() as d, pytest.raises(NotImplementedError):
+            toy_dataset.write(d, n=1)
+            run_inversion.run(['--not_use_wandb', '--data_root', d])
+    finally:
+        for k, v in saved_paths.items():
+            setattr(paths_config, k, v)
+        for k, v in saved_hp.items():
+            if not k.startswith('__'):
+                setattr(hyperparameters, k, v)
+
+
+def test_checkpoint_format_round_trip():
+    """base_coach.py:204-217: {'w', 'c', 'G': state_dict} on the CPU."""
+    from spi_b200.training.coaches.base_coach import BaseCoach
+    G = torch.nn.Linear(3, 2)
+    w, c = torch.randn(1, 14, 512), torch.randn(1, 25)
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, 'x.pt')
+        BaseCoach.save(None, w, c, G, path)
+        ckpt = torch.load(path, map_location='cpu')
+        assert sorted(ckpt) == ['G', 'c', 'w'] and sorted(ckpt['G']) == ['bias', 'weight']
+        assert torch.equal(ckpt['w'], w) and torch.equal(ckpt['c'], c) and torch.equal(ckpt['G']['weight'], G.weight.detach())
+        holder = types.SimpleNamespace(G=torch.nn.Linear(3, 2))
+        from spi_b200.configs import global_config
+        dev, global_config.device = global_config.device, 'cpu'
+        try:
+            w2, c2, G2 = BaseCoach.load(holder, path)
+        finally:
+            global_config.device = dev
+        assert torch.equal(w2, w) and torch.equal(c2, c) and torch.equal(G2.weight, G.weight)
