@@ -152,3 +152,29 @@ def test_checkpoint_format_round_trip():
         finally:
             global_config.device = dev
         assert torch.equal(w2, w) and torch.equal(c2, c) and torch.equal(G2.weight, G.weight)
+
+
+def test_product_camera_helpers_against_reference_goldens(golden):
+    """The product's camera helpers are device-agnostic host logic: on CPU tensors they must reproduce what the reference's
+    spi/utils/camera_utils.py produced for the same uniform draws (tests/golden/geometry_losses.npz)."""
+    from oracle import weights
+    from spi_b200.utils import camera_utils as cu, rng
+    from conftest import rel_l2
+    g = golden('geometry_losses')
+    c = weights.canonical_camera(0.3)
+    r = torch.from_numpy(g['rand42'])
+    rng.inject(r[:, 0:1].clone(), r[:, 1:2].clone())
+    assert rel_l2(cu.sample_surrounding_camera(c, batch_size=4, yaw_range=0.2, pitch_range=0.1), g['surround']) < 1e-6
+    rng.inject(r[:, 0:1].clone(), r[:, 1:2].clone())
+    assert rel_l2(cu.sample_camera(4, yaw_range=0.7, pitch_range=0.4, device='cpu'), g['sampled']) < 1e-6
+    assert rng.pending() == 0
+    assert rel_l2(cu.cal_camera_weight(c), g['cam_weight']) < 1e-6
+    assert rel_l2(cu.cal_canonical_c(0.3, 0, 1, 'cpu'), c) < 1e-6
+    # |yaw| < 0.2: the mirror branch is switched off (camera_utils.py:407-408)
+    assert float(cu.cal_camera_weight(cu.cal_canonical_c(0.1, 0, 1, 'cpu'))) == 0.0
+    # mirror pose: entries [0,1],[0,2],[0,3],[1,0],[2,0] negated, an involution, yaw changes sign
+    m = cu.cal_mirror_c(c)
+    d = (m[:, :16].view(4, 4) != c[:, :16].view(4, 4)).nonzero().tolist()
+    assert set(map(tuple, d)) <= {(0, 1), (0, 2), (0, 3), (1, 0), (2, 0)} and torch.equal(cu.cal_mirror_c(m), c)
+    yaw = lambda cam: float(cu.rotation_to_angle(cam.view(25)[:16].view(4, 4)[:3, :3])[0])
+    assert abs(yaw(m) + yaw(c)) < 1e-6 and abs(abs(yaw(c)) - 0.3) < 5e-2       # the orbit centre is the look-at point [0, 0, 0.2], not the origin
