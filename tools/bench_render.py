@@ -12,18 +12,23 @@ from spi_b200.training.volumetric_rendering.renderer import ImportanceRenderer
 from spi_b200.utils.camera_utils import cal_canonical_c
 
 
-def main():
+def main(sweep=False):
+    """Default: N in {1, 4} x {32+32, 48+48} at 128^2 rays.  `--sweep`: BASELINE configs[4], the ray-march sweep of
+    SURVEY.md §8d (5): (Dc, Df) in {32+32, 48+48, 64+64, 96+96} x neural_rendering_resolution in {64, 128}, N = 1."""
     dev = 'cuda'
     torch.manual_seed(0)
     dec = OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).to(dev)
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     R = ImportanceRenderer()
-    for n in (1, 4):
-        for dc, df in ((32, 32), (48, 48)):
+    cases = [(n, dc, df, 128) for n in (1, 4) for dc, df in ((32, 32), (48, 48))]
+    if sweep:
+        cases = [(1, dc, df, res) for res in (64, 128) for dc, df in ((32, 32), (48, 48), (64, 64), (96, 96))]
+    for n, dc, df, res in cases:
+        if True:
             rk = dict(depth_resolution=dc, depth_resolution_importance=df, ray_start=2.25, ray_end=3.3, box_warp=1, clamp_mode='softplus')
             planes = torch.randn(n, 3, 32, 256, 256, device=dev).requires_grad_(True)
             c = torch.cat([cal_canonical_c(0.1 * k, 0, 1, dev) for k in range(n)], 0)
-            o, d = RaySampler()(c[:, :16].view(-1, 4, 4), c[:, 16:].view(-1, 3, 3), 128)
+            o, d = RaySampler()(c[:, :16].view(-1, 4, 4), c[:, 16:].view(-1, 3, 3), res)
             for mode, dec_grad in (('planes only', False), ('planes+decoder', True)):
                 dec.requires_grad_(dec_grad)
                 tf, tb = [], []
@@ -39,8 +44,8 @@ def main():
                     if it >= 2:
                         tf.append(e[0].elapsed_time(e[1])); tb.append(e[1].elapsed_time(e[2]))
                     planes.grad = None
-                print(f'N={n} D={dc}+{df} {mode:15s} fwd {sum(tf) / len(tf) / n:7.3f} ms/img   bwd {sum(tb) / len(tb) / n:7.3f} ms/img', flush=True)
+                print(f'N={n} rays={res}^2 D={dc}+{df} {mode:15s} fwd {sum(tf) / len(tf) / n:7.3f} ms/img   bwd {sum(tb) / len(tb) / n:7.3f} ms/img', flush=True)
 
 
 if __name__ == '__main__':
-    main()
+    main(sweep='--sweep' in sys.argv[1:])
