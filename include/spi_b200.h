@@ -40,6 +40,16 @@ int spi_bias_act_noise(const void* x, const void* b, void* y, const float* noise
                        int size_b, int step_b, int hw, int channels_last_c, int dtype, int act, float alpha, float gain,
                        float clamp, cudaStream_t stream);
 
+/* The tail of an up-sampling SynthesisLayer in one pass: conv2d_resample.py:117-119 (4x4 FIR after the stride-2 transposed
+ * convolution) followed by networks_stylegan2.py:320-329 (noise, bias, activation, gain, clamp):
+ *   y = clamp(act(upfirdn2d(x, f[4x4], pad, fir_gain) + noise[h,w]*strength + b[c]) * gain)
+ * x, y: channels-last fp32 [n, c, h, w] given by element strides (c % 4 == 0, 16-byte aligned); act 1 (linear) or 3 (lrelu);
+ * noise (fp32 [out_h*out_w]) may be NULL; clamp < 0 = off.  Same arithmetic and order as spi_upfirdn2d + spi_bias_act_noise. */
+int spi_blur4_bias_act_noise(const float* x, const float* f, float* y, const float* b, const float* noise,
+                             const float* noise_strength, int n, int c, int in_h, int in_w, const long long* x_strides,
+                             const long long* y_strides, int padx0, int padx1, int pady0, int pady1, int flip, float fir_gain,
+                             int act, float alpha, float gain, float clamp, cudaStream_t stream);
+
 /* Gradient reductions of that epilogue in one pass over dx (channels-last fp32 [pixels, C]): db[c] = sum dx (bias_act.py:166),
  * dpix[h,w] = sum_{n,c} dx (gradient of the noise term), dstrength = sum dpix*noise.  Any output may be NULL; pixels = n * hw. */
 int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,

@@ -18,6 +18,7 @@ c_void_p, c_int, c_float, c_ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, 
 _SIGS = {
     'spi_bias_act': [c_void_p] * 6 + [c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_float, c_void_p],
     'spi_upfirdn2d': [c_void_p] * 3 + [c_int] * 5 + [c_void_p, c_void_p] + [c_int] * 11 + [c_float, c_void_p],
+    'spi_blur4_bias_act_noise': [c_void_p] * 6 + [c_int] * 4 + [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_int] + [c_float] * 3 + [c_void_p],
     'spi_filtered_lrelu_sign_shape': [c_int] * 5 + [c_void_p, c_void_p],
     'spi_filtered_lrelu': [c_void_p] * 6 + [c_int] * 5 + [c_void_p, c_void_p] + [c_int] * 14 + [c_float] * 3 + [c_int, c_int, c_void_p],
     'spi_filtered_lrelu_act': [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p] + [c_int] * 4 + [c_float] * 3 + [c_int, c_void_p],

@@ -8,7 +8,8 @@
 //     A[n,o]   = sum_{i,k} g * W * s
 //     t        = d * (g - d^2 * A * W * s)          (t = g when demodulate is off, with d = 1)
 //     dW[o,i,k] = sum_n s[n,i] * t;    ds[n,i] = sum_{o,k} W[o,i,k] * t      (ds accumulated with atomics over o)
-// Tensors are tiny (<= 4 x 2.4 M floats); the point is launch count and fusing the reductions, not bandwidth.
+// Tensors are small (<= 4 x 2.4 M floats) but there are 29 layers per pass: rows are staged in shared memory so that W and the
+// gradient are read once, coalesced (the first, unstaged kernels are kept for rows that do not fit).
 #include "common.cuh"
 
 namespace {
@@ -108,6 +109,158 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
     }
 }
 
+
+// ---- row-staged kernels (the per-layer weight tensors are small, but there are 29 layers per generator pass and the
+// three launches per layer added up to 4.5 % of an iteration: these variants read W once, coalesced, into shared memory)
+
+// Forward, layouts 0 (OIK) and 1 (OKI): grid (O, N), one CTA per output row; the modulated row W*s is staged in shared
+// memory, reduced for the demodulation coefficient, and written out in the destination order with coalesced stores.
+__global__ void __launch_bounds__(256) modulate_row_kernel(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ dcoef,
+                                                           float* __restrict__ out, int O, int I, int KK, int layout_flags, int demod) {
+    extern __shared__ float row[];
+    __shared__ float sh[32];
+    const int layout = layout_flags & 3;
+    const bool flip = (layout_flags & 4) != 0;
+    const int o = blockIdx.x, n = blockIdx.y, len = I * KK;
+    const float* w = W + (size_t)o * len;
+    const float* sn = s + (size_t)n * I;
+    float acc = 0.f;
+    for (int e = threadIdx.x; e < len; e += blockDim.x) { const float v = w[e] * sn[e / KK]; row[e] = v; acc += v * v; }
+    float d = 1.f;
+    if (demod) {
+        d = rsqrtf(block_sum(acc, sh) + 1e-8f);
+        if (threadIdx.x == 0) dcoef[(size_t)n * O + o] = d;
+    } else {
+        __syncthreads();
+    }
+    float* dst = out + ((size_t)n * O + o) * len;
+    if (layout == 0) {
+        for (int e = threadIdx.x; e < len; e += blockDim.x) {
+            int src = e;
+            if (flip) { const int k = e % KK; src = e - k + (KK - 1 - k); }
+            const float v = row[src];
+            dst[e] = demod ? v * d : v;
+        }
+    } else {
+        for (int k = 0; k < KK; k++) {
+            const int kk = flip ? KK - 1 - k : k;
+            for (int i = threadIdx.x; i < I; i += blockDim.x) {       // shared-memory stride KK (odd): conflict-free
+                const float v = row[i * KK + kk];
+                dst[k * I + i] = demod ? v * d : v;
+            }
+        }
+    }
+}
+
+// Forward, layout 2 (IKO, the transposed-convolution weights): 32 x 32 (o, e) tiles transposed through shared memory so that
+// both the W reads (contiguous in e = i*KK + k) and the stores (contiguous in o) are coalesced.  grid (ceil(len/32), ceil(O/32), N).
+__global__ void __launch_bounds__(256) modulate_apply_iko_kernel(const float* __restrict__ W, const float* __restrict__ s,
+                                                                 const float* __restrict__ dcoef, float* __restrict__ out, int O, int I,
+                                                                 int KK, int flip) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int e0 = blockIdx.x * 32, o0 = blockIdx.y * 32, n = blockIdx.z, len = I * KK;
+    {
+        const int e = e0 + tx;
+        const float se = e < len ? s[(size_t)n * I + e / KK] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int o = o0 + ty + 8 * j;
+            if (o < O && e < len) {
+                float v = W[(size_t)o * len + e] * se;
+                if (dcoef) v *= dcoef[(size_t)n * O + o];
+                tile[ty + 8 * j][tx] = v;
+            }
+        }
+    }
+    __syncthreads();
+    const int o = o0 + tx;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int el = ty + 8 * j, e = e0 + el;
+        if (e < len && o < O) {
+            int e2 = e;
+            if (flip) { const int k = e % KK; e2 = e - k + (KK - 1 - k); }
+            out[((size_t)n * len + e2) * O + o] = tile[tx][el];
+        }
+    }
+}
+
+// Backward, every layout: grid (O); the W row and the incoming gradient row are staged in shared memory in W's own (i, k)
+// order (coalesced loads for layouts 0 and 1), then each thread owns whole channels i: A, t, dW and ds come from shared memory,
+// dW leaves through a coalesced store.  Shared memory: 2 * I * KK floats.
+__global__ void __launch_bounds__(256) modulate_bwd_rows_kernel(const float* __restrict__ W, const float* __restrict__ s,
+                                                                const float* __restrict__ dcoef, const float* __restrict__ g,
+                                                                float* __restrict__ dW, float* __restrict__ ds, int N, int O, int I, int KK,
+                                                                int demod, int layout_flags) {
+    extern __shared__ float sm[];
+    __shared__ float sh[32];
+    const int layout = layout_flags & 3;
+    const bool flip = (layout_flags & 4) != 0;
+    const int o = blockIdx.x, len = I * KK;
+    float* wrow = sm;
+    float* grow = sm + len;
+    const float* w = W + (size_t)o * len;
+    for (int e = threadIdx.x; e < len; e += blockDim.x) wrow[e] = w[e];
+    for (int n = 0; n < N; n++) {
+        __syncthreads();                                   // previous sample's grow fully consumed; wrow visible
+        if (layout == 0) {
+            const float* gr = g + ((size_t)n * O + o) * len;
+            for (int e = threadIdx.x; e < len; e += blockDim.x) {
+                int dst = e;
+                if (flip) { const int k = e % KK; dst = e - k + (KK - 1 - k); }
+                grow[dst] = gr[e];
+            }
+        } else if (layout == 1) {
+            const float* gr = g + ((size_t)n * O + o) * len;
+            for (int k = 0; k < KK; k++) {
+                const int kk = flip ? KK - 1 - k : k;
+                for (int i = threadIdx.x; i < I; i += blockDim.x) grow[i * KK + kk] = gr[k * I + i];
+            }
+        } else {
+            const float* gr = g + (size_t)n * len * O + o;
+            for (int e = threadIdx.x; e < len; e += blockDim.x) {
+                int dst = e;
+                if (flip) { const int k = e % KK; dst = e - k + (KK - 1 - k); }
+                grow[dst] = gr[(size_t)e * O];
+            }
+        }
+        __syncthreads();
+        const float* sn = s + (size_t)n * I;
+        float d = 1.f, dA = 0.f;
+        if (demod) {
+            d = dcoef[(size_t)n * O + o];
+            float acc = 0.f;
+            for (int i = threadIdx.x; i < I; i += blockDim.x) {
+                const float si = sn[i];
+                float a = 0.f;
+                for (int k = 0; k < KK; k++) a = fmaf(grow[i * KK + k], wrow[i * KK + k], a);
+                acc = fmaf(a, si, acc);
+            }
+            dA = d * d * block_sum(acc, sh);
+        }
+        for (int i = threadIdx.x; i < I; i += blockDim.x) {       // thread owns channel i: one atomic per (n, i) per CTA
+            const float si = sn[i];
+            float dsi = 0.f;
+            for (int k = 0; k < KK; k++) {
+                const int e = i * KK + k;
+                const float we = wrow[e];
+                const float ge = grow[e];
+                const float t = demod ? d * (ge - dA * we * si) : ge;
+                grow[e] = si * t;                                  // this sample's contribution to dW[o, i, k]
+                dsi = fmaf(we, t, dsi);
+            }
+            if (ds) atomicAdd(ds + (size_t)n * I + i, dsi);
+        }
+        if (dW) {
+            __syncthreads();
+            float* dw = dW + (size_t)o * len;
+            if (n == 0) { for (int e = threadIdx.x; e < len; e += blockDim.x) dw[e] = grow[e]; }
+            else { for (int e = threadIdx.x; e < len; e += blockDim.x) dw[e] += grow[e]; }
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" int spi_modulate_weights(const float* weight, const float* styles, float* out, float* dcoef, int n, int o, int i, int kk,
@@ -116,11 +269,23 @@ extern "C" int spi_modulate_weights(const float* weight, const float* styles, fl
     SPI_CHECK_ARG(weight && styles && out, "modulate_weights: null pointer");
     SPI_CHECK_ARG(n >= 1 && o >= 1 && i >= 1 && kk >= 1 && n <= 65535, "modulate_weights: bad shape");
     SPI_CHECK_ARG(!demodulate || dcoef, "modulate_weights: dcoef buffer required when demodulating");
-    if (demodulate) demod_coef_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, dcoef, o, i, kk);
-    long long total = (long long)n * o * i * kk;
-    long long blocks = (total + 255) / 256, cap = (long long)spi_num_sms() * 8;
-    modulate_apply_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, stream>>>(weight, styles, demodulate ? dcoef : nullptr, out, n, o, i, kk, layout);
-    SPI_COUNT_LAUNCH(demodulate ? 2 : 1);
+    const size_t row_bytes = sizeof(float) * (size_t)i * kk;
+    if ((layout & 3) != 2 && row_bytes <= 40 * 1024) {
+        // one launch: the row is staged in shared memory between the reduction and the store
+        modulate_row_kernel<<<dim3(o, n), 256, row_bytes, stream>>>(weight, styles, dcoef, out, o, i, kk, layout, demodulate);
+        SPI_COUNT_LAUNCH(1);
+    } else if ((layout & 3) == 2) {
+        if (demodulate) demod_coef_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, dcoef, o, i, kk);
+        modulate_apply_iko_kernel<<<dim3((i * kk + 31) / 32, (o + 31) / 32, n), 256, 0, stream>>>(weight, styles, demodulate ? dcoef : nullptr, out,
+                                                                                                 o, i, kk, (layout & 4) != 0);
+        SPI_COUNT_LAUNCH(demodulate ? 2 : 1);
+    } else {
+        if (demodulate) demod_coef_kernel<<<dim3(o, n), 256, 0, stream>>>(weight, styles, dcoef, o, i, kk);
+        long long total = (long long)n * o * i * kk;
+        long long blocks = (total + 255) / 256, cap = (long long)spi_num_sms() * 8;
+        modulate_apply_kernel<<<(int)(blocks > cap ? cap : blocks), 256, 0, stream>>>(weight, styles, demodulate ? dcoef : nullptr, out, n, o, i, kk, layout);
+        SPI_COUNT_LAUNCH(demodulate ? 2 : 1);
+    }
     SPI_LAUNCH_CHECK("modulate_weights");
     return SPI_OK;
 }
@@ -131,7 +296,11 @@ extern "C" int spi_modulate_weights_backward(const float* weight, const float* s
     SPI_CHECK_ARG(weight && styles && grad_out, "modulate_weights_backward: null pointer");
     SPI_CHECK_ARG(!demodulate || dcoef, "modulate_weights_backward: dcoef required when demodulating");
     if (grad_styles) cudaMemsetAsync(grad_styles, 0, sizeof(float) * (size_t)n * i, stream);
-    modulate_bwd_kernel<<<o, 256, 0, stream>>>(weight, styles, dcoef, grad_out, grad_weight, grad_styles, n, o, i, kk, demodulate, layout);
+    const size_t rows_bytes = 2 * sizeof(float) * (size_t)i * kk;
+    if (rows_bytes <= 40 * 1024)
+        modulate_bwd_rows_kernel<<<o, 256, rows_bytes, stream>>>(weight, styles, dcoef, grad_out, grad_weight, grad_styles, n, o, i, kk, demodulate, layout);
+    else
+        modulate_bwd_kernel<<<o, 256, 0, stream>>>(weight, styles, dcoef, grad_out, grad_weight, grad_styles, n, o, i, kk, demodulate, layout);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("modulate_weights_backward");
     return SPI_OK;

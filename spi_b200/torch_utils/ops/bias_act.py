@@ -212,3 +212,79 @@ def bias_act_noise(x, b, noise_const, noise_strength, act='lrelu', alpha=None, g
     if x.dtype != torch.float32 or 'x' in spec.ref:
         return bias_act(x + noise_const * noise_strength, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
     return _BiasActNoise.apply(x, b, noise_const, noise_strength, cfg)
+
+
+class _BlurBiasActNoise(torch.autograd.Function):
+    """Tail of an up-sampling SynthesisLayer in one pass (`spi_blur4_bias_act_noise`): the 4x4 FIR that follows the stride-2
+    transposed convolution (conv2d_resample.py:117-119) with the noise / bias / activation / clamp epilogue
+    (networks_stylegan2.py:320-329) applied in its store, so the blurred tensor never goes to HBM un-activated.  Backward is the
+    unfused chain: epilogue gradient from the saved output, its reductions, then the FIR's own backward (upfirdn2d.py:258-263)."""
+
+    @staticmethod
+    def forward(ctx, x, f, b, noise_const, noise_strength, fir_cfg, cfg):
+        padx0, padx1, pady0, pady1, flip, fir_gain = fir_cfg
+        dim, spec, alpha, gain, clamp = cfg
+        n, c, ih, iw = x.shape
+        oh, ow = ih + pady0 + pady1 - 3, iw + padx0 + padx1 - 3
+        y = torch.empty([n, c, oh, ow], dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        nc = noise_const.contiguous() if noise_const is not None else None
+        f = f.to(x.device).contiguous()
+        with _lib.timed('upfirdn2d', (x.numel() + y.numel()) * 4):
+            _lib.check(_lib.load().spi_blur4_bias_act_noise(
+                _lib.ptr(x), _lib.ptr(f), _lib.ptr(y), _lib.ptr(b.contiguous()), _lib.ptr(nc), _lib.ptr(noise_strength), n, c, ih, iw,
+                _lib.strides4(x), _lib.strides4(y), padx0, padx1, pady0, pady1, int(bool(flip)), float(fir_gain), spec.cuda_idx, alpha,
+                gain, clamp, _lib.stream()))
+        ctx.save_for_backward(f, b, y, nc, noise_strength)
+        ctx.cfg, ctx.fir_cfg, ctx.x_shape = cfg, fir_cfg, x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import upfirdn2d
+        f, b, y, nc, strength = ctx.saved_tensors
+        padx0, padx1, pady0, pady1, flip, fir_gain = ctx.fir_cfg
+        dy = dy.contiguous(memory_format=torch.channels_last)
+        dpre = _BiasActGrad.apply(dy, None, b, y, ctx.cfg)
+        db = dn = ds = None
+        need_b, need_n, need_s = ctx.needs_input_grad[2], nc is not None and ctx.needs_input_grad[3], nc is not None and ctx.needs_input_grad[4]
+        red = _fused_reductions(dpre, need_b, noise=nc, want_dpix=need_n, want_ds=need_s) if (need_b or need_n or need_s) else None
+        if red is not None:
+            db, pix, ds = red
+            if need_n:
+                dn = pix * strength
+        else:
+            if need_b:
+                db = dpre.sum([0, 2, 3])
+            if need_n or need_s:
+                pix = dpre.sum([0, 1])
+                dn = pix * strength if need_n else None
+                ds = (pix * nc).sum() if need_s else None
+        dx = None
+        if ctx.needs_input_grad[0]:
+            _, _, ih, iw = ctx.x_shape
+            _, _, oh, ow = dpre.shape
+            p = (4 - padx0 - 1, iw - ow + padx0, 4 - pady0 - 1, ih - oh + pady0)
+            dx = upfirdn2d._Upfirdn2d.apply(dpre, f, (1, 1, 1, 1, *p, not flip, fir_gain))
+        return dx, None, db, dn, ds, None, None
+
+
+def blur_bias_act_noise(x, f, b, noise_const=None, noise_strength=None, padding=0, flip_filter=False, fir_gain=1, act='lrelu', alpha=None,
+                        gain=None, clamp=None):
+    """`bias_act(upfirdn2d(x, f, padding=padding, gain=fir_gain) + noise_const * noise_strength, b, act, gain, clamp)` for a 4x4 filter
+    at up = down = 1; one kernel when x is channels-last fp32 with C % 4 == 0 and the activation is linear / lrelu, the two ops otherwise."""
+    from . import upfirdn2d
+    spec = activation_funcs[act]
+    padx0, padx1, pady0, pady1 = upfirdn2d._parse_padding(padding)
+    fusable = (x.is_cuda and x.dtype == torch.float32 and x.ndim == 4 and x.shape[1] % 4 == 0 and x.stride(1) == 1 and x.shape[1] > 1
+               and f is not None and f.ndim == 2 and tuple(f.shape) == (4, 4) and f.dtype == torch.float32 and act in ('linear', 'lrelu')
+               and b is not None and x.data_ptr() % 16 == 0 and all(st % 4 == 0 for st in (x.stride(0), x.stride(2), x.stride(3)))
+               and x.shape[2] + pady0 + pady1 >= 4 and x.shape[3] + padx0 + padx1 >= 4)
+    if not fusable:
+        y = upfirdn2d.upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=fir_gain)
+        if noise_const is not None:
+            return bias_act_noise(y, b, noise_const, noise_strength, act=act, alpha=alpha, gain=gain, clamp=clamp)
+        return bias_act(y, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
+    assert clamp is None or clamp >= 0
+    cfg = (1, spec, float(alpha if alpha is not None else spec.def_alpha),
+           float(gain if gain is not None else spec.def_gain), float(clamp if clamp is not None else -1))
+    return _BlurBiasActNoise.apply(x, f, b, noise_const, noise_strength, (padx0, padx1, pady0, pady1, bool(flip_filter), fir_gain), cfg)

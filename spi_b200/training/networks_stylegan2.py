@@ -11,6 +11,8 @@ Module / parameter / buffer names and constructor signatures are the reference's
     a dense conv problem;
   * FIR / bias / activation passes are the sm_100a kernels behind `torch_utils.ops`.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -20,13 +22,18 @@ from ..torch_utils import misc, persistence
 from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
 
 
+# up-sampling layers: FIR + noise + bias + activation in one kernel (SPI_FUSE_BLUR_EPILOGUE=0: the two separate passes, for A/B timing)
+FUSE_BLUR_EPILOGUE = os.environ.get('SPI_FUSE_BLUR_EPILOGUE', '1') != '0'
+
+
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
     return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
 
 
-def _batched_resample_conv(x, w, f, up, padding, flip_weight):
+def _batched_resample_conv(x, w, f, up, padding, flip_weight, epilogue=None):
     """conv2d_resample (conv2d_resample.py:48-143) for per-sample weights w [N, O, I, kh, kw]: the two branches a
-    generator layer takes (up = 1: plain conv; up = 2: stride-2 transposed conv then 4x4 FIR with gain 4)."""
+    generator layer takes (up = 1: plain conv; up = 2: stride-2 transposed conv then 4x4 FIR with gain 4).  `epilogue` (keyword
+    arguments of `bias_act.blur_bias_act_noise`) folds the layer's noise / bias / activation pass into the FIR kernel."""
     o, i, kh, kw = w.shape[1:]
     if up == 1:
         return conv_engine.conv2d_per_sample(x, w, padding=[padding, padding], flip_weight=flip_weight)
@@ -37,12 +44,15 @@ def _batched_resample_conv(x, w, f, up, padding, flip_weight):
     py1 = padding + (fh - up) // 2 - (kh - up)
     pxt, pyt = max(min(-px0, -px1), 0), max(min(-py0, -py1), 0)
     y = conv_engine.conv2d_per_sample(x, w, stride=up, padding=[pyt, pxt], transpose=True, flip_weight=(not flip_weight))
+    if epilogue is not None:
+        return bias_act.blur_bias_act_noise(y, f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], fir_gain=up ** 2, **epilogue)
     return upfirdn2d.upfirdn2d(x=y, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2)
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True):
-    """networks_stylegan2.py:34-91.  x [N,I,H,W], weight [O,I,kh,kw], styles [N,I]."""
+                     flip_weight=True, fused_modconv=True, blur_epilogue=None):
+    """networks_stylegan2.py:34-91.  x [N,I,H,W], weight [O,I,kh,kw], styles [N,I].  `blur_epilogue` (up = 2, fused branch only):
+    the caller's noise / bias / activation pass, applied inside the FIR kernel that ends the up-sampling convolution."""
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
     misc.assert_shape(weight, [out_channels, in_channels, kh, kw])
@@ -57,7 +67,10 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
             # flip_weight is set (conv2d_resample.py:38-40,117): modulate_weights writes them like that directly
             pre = bool(flip_weight) and (kh > 1 or kw > 1)
             w = modulate_weights(weight, styles, demodulate, layout='ihwo', flip=pre)
-            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight and not pre)
+            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight and not pre, epilogue=blur_epilogue)
+            if blur_epilogue is not None:
+                assert noise is None
+                return x
         else:
             w = modulate_weights(weight, styles, demodulate, layout='ohwi')
             x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
@@ -195,10 +208,17 @@ class SynthesisLayer(torch.nn.Module):
         fuse_noise = self.use_noise and noise_mode == 'const' and x.dtype == torch.float32
         if self.use_noise and noise_mode == 'const' and not fuse_noise:
             noise = self.noise_const * self.noise_strength
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        if self.up == 2 and fused_modconv and noise is None and x.dtype == torch.float32 and FUSE_BLUR_EPILOGUE:
+            # up-sampling layer: transposed conv -> [4x4 FIR + (constant noise) + bias + lrelu*gain + clamp] in one kernel
+            epi = dict(b=self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
+            if fuse_noise:
+                epi.update(noise_const=self.noise_const, noise_strength=self.noise_strength)
+            return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=None, up=self.up, padding=self.padding,
+                                    resample_filter=self.resample_filter, flip_weight=False, fused_modconv=True, blur_epilogue=epi)
+        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         if fuse_noise:      # + noise_const*noise_strength + bias -> lrelu*gain -> clamp in one pass
             return bias_act.bias_act_noise(x, self.bias.to(x.dtype), self.noise_const, self.noise_strength, act=self.activation,
                                            gain=act_gain, clamp=act_clamp)

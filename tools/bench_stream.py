@@ -64,11 +64,21 @@ def main():
         report(f'epilogue_grad_reduce [{n},{c},{h},{h}]', nb, time_ms(lambda: bias_act._fused_reductions(dy, True, noise=nz, want_dpix=True, want_ds=True)))
         del x, y, dy
     f = upfirdn2d.setup_filter([1, 3, 3, 1], device='cuda')
-    for n, c, h in ((1, 128, 513), (1, 256, 257), (4, 128, 513), (1, 128, 257)):
+    for n, c, h in ((1, 128, 513), (1, 256, 257), (4, 128, 513), (4, 256, 257), (1, 128, 257)):
         x = cl(n, c, h, h)
         out = upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)
         report(f'upfirdn2d blur4 [{n},{c},{h},{h}] -> {tuple(out.shape[2:])}', (x.numel() + out.numel()) * 4,
                time_ms(lambda: upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4)))
+        b = torch.randn(c, device='cuda')
+        nz = torch.randn(h - 1, h - 1, device='cuda')
+        st = torch.tensor(0.3, device='cuda')
+        with torch.no_grad():
+            t2 = time_ms(lambda: bias_act.bias_act(upfirdn2d.upfirdn2d(x, f, padding=[1, 1, 1, 1], gain=4), b, act='lrelu', clamp=256))
+            report(f'  blur4 then bias_act (two passes) [{n},{c},{h},{h}]', (x.numel() + out.numel()) * 4, t2)
+            report(f'  blur4 + bias + lrelu fused [{n},{c},{h},{h}]', (x.numel() + out.numel()) * 4,
+                   time_ms(lambda: bias_act.blur_bias_act_noise(x, f, b, padding=[1, 1, 1, 1], fir_gain=4, act='lrelu', clamp=256)))
+            report(f'  blur4 + noise + bias + lrelu fused [{n},{c},{h},{h}]', (x.numel() + out.numel()) * 4,
+                   time_ms(lambda: bias_act.blur_bias_act_noise(x, f, b, nz, st, padding=[1, 1, 1, 1], fir_gain=4, act='lrelu', clamp=256)))
         del x, out
     for n, c, h in ((1, 96, 128), (1, 3, 256), (4, 3, 256)):
         x = cl(n, c, h, h)
