@@ -106,6 +106,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_xfast(UpfirdnParams p) {
 }
 
 // channels_last, fp32, C % 4 == 0, 16-B aligned
+// IDX: 32-bit index arithmetic when the launch fits (the 64-bit div/mod chain per thread made these kernels instruction-bound);
+// UP / DOWN: compile-time resampling factors of the two hot cases (x2 up-sampling, x2 down-sampling), 0 = run-time values.
+template <typename IDX, int UP, int DOWN>
 __global__ void __launch_bounds__(256) upfirdn2d_cfast_f32(UpfirdnParams p) {
     __shared__ float sf[MAXF * MAXF];
     for (int i = threadIdx.x; i < p.fw * p.fh; i += blockDim.x) {
@@ -114,20 +117,21 @@ __global__ void __launch_bounds__(256) upfirdn2d_cfast_f32(UpfirdnParams p) {
     }
     __syncthreads();
     const float* x = (const float*)p.x; float* y = (float*)p.y;
+    const int upx = UP ? UP : p.upx, upy = UP ? UP : p.upy, downx = DOWN ? DOWN : p.downx, downy = DOWN ? DOWN : p.downy;
     const int c4 = p.c / 4;
-    const long long total = (long long)p.n * p.outH * p.outW * c4;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        int cv = (int)(idx % c4); long long r = idx / c4;
-        int ox = (int)(r % p.outW); r /= p.outW;
-        int oy = (int)(r % p.outH); int nn = (int)(r / p.outH);
+    const IDX total = (IDX)p.n * p.outH * p.outW * c4;
+    for (IDX idx = (IDX)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IDX)gridDim.x * blockDim.x) {
+        int cv = (int)(idx % (IDX)c4); IDX r = idx / (IDX)c4;
+        int ox = (int)(r % (IDX)p.outW); r /= (IDX)p.outW;
+        int oy = (int)(r % (IDX)p.outH); int nn = (int)(r / (IDX)p.outH);
         int ky0, iy0, kx0, ix0;
-        tap_start(oy, p.downy, p.upy, p.pady0, ky0, iy0);
-        tap_start(ox, p.downx, p.upx, p.padx0, kx0, ix0);
+        tap_start(oy, downy, upy, p.pady0, ky0, iy0);
+        tap_start(ox, downx, upx, p.padx0, kx0, ix0);
         const float* xb = x + nn * p.xs_n + cv * 4;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int ky = ky0, iy = iy0; ky < p.fh; ky += p.upy, iy++) {
+        for (int ky = ky0, iy = iy0; ky < p.fh; ky += upy, iy++) {
             if (iy < 0 || iy >= p.inH) continue;
-            for (int kx = kx0, ix = ix0; kx < p.fw; kx += p.upx, ix++) {
+            for (int kx = kx0, ix = ix0; kx < p.fw; kx += upx, ix++) {
                 if (ix < 0 || ix >= p.inW) continue;
                 float w = sf[ky * p.fw + kx];
                 float4 v = __ldg((const float4*)(xb + iy * p.xs_h + ix * p.xs_w));
@@ -286,7 +290,7 @@ __global__ void __launch_bounds__(256, MINB) upfirdn2d_blur4_strip_cl_f32(Upfird
 }
 
 // channel-fastest scalar fallback (any dtype / C)
-template <class T>
+template <class T, typename IDX, int UP, int DOWN>
 __global__ void __launch_bounds__(256) upfirdn2d_cfast(UpfirdnParams p) {
     typedef typename Acc<T>::t S;
     __shared__ float sf[MAXF * MAXF];
@@ -296,19 +300,20 @@ __global__ void __launch_bounds__(256) upfirdn2d_cfast(UpfirdnParams p) {
     }
     __syncthreads();
     const T* x = (const T*)p.x; T* y = (T*)p.y;
-    const long long total = (long long)p.n * p.outH * p.outW * p.c;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-        int ch = (int)(idx % p.c); long long r = idx / p.c;
-        int ox = (int)(r % p.outW); r /= p.outW;
-        int oy = (int)(r % p.outH); int nn = (int)(r / p.outH);
+    const int upx = UP ? UP : p.upx, upy = UP ? UP : p.upy, downx = DOWN ? DOWN : p.downx, downy = DOWN ? DOWN : p.downy;
+    const IDX total = (IDX)p.n * p.outH * p.outW * p.c;
+    for (IDX idx = (IDX)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (IDX)gridDim.x * blockDim.x) {
+        int ch = (int)(idx % (IDX)p.c); IDX r = idx / (IDX)p.c;
+        int ox = (int)(r % (IDX)p.outW); r /= (IDX)p.outW;
+        int oy = (int)(r % (IDX)p.outH); int nn = (int)(r / (IDX)p.outH);
         int ky0, iy0, kx0, ix0;
-        tap_start(oy, p.downy, p.upy, p.pady0, ky0, iy0);
-        tap_start(ox, p.downx, p.upx, p.padx0, kx0, ix0);
+        tap_start(oy, downy, upy, p.pady0, ky0, iy0);
+        tap_start(ox, downx, upx, p.padx0, kx0, ix0);
         const T* xb = x + nn * p.xs_n + ch * p.xs_c;
         S acc = 0;
-        for (int ky = ky0, iy = iy0; ky < p.fh; ky += p.upy, iy++) {
+        for (int ky = ky0, iy = iy0; ky < p.fh; ky += upy, iy++) {
             if (iy < 0 || iy >= p.inH) continue;
-            for (int kx = kx0, ix = ix0; kx < p.fw; kx += p.upx, ix++)
+            for (int kx = kx0, ix = ix0; kx < p.fw; kx += upx, ix++)
                 if (ix >= 0 && ix < p.inW) acc += (S)xb[iy * p.xs_h + ix * p.xs_w] * (S)sf[ky * p.fw + kx];
         }
         y[nn * p.ys_n + ch * p.ys_c + oy * p.ys_h + ox * p.ys_w] = (T)(acc * (S)p.gain);
@@ -350,6 +355,8 @@ static int upfirdn2d_impl(const void* x, const float* f, void* y, int dtype, int
         return (int)(b < 1 ? 1 : (b > cap ? cap : b));
     };
     long long outs = (long long)n * c * out_h * out_w;
+    const bool small = outs < (1LL << 31) - (1LL << 24);          // 32-bit index arithmetic (grid stride < 2^22 threads)
+    const bool up2 = upx == 2 && upy == 2 && downx == 1 && downy == 1, down2 = upx == 1 && upy == 1 && downx == 2 && downy == 2;
     if (cfast) {
         bool v4 = dtype == SPI_DT_F32 && (c % 4 == 0) && (((uintptr_t)x | (uintptr_t)y) % 16 == 0) &&
                   (p.xs_n % 4 == 0) && (p.xs_h % 4 == 0) && (p.xs_w % 4 == 0) && (p.ys_n % 4 == 0) && (p.ys_h % 4 == 0) && (p.ys_w % 4 == 0);
@@ -374,10 +381,19 @@ static int upfirdn2d_impl(const void* x, const float* f, void* y, int dtype, int
             if (epi) upfirdn2d_blur4_cl_f32<true><<<grid_for(patches), block, 0, stream>>>(p);
             else upfirdn2d_blur4_cl_f32<false><<<grid_for(patches), block, 0, stream>>>(p);
         }
-        else if (v4) upfirdn2d_cfast_f32<<<grid_for(outs / 4), block, 0, stream>>>(p);
-        else if (dtype == SPI_DT_F32) upfirdn2d_cfast<float><<<grid_for(outs), block, 0, stream>>>(p);
-        else if (dtype == SPI_DT_F16) upfirdn2d_cfast<__half><<<grid_for(outs), block, 0, stream>>>(p);
-        else if (dtype == SPI_DT_F64) upfirdn2d_cfast<double><<<grid_for(outs), block, 0, stream>>>(p);
+        else if (v4) {
+            if (!small) upfirdn2d_cfast_f32<long long, 0, 0><<<grid_for(outs / 4), block, 0, stream>>>(p);
+            else if (up2) upfirdn2d_cfast_f32<unsigned, 2, 1><<<grid_for(outs / 4), block, 0, stream>>>(p);
+            else if (down2) upfirdn2d_cfast_f32<unsigned, 1, 2><<<grid_for(outs / 4), block, 0, stream>>>(p);
+            else upfirdn2d_cfast_f32<unsigned, 0, 0><<<grid_for(outs / 4), block, 0, stream>>>(p);
+        } else if (dtype == SPI_DT_F32) {
+            if (!small) upfirdn2d_cfast<float, long long, 0, 0><<<grid_for(outs), block, 0, stream>>>(p);
+            else if (up2) upfirdn2d_cfast<float, unsigned, 2, 1><<<grid_for(outs), block, 0, stream>>>(p);
+            else if (down2) upfirdn2d_cfast<float, unsigned, 1, 2><<<grid_for(outs), block, 0, stream>>>(p);
+            else upfirdn2d_cfast<float, unsigned, 0, 0><<<grid_for(outs), block, 0, stream>>>(p);
+        }
+        else if (dtype == SPI_DT_F16) upfirdn2d_cfast<__half, long long, 0, 0><<<grid_for(outs), block, 0, stream>>>(p);
+        else if (dtype == SPI_DT_F64) upfirdn2d_cfast<double, long long, 0, 0><<<grid_for(outs), block, 0, stream>>>(p);
         else { spi_set_error("upfirdn2d: unsupported dtype %d", dtype); return SPI_ERR_ARG; }
     } else {
         if (epi) { spi_set_error("blur4_bias_act_noise: x and y must be channels-last"); return SPI_ERR_ARG; }
