@@ -10,7 +10,13 @@ from ..criteria.lpips.lpips import LPIPS
 class Metric:
     def __init__(self, lpips_loss=None, id_loss=None):
         self.lpips_loss = lpips_loss if lpips_loss is not None else LPIPS(net_type='vgg').to(global_config.device).eval()
-        self.id_loss = id_loss if id_loss is not None else IDLoss(paths_config.IDLOSS_PATH).to(global_config.device).eval()
+        if id_loss is None:
+            import os
+            if not os.path.isfile(paths_config.IDLOSS_PATH):
+                print(f'[WARNING]: {paths_config.IDLOSS_PATH} not found: the ID similarity column of metric_log.txt comes from a randomly '
+                      'initialised IR-SE50 and is only meaningful for plumbing runs')
+            id_loss = IDLoss(paths_config.IDLOSS_PATH).to(global_config.device).eval()
+        self.id_loss = id_loss
 
     @torch.no_grad()
     def run(self, gt, fake):

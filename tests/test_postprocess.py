@@ -113,3 +113,89 @@ def test_interpolated_keyframes_are_periodic_and_hit_the_keys():
     assert w.shape == (12, 14, 8)
     for k in range(3):
         torch.testing.assert_close(w[4 * k], ws[k], rtol=1e-5, atol=1e-5)
+
+
+class _FakeG(torch.nn.Module):
+    """Stands in for TriPlaneGenerator on the CPU: records how `synthesis` is called and paints the camera into the image."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self._last_planes = 'kept'
+        self.calls = []
+
+    def synthesis(self, ws, c, noise_mode='const', need_image=True, cache_backbone=False, use_cached_backbone=False, **kw):
+        self.calls.append(dict(n=ws.shape[0], stride0=ws.stride(0), noise_mode=noise_mode, need_image=need_image,
+                               cache=cache_backbone, use_cached=use_cached_backbone))
+        if cache_backbone:
+            self._last_planes = 'planes of this clip'
+        n = c.shape[0]
+        img = c[:, 3].reshape(n, 1, 1, 1).expand(n, 3, 16, 16).clone() / 3.0           # cam2world[0, 3]: the camera's x position
+        return {'image': img if need_image else None, 'image_raw': img[:, :, ::2, ::2], 'image_depth': img[:, :1, ::2, ::2] + torch.rand(n, 1, 8, 8)}
+
+
+def test_render_orbit_uses_one_backbone_pass_and_broadcast_latents():
+    from spi_b200.utils.video_utils import render_orbit
+    G = _FakeG()
+    ws = torch.randn(1, 14, 512)
+    frames, poses = render_orbit(G, ws, w_frames=10, batch=4)
+    assert frames.shape == (10, 16, 16, 3) and frames.dtype == torch.uint8 and poses.shape == (10, 4, 4)
+    assert [c['n'] for c in G.calls] == [4, 4, 2]
+    assert all(c['stride0'] == 0 and c['noise_mode'] == 'const' and c['need_image'] for c in G.calls)        # a broadcast view, never a copy
+    assert [(c['cache'], c['use_cached']) for c in G.calls] == [(True, False), (False, True), (False, True)]
+    assert G._last_planes == 'kept'                                        # the caller's cached planes are put back
+    assert len({int(f[0, 0, 0]) for f in frames}) > 3                      # the orbit moves
+    G.calls.clear()
+    depth, _ = render_orbit(G, ws, w_frames=3, batch=8, image_mode='image_depth')
+    assert depth.shape == (3, 8, 8, 3) and not G.calls[0]['need_image']
+    assert int(depth.amin()) == 0 and int(depth.amax()) == 255
+    G.calls.clear()
+    two = torch.randn(2, 14, 512)                                          # two keyframes: interpolated latents, no backbone sharing
+    frames, _ = render_orbit(G, two, w_frames=3, batch=4)
+    assert frames.shape[0] == 6 and all(not c['cache'] and not c['use_cached'] and c['stride0'] != 0 for c in G.calls)
+
+
+def test_coach_tail_writes_checkpoint_stills_clip_and_metrics():
+    """`BaseCoach.finish_image` + `log_metric` with logging on (pti_coach.py:87-98): files of the reference's output tree."""
+    cv2 = pytest.importorskip('cv2')
+    from spi_b200.configs import global_config, hyperparameters, paths_config
+    from spi_b200.training.coaches.base_coach import BaseCoach
+    keys = ('checkpoints_dir', 'embedding_base_dir', 'experiments_output_dir', 'images_output_dir', 'mirror_images_output_dir', 'video_output_dir')
+    saved = {k: getattr(paths_config, k) for k in keys}
+    saved_step, saved_dev = hyperparameters.G_1_step, global_config.device
+
+    class M:
+        def run(self, gt, fake):
+            return float((gt - fake).square().mean()), 0.25, 0.5
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            for k in keys:
+                setattr(paths_config, k, os.path.join(d, k) + '/')
+                os.makedirs(os.path.join(d, k, 'Coach_x'))
+            hyperparameters.G_1_step, global_config.device = 3, 'cpu'
+            coach = object.__new__(BaseCoach)
+            coach.G, coach.use_wandb, coach.coach_name, coach.metric_dic, coach._metric = _FakeG(), True, 'Coach_x', {}, M()
+            from spi_b200.utils.camera_utils import cal_canonical_c
+            w, c, image = torch.randn(1, 14, 512), cal_canonical_c(0.3, 0, 1, 'cpu'), torch.rand(1, 3, 16, 16) * 2 - 1
+            paths_config.experiments_output_dir = os.path.join(d, 'experiments_output_dir', 'Coach_x', 'img0')
+            os.makedirs(paths_config.experiments_output_dir)
+            coach.finish_image(w, image, c, 'img0')
+            exp = paths_config.experiments_output_dir
+            assert sorted(os.listdir(exp)) == ['img0_G1_inv.avi', 'img0_G1_inv.jpg', 'img0_G1_inv_m.jpg']
+            assert os.path.isfile(os.path.join(d, 'images_output_dir', 'Coach_x', 'img0.jpg'))
+            assert os.path.isfile(os.path.join(d, 'mirror_images_output_dir', 'Coach_x', 'img0.jpg'))
+            clip = os.path.join(d, 'video_output_dir', 'Coach_x', 'img0.avi')
+            cap = cv2.VideoCapture(clip)
+            assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 120          # base_coach.py:236-237: the default 120-frame orbit
+            cap.release()
+            ckpt = torch.load(os.path.join(d, 'checkpoints_dir', 'Coach_x', 'img0.pt'))
+            assert sorted(ckpt) == ['G', 'c', 'w'] and torch.equal(ckpt['w'], w)
+            assert list(coach.metric_dic) == ['G1_inv'] and len(coach.metric_dic['G1_inv']['l2_m']) == 1
+            paths_config.experiments_output_dir = os.path.join(d, 'experiments_output_dir', 'Coach_x')
+            coach.log_metric()
+            text = open(os.path.join(paths_config.experiments_output_dir, 'metric_log.txt')).read()
+            assert text.startswith('Coach name: Coach_x\n') and 'Mode: G1_inv AVG' in text and 'Lpips: 0.250000; ID Sim: 0.500000' in text
+    finally:
+        for k, v in saved.items():
+            setattr(paths_config, k, v)
+        hyperparameters.G_1_step, global_config.device = saved_step, saved_dev
