@@ -259,9 +259,6 @@ def test_shared_backbone_equals_per_view_evaluation(gen_sd, lpips_mod, cx_mod):
             w = weights.w_pivot(5).cuda().requires_grad_(True)
             jit, u = src.render(1, 128 * 128, rk)
             coach.G.renderer.inject_noise(jit.cuda(), u.cuda())
-            for which in ('G', 'G', 'G', 'O'):
-                if which == 'G' or True:
-                    pass
             for k in range(3):
                 r = src.rand(4, 2)
                 rng.inject(r[:, 0:1].clone(), r[:, 1:2].clone())
