@@ -362,12 +362,12 @@ static int upfirdn2d_impl(const void* x, const float* f, void* y, int dtype, int
                   (p.xs_n % 4 == 0) && (p.xs_h % 4 == 0) && (p.xs_w % 4 == 0) && (p.ys_n % 4 == 0) && (p.ys_h % 4 == 0) && (p.ys_w % 4 == 0);
         const bool blur4 = v4 && upx == 1 && upy == 1 && downx == 1 && downy == 1 && fw == 4 && fh == 4;
         auto strips = [&](int ty) { return (long long)n * ((out_h + ty - 1) / ty) * ((out_w + 3) / 4) * (c / 4); };
-        // large layers: 16-row strips while they still give every SM two CTAs, else 8-row strips (measured on B200: 84 -> 72 us at
-        // [1,128,513,513], 307 -> 227 us at [4,128,513,513], 45 -> 41 us at [1,256,257,257]; profiles/r1_bench_stream_kernels.txt)
         if (epi && !blur4) {
             spi_set_error("blur4_bias_act_noise: needs channels-last float32 with C %% 4 == 0, 16-byte aligned, and a 4x4 filter at up = down = 1");
             return SPI_ERR_ARG;
         }
+        // large layers: 16-row strips while they still give every SM two CTAs, else 8-row strips (measured on B200: 84 -> 72 us at
+        // [1,128,513,513], 307 -> 227 us at [4,128,513,513], 45 -> 41 us at [1,256,257,257]; profiles/r1_bench_stream_kernels.txt)
         const bool big = blur4 && out_h >= 64;
         const long long patches = (long long)n * ((out_h + 3) / 4) * ((out_w + 1) / 2) * (c / 4);
         if (big && !epi && strips(16) >= 148LL * 512) {
