@@ -141,3 +141,16 @@ def test_id_similarity(golden):
     with torch.no_grad():
         assert rel_l2(idloss.extract_feats(x, sd), g['feats_x']) < TOL
         assert abs(float(idloss.similarity(x, y, sd)) - float(g['sim'])) < 1e-5
+
+
+def test_sgw_plus_projector_matches_reference(golden):
+    """Two steps of the oracle's `sgw+` projector against the latent the reference's w_plus_projector.py produced for the same
+    draws (oracle/make_golden_sgw.py)."""
+    from oracle.make_golden import make_nets
+    g = golden('sgw_plus')
+    sd = weights.generator_state_dict(0)
+    p = loops.Projector(sd, weights.target_image(), weights.canonical_camera(0.3), make_nets(), kind='sgw+', num_steps=500,
+                        noise=loops.NoiseSource(300))
+    infos = [p.step(i) for i in range(2)]
+    assert rel_l2(p.result(), g['w']) < 1e-6
+    assert abs(infos[1]['loss'] / float(g['loss'][1]) - 1) < 1e-4 and abs(p.w_std / float(g['w_std']) - 1) < 1e-6
