@@ -178,3 +178,22 @@ def test_product_camera_helpers_against_reference_goldens(golden):
     assert set(map(tuple, d)) <= {(0, 1), (0, 2), (0, 3), (1, 0), (2, 0)} and torch.equal(cu.cal_mirror_c(m), c)
     yaw = lambda cam: float(cu.rotation_to_angle(cam.view(25)[:16].view(4, 4)[:3, :3])[0])
     assert abs(yaw(m) + yaw(c)) < 1e-6 and abs(abs(yaw(c)) - 0.3) < 5e-2       # the orbit centre is the look-at point [0, 0, 0.2], not the origin
+
+
+def test_projector_schedule_all_steps():
+    """LR / w-noise schedule of the stage-1 projectors (mirror_projector.py:84-91): the product's host code against the oracle's and
+    against the closed form, at every step of the 500-step run; fixed points: lr = 0 at step 0, peak lr 0.01 from 5 % to 75 %
+    (`initial_learning_rate`, not `first_inv_lr`), noise off after 75 %."""
+    import types
+    from oracle import loops
+    from spi_b200.training.projectors._common import LatentProjector
+    fake = types.SimpleNamespace(num_steps=500, w_std=9.7, hp=dict(lr0=0.01, noise0=0.05, down=0.25, up=0.05, nramp=0.75, regw=1e5))
+    for step in range(500):
+        lr, wn = LatentProjector.schedule(fake, step)
+        lr_o, wn_o = loops.lr_schedule(step, 500, 9.7)
+        t = step / 500
+        ramp = (0.5 - 0.5 * np.cos(min(1.0, (1.0 - t) / 0.25) * np.pi)) * min(1.0, t / 0.05)
+        assert lr == lr_o == 0.01 * ramp and wn == wn_o == 9.7 * 0.05 * max(0.0, 1.0 - t / 0.75) ** 2
+    assert LatentProjector.schedule(fake, 0)[0] == 0.0
+    assert all(LatentProjector.schedule(fake, s)[0] == 0.01 for s in (25, 100, 375))
+    assert LatentProjector.schedule(fake, 376)[0] < 0.01 and LatentProjector.schedule(fake, 375)[1] == 0.0
