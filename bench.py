@@ -37,7 +37,7 @@ def parse():
     ap.add_argument('--steps', type=int, default=24)
     ap.add_argument('--warmup', type=int, default=6)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--cpu-budget-s', type=float, default=150.0, help='wall budget of the reference / cpu_baseline legs')
+    ap.add_argument('--cpu-budget-s', type=float, default=420.0, help='wall budget of the timed part of the reference leg')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -74,7 +74,7 @@ def synthetic_inputs(seed=4):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms 200`
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe): ONE `nvidia-smi -lms 50`
     child started from the main thread before the timed region and killed after it (no fork while CUDA calls are in flight)."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
@@ -87,7 +87,7 @@ class ClockSampler:
         fd, self.path = tempfile.mkstemp(prefix='clocks_', suffix='.csv')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '200'], stdout=fd, stderr=subprocess.DEVNULL)
+                                          '-lms', '50'], stdout=fd, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
         os.close(fd)
@@ -219,7 +219,7 @@ class OursJob:
         self.proj = LatentProjector(coach.G, self.dev['img'], self.dev['c'], 'mir', lpips_func=self.lpips, num_steps=500, w_avg_samples=600)
         self.state = SPIState(self.dev['img'], self.dev['c'], self.dev['mask'], self.dev['lm'])
         self.w_pivot = None
-        self.i_mir = self.i_rot = 0
+        self.i_mir = 0
 
     def upload(self):
         """Pinned host -> the SAME device buffers (addresses stay valid for the captured graphs)."""
@@ -230,7 +230,8 @@ class OursJob:
                 self.dev[k].copy_(v, non_blocking=True)
         return sum(v.numel() * v.element_size() for v in self.pinned.values())
 
-    def step(self, kind, e2e=False):
+    def step(self, item, e2e=False):
+        kind, idx = item
         if e2e:      # host buffers in (image, camera, parsing mask, landmarks), loss scalar out, every step
             self.upload()
         if kind == 'mir':
@@ -240,17 +241,51 @@ class OursJob:
         else:
             if self.w_pivot is None:
                 self.w_pivot = self.proj.result().detach().clone().requires_grad_(True)
-            res, _ = self.coach.train_step(self.i_rot, self.state, self.w_pivot)
-            self.i_rot += 1
+            res, _ = self.coach.train_step(idx, self.state, self.w_pivot)
         if e2e:
             return float(res)          # device -> host read of the step's loss
         return res
 
 
 def schedule(k):
-    n_mir = k // 3
+    """K optimiser iterations in the 500 : 1000 stage proportion of configs[1]: round(K/3) `mir` projector iterations, the rest
+    RotBbox iterations with consecutive loop indices i (so `i % 4 == 0` selects the heavy iteration exactly as
+    rot_bbox_cx_coach.py:68-151 does); the first index is chosen so that the heavy share is round(n_rot / 4), the closest a
+    K-step sample can get to the 250 : 750 split of the full stage.  Returns [('mir', step) | ('rot', i)]."""
+    k = max(1, int(k))
+    n_mir = int(round(k / 3.0)) if k >= 3 else 0
     n_rot = k - n_mir
-    return ['mir'] * n_mir + ['rot'] * n_rot
+    want = int(round(n_rot / 4.0))
+    start = 0
+    for s0 in (0, 1, 2, 3):
+        if sum(1 for i in range(s0, s0 + n_rot) if i % 4 == 0) == want:
+            start = s0
+            break
+    return [('mir', j) for j in range(n_mir)] + [('rot', i) for i in range(start, start + n_rot)]
+
+
+def mix_of(sched):
+    n_mir = sum(1 for kind, _ in sched if kind == 'mir')
+    heavy = sum(1 for kind, i in sched if kind == 'rot' and i % 4 == 0)
+    light = len(sched) - n_mir - heavy
+    return n_mir, heavy, light
+
+
+def mix_text(sched):
+    n_mir, heavy, light = mix_of(sched)
+    return f'{n_mir} mir + {heavy + light} RotBbox iterations ({heavy} with i%4==0: rot + mirror + depth branches, {light} plain)'
+
+
+def traffic_from_profiles(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/roofline_traffic.json records the metric,
+    the command and the .csv it was read from); None when no capture of the current kernel is committed."""
+    p = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+    if not os.path.exists(p):
+        return None, None
+    d = json.load(open(p)).get(kernel)
+    if not d:
+        return None, None
+    return d.get('dram_bytes_per_launch'), d.get('source')
 
 
 def run_ours(args):
@@ -266,13 +301,14 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device(device))
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))     # N ranks share the host cores
     _lib.load()
     data = synthetic_inputs(seed=4 + rank)       # one independent image per rank
     job = OursJob(device, data)
-    k, w = args.steps, args.warmup
-    assert k % 12 == 0, '--steps must be a multiple of 12 (1:2 stage mix, whole 4-iteration RotBbox cycles)'
+    k, w = max(1, args.steps), max(0, args.warmup)
     sched = schedule(k)
-    warm = ['mir'] * max(3, w // 3) + ['rot'] * max(4, (w - w // 3 + 3) // 4 * 4)
+    # warm-up: at least W iterations and at least one of every iteration kind (each kind is captured as a CUDA graph on first use)
+    warm = schedule(max(w, 3)) + [('mir', 0), ('mir', 1), ('mir', 2), ('rot', 0), ('rot', 1), ('rot', 2), ('rot', 3)]
 
     def barrier():
         if world > 1:
@@ -280,7 +316,6 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def timed(e2e):
-        job.i_rot = 0
         barrier()
         sampler = ClockSampler(local) if not e2e else None
         if sampler:
@@ -288,47 +323,52 @@ def run_ours(args):
         _lib.reset_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for kind in sched:
-            job.step(kind, e2e=e2e)
+        for item in sched:
+            job.step(item, e2e=e2e)
         e1.record()
         barrier()
-        launches = _lib.launch_count()
-        ms = e0.elapsed_time(e1)
+        ms_rank = e0.elapsed_time(e1)
         clocks = sampler.finish() if sampler else None
+        ms, per_rank = ms_rank, [ms_rank]
         if world > 1:
-            t = torch.tensor([ms], device=device)
-            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, clocks
+            t = torch.tensor([ms_rank], device=device)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            torch.distributed.all_gather(allt, t)
+            per_rank = [float(x.item()) for x in allt]
+            ms = max(per_rank)
+        return ms, per_rank, clocks
 
-    for kind in warm:
-        job.step(kind)
-    ms, launches, clocks = timed(e2e=False)
+    for item in warm:
+        job.step(item)
+    ms, per_rank, clocks = timed(e2e=False)
     value = world * k / (ms / 1e3)
-    # launches inside a replayed graph do not pass through the library's host entry points: count them from one eager pass
+    e2e = None
+    if not args.no_e2e:
+        job.step(('mir', 0), e2e=True)
+        ms2, per_rank2, _ = timed(e2e=True)
+        h2d = sum(v.numel() * v.element_size() for v in job.pinned.values())
+        e2e = {'value': world * k / (ms2 / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms2 / k,
+               'per_rank_it_s': [k / (m / 1e3) for m in per_rank2]}
+    # launches inside a replayed graph do not pass through the library's host entry points: count them from one eager pass of
+    # the same K steps, which also times the tagged kernels with CUDA events on the launching stream
     from spi_b200.configs import global_config
     global_config.use_cuda_graphs = False
     timer = KernelTimer()
     R.KERNEL_TIMER = timer
     _lib.KERNEL_TIMER = timer
-    job.i_rot = 0
     torch.cuda.synchronize()
     _lib.reset_launch_count()
-    for kind in sched:
-        job.step(kind)
+    ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ee0.record()
+    for item in sched:
+        job.step(item)
+    ee1.record()
     torch.cuda.synchronize()
+    eager_ms = ee0.elapsed_time(ee1)
     launches = _lib.launch_count()
     R.KERNEL_TIMER = None
     _lib.KERNEL_TIMER = None
     global_config.use_cuda_graphs = True
-    e2e = None
-    if not args.no_e2e:
-        job.step('mir', e2e=True)
-        ms2, _, _ = timed(e2e=True)
-        h2d = sum(v.numel() * v.element_size() for v in job.pinned.values())
-        e2e = {'value': world * k / (ms2 / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms2 / k}
-    # roofline of the dominant hand-written kernel (fused render backward; the forward beside it), timed with CUDA events on the
-    # launching stream in an eager pass of the same K steps
     peak, peak_src = measured_peaks()
     rf, rb = timer.summary('render_fwd'), timer.summary('render_bwd')
     roofline = None
@@ -337,47 +377,61 @@ def run_ours(args):
         ach = bytes_per_img / (rb['ms_per_unit'] * 1e-3) / 1e9
         tf32_peak = bf16_peak() / 2.0
         gf_bwd, gf_fwd = render_gflop(*DEPTH)
-        roofline = {'kernel': 'tcb::render_bwd_tc_kernel (spi_b200/csrc/raymarch_tc_bwd.cuh)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                    'frac': ach / peak, 'traffic': 38.7e6, 'traffic_source': 'ncu --set full, N=1 launch: dram read 38.7 MB + write 0.008 MB (profiles/r1_prof_render_bwd_tc.csv); plane gradients stay L2-resident',
+        tr_b, tr_b_src = traffic_from_profiles('render_bwd')
+        tr_f, tr_f_src = traffic_from_profiles('render_fwd')
+        roofline = {'kernel': 'render backward (spi_render_backward*, spi_b200/csrc/raymarch_tc_bwd.cuh)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                    'frac': ach / peak, 'traffic': tr_b, 'traffic_source': tr_b_src,
                     'peak_source': peak_src, 'algorithmic_bytes_per_image': bytes_per_img,
                     'ms_per_image': rb['ms_per_unit'], 'launches_timed': rb['launches'],
+                    'share_of_eager_step_time': rb['ms_total'] / eager_ms,
                     'tensor_view': {'tf32_tflops_3x_issued': 3 * gf_bwd / rb['ms_per_unit'], 'fp32_equivalent_tflops': gf_bwd / rb['ms_per_unit'],
                                     'tf32_peak_tflops': tf32_peak, 'frac_3x_issued': 3 * gf_bwd / rb['ms_per_unit'] / tf32_peak,
                                     'note': 'decoder GEMMs (fwd recompute + dH + dF) = %.1f GF/img, issued 3x as TF32 (hi*hi + lo*hi + hi*lo); peak = measured bf16 / 2' % gf_bwd},
-                    'note': 'arithmetic intensity ~340 FLOP/B and 12 x 128-byte texel lines gathered AND scattered per sample (3.2 GB of L2 traffic per image): '
+                    'note': 'arithmetic intensity ~340 FLOP/B and 12 x 128-byte texel lines gathered AND scattered per sample: '
                             'the kernel is L2-gather / issue bound, the HBM fraction is reported because the contract asks for it'}
         if rf:
             fb = render_fwd_bytes(*DEPTH)
-            roofline['render_fwd_tc_kernel'] = {'ms_per_image': rf['ms_per_unit'], 'achieved_GBps': fb / (rf['ms_per_unit'] * 1e-3) / 1e9,
-                                                'frac_of_hbm_peak': fb / (rf['ms_per_unit'] * 1e-3) / 1e9 / peak, 'algorithmic_bytes_per_image': fb,
-                                                'traffic': 20.6e6, 'tf32_tflops_3x_issued': 3 * gf_fwd / rf['ms_per_unit'],
-                                                'frac_3x_issued_of_tf32_peak': 3 * gf_fwd / rf['ms_per_unit'] / tf32_peak, 'launches_timed': rf['launches']}
-    # streaming kernels of this library, same eager pass: achieved GB/s = bytes the call must move / CUDA-event time
+            roofline['render_fwd'] = {'ms_per_image': rf['ms_per_unit'], 'achieved_GBps': fb / (rf['ms_per_unit'] * 1e-3) / 1e9,
+                                      'frac_of_hbm_peak': fb / (rf['ms_per_unit'] * 1e-3) / 1e9 / peak, 'algorithmic_bytes_per_image': fb,
+                                      'traffic': tr_f, 'traffic_source': tr_f_src, 'tf32_tflops_3x_issued': 3 * gf_fwd / rf['ms_per_unit'],
+                                      'frac_3x_issued_of_tf32_peak': 3 * gf_fwd / rf['ms_per_unit'] / tf32_peak, 'launches_timed': rf['launches'],
+                                      'share_of_eager_step_time': rf['ms_total'] / eager_ms}
+    # streaming / tensor kernels of this library, same eager pass: achieved = bytes (flops) the call must move / CUDA-event time
     streaming = {}
-    for tag in ('bias_act', 'upfirdn2d', 'adam'):
+    for tag in ('bias_act', 'upfirdn2d', 'adam', 'warp'):
         sm = timer.summary(tag)
         if sm:
             gbs = sm['units'] / (sm['ms_total'] * 1e-3) / 1e9
-            streaming[tag] = {'launches': sm['launches'], 'achieved_GBps': gbs, 'frac_of_hbm_peak': gbs / peak, 'ms_total': sm['ms_total']}
+            streaming[tag] = {'launches': sm['launches'], 'achieved_GBps': gbs, 'frac_of_hbm_peak': gbs / peak, 'ms_total': sm['ms_total'],
+                              'share_of_eager_step_time': sm['ms_total'] / eager_ms}
+    cv = timer.summary('conv')
+    conv = None
+    if cv:
+        tfs = cv['units'] / (cv['ms_total'] * 1e-3) / 1e12
+        conv = {'launches': cv['launches'], 'achieved_TFLOPs': tfs, 'tf32_peak_tflops': bf16_peak() / 2.0, 'frac_of_tf32_peak': tfs / (bf16_peak() / 2.0),
+                'ms_total': cv['ms_total'], 'share_of_eager_step_time': cv['ms_total'] / eager_ms}
     if roofline is not None:
         roofline['streaming_kernels'] = streaming
+        roofline['conv_engine'] = conv
         dg = timer.summary('render_dec_grads')
         roofline['decoder_grad_gemms_ms_per_image_eager'] = dg['ms_per_unit'] if dg else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(job, budget_s=min(args.cpu_budget_s, 60.0), heavy=False)
+        cpu = cpu_baseline(job, sched)
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': k, 'warmup': len(warm), 'ms_per_step': ms / k,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (TF32 tensor-core contractions)',
                 'data': 'synthetic', 'impl': 'ours',
                 'config': {'workload': 'configs[1]: single 512^2 image per GPU, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
-                           'execution': 'each iteration replayed as a captured CUDA graph; roofline kernel timed with CUDA events in an eager pass of the same K steps',
-                           'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': f'{k // 3} mir + {k - k // 3} RotBbox iterations',
+                           'execution': 'each iteration replayed as a captured CUDA graph; roofline kernels timed with CUDA events in an eager pass of the same K steps',
+                           'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': mix_text(sched),
                            'dedup': 'views of one iteration share w_pivot: the camera-independent tri-plane backbone is evaluated once per iteration and the SR net is skipped for the depth-only views (identical results, tests/test_gpu_loop.py::test_shared_backbone_equals_per_view_evaluation); global_config.share_backbone=False restores the literal structure',
                            'l2_policy': 'per-step working set (weights + activations, > 1 GB) exceeds the 126 MB L2', 'images_per_gpu': 1},
+                'per_rank_it_s': [k / (m / 1e3) for m in per_rank],
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 
 
@@ -411,68 +465,82 @@ def oracle_job(job_or_none, rank=0):
     return OL, sd, nets, rk, data
 
 
-def cpu_baseline(job, budget_s, heavy):
-    """The oracle (CPU restatement of the reference, kind='port') timed on the host cores on a bounded sample."""
+def cpu_baseline(job, sched):
+    """The oracle (CPU restatement of the reference, kind='port') on the host cores: ONE iteration of each kind of the timed
+    schedule (mir, RotBbox i%4==0, RotBbox plain) is timed and the three are weighted by the schedule's own mix, so the figure is
+    the same workload `value` measures (and the one `--impl reference` runs in full)."""
     torch.set_num_threads(os.cpu_count() or 1)
     OL, sd, nets, rk, data = oracle_job(job)
     w = torch.randn(1, 14, 512, generator=torch.Generator().manual_seed(5)) * 0.5
     coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind='RotBbox', rk=rk, noise=OL.NoiseSource(0))
-    t0 = time.perf_counter()
-    n = 0
-    i = 1                          # i % 4 != 0: main branch only (the light iteration)
-    while True:
-        coach.step(i)
-        n += 1
-        i += 1
-        if i % 4 == 0:
-            i += 1
-        if time.perf_counter() - t0 > budget_s / 3 or n >= 3:
-            break
-    dt = time.perf_counter() - t0
-    return {'value': n / dt, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f'{n} RotBbox G-stage iteration(s) with i%4!=0 (main L2+LPIPS branch only; the i%4==0 iteration is ~10x heavier '
-                      f'and is timed by --impl reference), depth 32+32, oracle/loops.py on torch CPU fp32'}
+    proj = OL.Projector(sd, data['img'], data['c'], nets, kind='mir', num_steps=500, rk=rk, noise=OL.NoiseSource(1), w_avg_samples=600)
+    n_mir, heavy, light = mix_of(sched)
+    t = {}
+    t0 = time.perf_counter(); coach.step(1); t['light'] = time.perf_counter() - t0
+    t0 = time.perf_counter(); proj.step(25); t['mir'] = time.perf_counter() - t0
+    t0 = time.perf_counter(); coach.step(4); t['heavy'] = time.perf_counter() - t0
+    total = n_mir * t['mir'] + heavy * t['heavy'] + light * t['light']
+    return {'value': len(sched) / total, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': f"one iteration of each kind timed once (mir {t['mir']:.2f} s, RotBbox i%4==0 {t['heavy']:.2f} s, RotBbox plain {t['light']:.2f} s), "
+                      f'weighted by the timed schedule ({mix_text(sched)}); depth 32+32, oracle/loops.py on torch CPU fp32'}
+
+
+def interleave(sched):
+    """The same multiset of iterations ordered so that every prefix keeps the mix (the CPU arm may be cut by its wall budget)."""
+    groups = {'mir': [s for s in sched if s[0] == 'mir'], 'heavy': [s for s in sched if s[0] == 'rot' and s[1] % 4 == 0],
+              'light': [s for s in sched if s[0] == 'rot' and s[1] % 4 != 0]}
+    total = {g: len(v) for g, v in groups.items()}
+    out, done = [], {g: 0 for g in groups}
+    for n in range(1, len(sched) + 1):
+        g = max((g for g in groups if done[g] < total[g]), key=lambda g: (total[g] * n / len(sched) - done[g], g == 'heavy'))
+        out.append(groups[g][done[g]])
+        done[g] += 1
+    return out
 
 
 def run_reference(args):
-    """`--impl reference`: the reference algorithm on the host CPU (oracle port; the reference itself is Python and cannot
-    travel to the GPU box).  Steps are time-bounded: 1 warm-up + up to K iterations following the same stage mix, stopped
-    once the wall budget is spent (always at least one full 4-iteration RotBbox cycle is attempted first)."""
+    """`--impl reference`: the reference algorithm on the host CPU with every host thread (oracle port; the reference itself is
+    Python and cannot travel to the GPU box).  Runs W warm-up iterations (plain ones) and then the SAME K-iteration schedule as
+    the GPU arm; a wall budget (--cpu-budget-s) can cut the run short, in which case `steps` and `step_mix` report what ran."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
     OL, sd, nets, rk, data = oracle_job(None)
     t_all = time.perf_counter()
-    proj = OL.Projector(sd, data['img'], data['c'], nets, kind='mir', num_steps=500, rk=rk, noise=OL.NoiseSource(1))
+    proj = OL.Projector(sd, data['img'], data['c'], nets, kind='mir', num_steps=500, rk=rk, noise=OL.NoiseSource(1), w_avg_samples=600)
     w = proj.result().clone()
     coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind='RotBbox', rk=rk, noise=OL.NoiseSource(2))
-    coach.step(1)                                   # warm-up (light iteration)
+    n_warm = max(0, args.warmup)
+    for j in range(n_warm):                         # warm-up: plain iterations (allocator, thread pool, oneDNN primitive caches)
+        if j % 3 == 0:
+            proj.step(j)
+        else:
+            coach.step(4 * j + 1)
+    sched = interleave(schedule(max(1, args.steps)))
     budget = args.cpu_budget_s
     t0 = time.perf_counter()
-    done = {'mir': 0, 'rot': 0}
-    # one whole RotBbox cycle first (i = 0 heavy + 3 light), then mir steps in the 1:2 proportion, budget permitting
-    for i in range(4):
-        coach.step(i)
-        done['rot'] += 1
+    ran = []
+    for kind, idx in sched:
+        if kind == 'mir':
+            proj.step(25 + idx)
+        else:
+            coach.step(idx)
+        ran.append((kind, idx))
         if time.perf_counter() - t0 > budget:
             break
-    while done['mir'] < max(1, done['rot'] // 2) and time.perf_counter() - t0 < budget:
-        proj.step(done['mir'] + 25)
-        done['mir'] += 1
     dt = time.perf_counter() - t0
-    n = done['mir'] + done['rot']
+    n = len(ran)
     value = n / dt
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': 1, 'ms_per_step': dt / n * 1e3,
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': n_warm, 'ms_per_step': dt / n * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
             'config': {'workload': 'configs[1]: single 512^2 image, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
-                       'depth_samples': '32+32', 'neural_rendering_resolution': 128,
-                       'step_mix': f"{done['mir']} mir + {done['rot']} RotBbox iterations (time-bounded sample)"},
+                       'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': mix_text(ran),
+                       'truncated_by_budget': n < len(sched)},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': f"{done['rot']} RotBbox iterations (i=0..{done['rot'] - 1}, one heavy i%4==0) + {done['mir']} mir iterations, "
-                                       f'{dt:.1f} s wall, setup {t0 - t_all:.1f} s excluded'},
+                             'sample': f'{mix_text(ran)}, {dt:.1f} s wall, setup + {n_warm} warm-up iterations ({t0 - t_all:.1f} s) excluded'},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == '__main__':

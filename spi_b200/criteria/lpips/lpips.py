@@ -51,6 +51,12 @@ class LPIPS(nn.Module):
             self._cache[id(y)] = (y, None, None, None)
         return y
 
+    def release_targets(self):
+        """Drop every registered target with its cached taps (and the retired ones).  Call only when no captured graph that
+        reads them will be replayed again -- the coaches do so when they start a new image and drop that image's graphs."""
+        self._cache.clear()
+        self._retired.clear()
+
     def _target_feats(self, y, resize):
         if y.requires_grad:
             return self.net(self._resize(y) if resize else y)

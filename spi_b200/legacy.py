@@ -7,8 +7,8 @@ module's `__dict__` (`_parameters`, `_buffers`, `_modules`, `_init_args`, `_init
 `module_src` (persistence.py:181-205, :218-230).  Here a restricted unpickler turns every persistent object into an inert
 `PersistentStub(class_name, state)`; a `TriPlaneGenerator` stub is then rebuilt as THIS repo's generator from its constructor
 arguments and its parameters / buffers collected by name (`require_all=True`, as load_utils.py:26).  Classes that are not on the
-inversion path (the discriminator, the augmentation pipe) stay stubs.  Nothing outside torch / numpy / collections / builtins
-containers is ever imported on behalf of the file, and no code from the file runs.
+inversion path (the discriminator, the augmentation pipe) stay stubs.  Globals are resolved from an explicit allowlist of exact (module, name) pairs (tensor rebuild functions, storages, dtypes,
+OrderedDict, a few parameter-free nn containers); nothing else is imported on behalf of the file and no code from it runs.
 """
 import collections
 import copy
@@ -21,6 +21,35 @@ from . import dnnlib
 
 _SAFE_BUILTINS = {'set', 'frozenset', 'slice', 'complex', 'range', 'dict', 'list', 'tuple', 'int', 'float', 'bool', 'str', 'bytes', 'bytearray',
                   'object'}
+
+
+# Exact (module, name) pairs a network pickle needs for tensors and containers.  Everything else under torch.* / numpy.* is
+# refused: those packages are full of callables that run commands or unpickle again (torch.utils.collect_env.run, torch.load,
+# torch.hub.*, numpy.load, numpy.testing.*), so "any global below the torch root" is not a safe rule.
+_ALLOWED_GLOBALS = {
+    ('collections', 'OrderedDict'),
+    ('copyreg', '_reconstructor'),
+    ('_codecs', 'encode'),
+    ('numpy', 'dtype'), ('numpy', 'ndarray'),
+    ('numpy.core.multiarray', '_reconstruct'), ('numpy.core.multiarray', 'scalar'),
+    ('numpy._core.multiarray', '_reconstruct'), ('numpy._core.multiarray', 'scalar'),
+    ('torch._utils', '_rebuild_tensor'), ('torch._utils', '_rebuild_tensor_v2'),
+    ('torch._utils', '_rebuild_parameter'), ('torch._utils', '_rebuild_parameter_with_state'),
+    ('torch.nn.parameter', 'Parameter'),
+    ('torch.nn.modules.container', 'Sequential'), ('torch.nn.modules.container', 'ModuleList'), ('torch.nn.modules.container', 'ModuleDict'),
+    ('torch.nn.modules.activation', 'Softplus'), ('torch.nn.modules.activation', 'LeakyReLU'), ('torch.nn.modules.activation', 'ReLU'),
+    ('torch.nn.modules.linear', 'Identity'),
+}
+_TORCH_NAMES = {'Size', 'device', 'FloatStorage', 'HalfStorage', 'DoubleStorage', 'BFloat16Storage', 'LongStorage', 'IntStorage', 'ShortStorage',
+                'CharStorage', 'ByteStorage', 'BoolStorage', 'float32', 'float16', 'float64', 'bfloat16', 'int64', 'int32', 'int16', 'int8',
+                'uint8', 'bool'}
+
+
+def _load_storage_from_bytes(b):
+    """Stand-in for torch.storage._load_from_bytes (plain-pickled storages): the original calls torch.load(weights_only=False) on
+    bytes taken from the file, i.e. a second, unrestricted unpickle; this one only accepts tensor data."""
+    import io
+    return torch.load(io.BytesIO(b), weights_only=True)
 
 
 class PersistentStub:
@@ -81,9 +110,11 @@ class _SafeUnpickler(pickle.Unpickler):
             return dnnlib.EasyDict
         if module == 'dnnlib.tflib.network':
             raise pickle.UnpicklingError('legacy TensorFlow pickles are not supported (no EG3D checkpoint uses them)')
-        root = module.split('.')[0]
-        if root in ('torch', 'numpy', 'collections', 'copyreg', '_codecs') or (module == 'builtins' and name in _SAFE_BUILTINS):
+        if (module, name) == ('torch.storage', '_load_from_bytes'):
+            return _load_storage_from_bytes
+        if (module, name) in _ALLOWED_GLOBALS or (module == 'torch' and name in _TORCH_NAMES) or (module == 'builtins' and name in _SAFE_BUILTINS):
             return super().find_class(module, name)
+        root = module.split('.')[0]
         if root in ('training', 'torch_utils', 'dnnlib'):
             return _class_stub(module, name)
         raise pickle.UnpicklingError(f'refusing to import {module}.{name} while reading a network pickle')

@@ -84,16 +84,16 @@ class FlatAdam:
     def use_device_hyper(self):
         """Keep {lr, 1-b1^t, 1-b2^t} in a device tensor refreshed by `advance()` so that `step()` can live inside a CUDA graph."""
         self.hyper = torch.zeros(3, device=self.arena.device)
-        self._hyper_host = torch.zeros(3).pin_memory()
 
     def advance(self):
         """Host side of a graphed step: bump the step counter and upload the scalars the captured kernel reads."""
         self.steps += 1
         g = self.param_groups[0]
-        self._hyper_host[0] = float(g['lr'])
-        self._hyper_host[1] = 1.0 - g['betas'][0] ** self.steps
-        self._hyper_host[2] = 1.0 - g['betas'][1] ** self.steps
-        self.hyper.copy_(self._hyper_host, non_blocking=True)
+        # fill_ passes the value as a kernel argument fixed at enqueue time.  (An async copy from ONE reused pinned buffer reads
+        # the buffer when the copy executes: the host, running hundreds of graph replays ahead, would have overwritten it.)
+        self.hyper[0:1].fill_(float(g['lr']))
+        self.hyper[1:2].fill_(1.0 - g['betas'][0] ** self.steps)
+        self.hyper[2:3].fill_(1.0 - g['betas'][1] ** self.steps)
 
     @torch.no_grad()
     def step(self, in_graph=False):
@@ -131,21 +131,37 @@ class FlatAdam:
         if not rows:
             return
         capturing = torch.cuda.is_current_stream_capturing()
-        if capturing or self._eager_table is None:
+        new_pair = lambda: (torch.empty(self._max_rows, 5, dtype=torch.int64).pin_memory(),
+                            torch.empty(self._max_rows, 5, dtype=torch.int64, device=self.arena.device))
+        if capturing:
             # a captured graph re-uploads ITS table on every replay: it must own the pinned buffer (eager steps in between
             # would otherwise overwrite the pointers the graph was captured with)
-            pair = (torch.empty(self._max_rows, 5, dtype=torch.int64).pin_memory(), torch.empty(self._max_rows, 5, dtype=torch.int64, device=self.arena.device))
-            if capturing:
-                self._tables.append(pair)
-            else:
-                self._eager_table = pair
+            host, dev = new_pair()
+            self._tables.append((host, dev))
+            host[:len(rows)] = torch.tensor(rows, dtype=torch.int64)
+            dev.copy_(host, non_blocking=True)
         else:
-            pair = self._eager_table
-        host, dev = pair
-        host[:len(rows)] = torch.tensor(rows, dtype=torch.int64)
-        dev.copy_(host, non_blocking=True)
+            # eager: a ring of pinned slots, each guarded by an event recorded after the kernel that read its device table, so
+            # a slot is never rewritten while its upload (or the step reading it) is still in flight
+            if self._eager_table is None:
+                self._eager_table = {'slots': [], 'next': 0}
+            ring = self._eager_table
+            if len(ring['slots']) < 4:
+                ring['slots'].append([*new_pair(), None])
+                slot = ring['slots'][-1]
+            else:
+                slot = ring['slots'][ring['next'] % 4]
+                ring['next'] += 1
+                if slot[2] is not None:
+                    slot[2].synchronize()
+            host, dev = slot[0], slot[1]
+            host[:len(rows)] = torch.tensor(rows, dtype=torch.int64)
+            dev.copy_(host, non_blocking=True)
         nbytes = sum(r[4] for r in rows) * 28
         with _lib.timed('adam', nbytes):
             _lib.check(_lib.load().spi_adam_step_multi(_lib.ptr(dev), len(rows), 1, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]), float(g['eps']),
                                                        max(self.steps, 1), _lib.ptr(self.hyper) if self.hyper is not None else None,
                                                        _lib.ptr(cond) if cond is not None else None, float(thr), _lib.stream()))
+        if not capturing:
+            slot[2] = torch.cuda.Event()
+            slot[2].record()

@@ -52,7 +52,15 @@ class BaseCoach:
         return self._metric
 
     def restart_training(self):
-        """base_coach.py:53-60: fresh G and original_G per image, new optimiser, then fix_seed()."""
+        """base_coach.py:53-60: fresh G and original_G per image, new optimiser, then fix_seed().  Everything keyed to the
+        previous image is dropped first: its captured iteration graphs (each owns a private memory pool of several GB and can
+        never be replayed against the new G), the cached tri-planes of the old original_G, and the LPIPS taps of its targets."""
+        self._graphs = {}
+        self._stable_key = None
+        self._registered = None
+        self.G = self.original_G = self.optimizer = None
+        if hasattr(getattr(self, 'lpips_loss', None), 'release_targets'):
+            self.lpips_loss.release_targets()
         self.G = load_utils.load_eg3d()
         toogle_grad(self.G, True)
         self.original_G = load_utils.load_eg3d()

@@ -63,7 +63,6 @@ class LatentProjector:
         self.optimizer = FlatAdam([self.w_opt] + list(self.noise_bufs.values()), betas=(0.9, 0.999), lr=initial_learning_rate, steal_grads=True)
         self.optimizer.use_device_hyper()
         self.w_noise_scale = torch.zeros((), device=device)          # per-step scalar, read on device (graph replay)
-        self._scale_host = torch.zeros(()).pin_memory()
         self._graph = None
         self._out = dict(loss=torch.zeros((), device=device), dist=torch.zeros((), device=device), image=None)
         self.target, self.c = target, c
@@ -126,8 +125,7 @@ class LatentProjector:
         lr, w_noise_scale = self.schedule(step)
         for g in self.optimizer.param_groups:
             g['lr'] = lr
-        self._scale_host.fill_(float(w_noise_scale))
-        self.w_noise_scale.copy_(self._scale_host, non_blocking=True)
+        self.w_noise_scale.fill_(float(w_noise_scale))        # value travels as a kernel argument (no reused pinned buffer in flight)
         self.optimizer._reseat()
         self.optimizer.advance()
         eager = (not global_config.use_cuda_graphs) or rng.pending() or bool(self.G.renderer._noise_queue)

@@ -32,15 +32,22 @@ DEPTH_OVERRIDE = None   # (depth_resolution, depth_resolution_importance) forced
 _template = {}      # network_pkl -> (init_kwargs, cpu state dict): unpickle / initialise once, clone per restart_training()
 
 
-def build_generator(init_kwargs=None, state_dict=None, device=None, seed=None):
+def build_generator(init_kwargs=None, state_dict=None, device=None, seed=None, rendering_kwargs=None):
+    """`rendering_kwargs`: the pickled ATTRIBUTE of the source generator; the reference assigns it over the constructor's copy
+    after re-instantiating (`G_new.rendering_kwargs = G.rendering_kwargs`, load_utils.py:27-28), so a pickle re-saved with a changed
+    depth_resolution / ray_start / box_warp renders with the changed values."""
     kw = copy.deepcopy(init_kwargs or FFHQ512_KWARGS)
-    if DEPTH_OVERRIDE is not None:
-        kw['rendering_kwargs']['depth_resolution'], kw['rendering_kwargs']['depth_resolution_importance'] = DEPTH_OVERRIDE
+    rk = copy.deepcopy(dict(rendering_kwargs)) if rendering_kwargs is not None else None
+    for d in (kw['rendering_kwargs'], rk):
+        if DEPTH_OVERRIDE is not None and d is not None:
+            d['depth_resolution'], d['depth_resolution_importance'] = DEPTH_OVERRIDE
     if seed is not None:
         torch.manual_seed(seed)
     G = TriPlaneGenerator(**kw).eval().requires_grad_(False)
     if state_dict is not None:
         G.load_state_dict(state_dict, strict=True)
+    if rk is not None:
+        G.rendering_kwargs = rk
     G.neural_rendering_resolution = 128
     return G.to(device or global_config.device)
 
@@ -53,19 +60,19 @@ def load_eg3d(reload_modules=True, device=None, network_pkl=None):
         if network_pkl.startswith('synthetic'):
             seed = int(network_pkl.split(':')[1]) if ':' in network_pkl else 0
             G = build_generator(device='cpu', seed=seed)
-            _template[network_pkl] = (copy.deepcopy(FFHQ512_KWARGS), {k: v.clone() for k, v in G.state_dict().items()})
+            _template[network_pkl] = (copy.deepcopy(FFHQ512_KWARGS), {k: v.clone() for k, v in G.state_dict().items()}, None)
         elif network_pkl.endswith('.pt'):
             blob = torch.load(network_pkl, map_location='cpu')
-            _template[network_pkl] = (blob.get('init_kwargs', FFHQ512_KWARGS), blob['G'])
+            _template[network_pkl] = (blob.get('init_kwargs', FFHQ512_KWARGS), blob['G'], blob.get('rendering_kwargs'))
         else:
             from .. import legacy                 # source-carrying pickle (eg3d/legacy.py:23) read without executing its source
             with open(network_pkl, 'rb') as f:
                 G = legacy.load_network_pkl(f)['G_ema']
             kw = dict(G.init_kwargs)
             assert not G.init_args, 'TriPlaneGenerator pickles carry keyword arguments only'
-            _template[network_pkl] = (kw, {k: v.clone() for k, v in G.state_dict().items()})
-    kw, sd = _template[network_pkl]
-    return build_generator(kw, sd, device=device)
+            _template[network_pkl] = (kw, {k: v.clone() for k, v in G.state_dict().items()}, copy.deepcopy(dict(G.rendering_kwargs)))
+    kw, sd, rk = _template[network_pkl]
+    return build_generator(kw, sd, device=device, rendering_kwargs=rk)
 
 
 def load_sg_vgg(device=None):

@@ -55,6 +55,13 @@ def test_load_eg3d_accepts_a_pkl_path(tmp_path):
     G = load_utils.load_eg3d(device='cpu', network_pkl=str(p))
     assert G.neural_rendering_resolution == 128 and G.w_dim == 512 and G.z_dim == 64
     G2 = load_utils.load_eg3d(device='cpu', network_pkl=str(p))                 # restart_training(): a fresh copy from the cached template
+    # load_utils.py:27-28: the pickled rendering_kwargs ATTRIBUTE wins over the constructor's copy
+    kw, sd, rk = load_utils._template[str(p)]
+    rk2 = dict(rk, ray_start=2.0, box_warp=1.5)
+    load_utils._template['edited'] = (kw, sd, rk2)
+    G3 = load_utils.load_eg3d(device='cpu', network_pkl='edited')
+    assert G3.rendering_kwargs['ray_start'] == 2.0 and G3.rendering_kwargs['box_warp'] == 1.5 and G3.init_kwargs['rendering_kwargs']['ray_start'] != 2.0
+    del load_utils._template['edited']
     assert G2 is not G and all(torch.equal(a, b) for a, b in zip(G.state_dict().values(), G2.state_dict().values()))
 
 
@@ -72,6 +79,14 @@ def test_embedded_source_is_never_executed_and_foreign_classes_are_refused():
     payload = (b'\x80\x04' + b'ctorch_utils.persistence\n_reconstruct_persistent_obj\n' + pickle.dumps((meta,))[2:-1] + b'R.')
     obj = legacy._SafeUnpickler(io.BytesIO(payload)).load()
     assert isinstance(obj, legacy.PersistentStub) and obj.class_name == 'Whatever'
+    # gadgets that live UNDER the torch / numpy roots are refused too (explicit allowlist, not a root-package test)
+    for payload in (b"ctorch.utils.collect_env\nrun\n(S'echo pwned > /tmp/spi_b200_pwned'\ntR.",
+                    b"ctorch.serialization\nload\n(S'/etc/hostname'\ntR.",
+                    b"cnumpy\nload\n(S'/etc/hostname'\ntR.",
+                    b"ctorch.hub\nload\n(S'x'\nS'y'\ntR."):
+        with pytest.raises(pickle.UnpicklingError):
+            legacy._SafeUnpickler(io.BytesIO(payload)).load()
+    assert not os.path.exists('/tmp/spi_b200_pwned')
 
 
 @pytest.mark.gpu
