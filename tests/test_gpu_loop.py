@@ -276,3 +276,103 @@ def test_shared_backbone_equals_per_view_evaluation(gen_sd, lpips_mod, cx_mod):
     assert abs(lps[0] / lps[1] - 1) < 1e-4
     assert rel_l2(grads[0][0], grads[1][0]) < 2e-2          # TF32 contractions, different summation order
     assert rel_l2(grads[0][1], grads[1][1]) < 2e-2
+
+
+def _opt_state(coach):
+    o = coach.optimizer
+    return (o.arena.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone(), o.steps)
+
+
+def _restore(coach, state):
+    o = coach.optimizer
+    with torch.no_grad():
+        o.arena.copy_(state[0]); o.exp_avg.copy_(state[1]); o.exp_avg_sq.copy_(state[2])
+    o.steps = state[3]
+
+
+def test_graph_replay_of_rotbbox_iterations_equals_the_eager_body(gen_sd, lpips_mod, cx_mod):
+    """The path bench.py times: the RotBbox heavy (i%4==0) and plain iterations replayed as captured CUDA graphs must compute what
+    the eager body computes from the same device-RNG state -- same gradients, same parameters after two consecutive iterations.
+    (A stale pointer or a capture-order bug in the graphed body would pass every eager test.)"""
+    from spi_b200.configs import global_config, hyperparameters as hp
+    from spi_b200.training.coaches.rot_bbox_cx_coach import SPIState
+    hp.pt_rot_lambda, hp.pt_mirror_rot_lambda, hp.pt_depth_lambda, hp.pt_tv_lambda = 0.1, 0.05, 1.0, 0.0
+    hp.LPIPS_value_threshold = -1.0
+    image, camera = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
+    mask, lm = weights.parsing_mask().cuda(), weights.landmarks68().cuda()
+    results = {}
+    try:
+        for mode in ('eager', 'graph'):
+            global_config.use_cuda_graphs = (mode == 'graph')
+            coach = make_coach('RotBbox', gen_sd, lpips_mod, cx_mod)
+            st = SPIState(image, camera, mask, lm)
+            assert st.mirror_on
+            w = weights.w_pivot(5).cuda().requires_grad_(True)
+            s0 = _opt_state(coach)
+            if mode == 'graph':          # first use captures (warm-up iterations consume RNG and move the state): capture, then rewind
+                coach.train_step(0, st, w)
+                coach.train_step(1, st, w)
+                assert len(coach._graphs) == 2
+                _restore(coach, s0)
+            torch.cuda.manual_seed(1234)
+            out = []
+            for i in (0, 1, 4, 5):       # heavy, plain, heavy (second replay of the same graph), plain
+                lp, stepped = coach.train_step(i, st, w)
+                assert stepped
+                out.append((float(lp), coach.optimizer.flat_grads().clone(), coach.optimizer.arena.clone()))
+            if mode == 'graph':
+                assert len(coach._graphs) == 2
+            results[mode] = out
+            coach._graphs = {}
+            del coach
+    finally:
+        global_config.use_cuda_graphs = True
+        hp.LPIPS_value_threshold = 0.05
+    for k, ((lp_e, g_e, a_e), (lp_g, g_g, a_g)) in enumerate(zip(results['eager'], results['graph'])):
+        eg, ea = rel_l2(g_g, g_e), rel_l2(a_g - results['eager'][0][2] + 0, a_e - results['eager'][0][2] + 0) if k else 0.0
+        print(f'iteration {k}: lpips eager {lp_e:.6f} graph {lp_g:.6f}  grad rel-L2 {eg:.2e}  param rel-L2 {rel_l2(a_g, a_e):.2e}')
+        assert abs(lp_g / lp_e - 1) < 1e-4
+        # float atomics (plane-gradient REDs, split-K reductions) reorder sums between runs: 1e-5 on the first iteration; later
+        # iterations start from parameters that already differ by that noise
+        assert eg < (1e-5 if k == 0 else 2e-3), (k, eg)
+        assert rel_l2(a_g, a_e) < 1e-5
+
+
+def test_graphed_projector_without_host_sync_follows_the_schedule(gen_sd, lpips_mod):
+    """50 graphed `mir` projector steps enqueued with NO host synchronisation must see, on the device, the lr / bias-correction /
+    w-noise scalars of their own step (round 1 refreshed them by async copies out of one reused pinned buffer: the host, running far
+    ahead of the device, overwrote them and step i used the scalars of step i+K).  Checked against an eager run that synchronises
+    every step, from the same device-RNG state."""
+    from spi_b200.configs import global_config
+    from spi_b200.training.projectors._common import LatentProjector
+    from spi_b200.utils import load_utils
+    target, c = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
+    n_steps, res = 50, {}
+    try:
+        for mode in ('eager', 'graph'):
+            global_config.use_cuda_graphs = (mode == 'graph')
+            G = load_utils.build_generator(state_dict=gen_sd, device='cuda')
+            torch.manual_seed(7)
+            torch.cuda.manual_seed(7)
+            p = LatentProjector(G, target, c, 'mir', lpips_func=lpips_mod, num_steps=n_steps, w_avg_samples=600)
+            o = p.optimizer
+            s0 = (o.arena.clone(), o.exp_avg.clone(), o.exp_avg_sq.clone())
+            if mode == 'graph':
+                p.step(0)            # capture
+                with torch.no_grad():
+                    o.arena.copy_(s0[0]); o.exp_avg.copy_(s0[1]); o.exp_avg_sq.copy_(s0[2])
+                o.steps = 0
+            torch.cuda.synchronize()
+            torch.cuda.manual_seed(99)
+            for i in range(n_steps):
+                p.step(i)
+                if mode == 'eager':
+                    torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            res[mode] = (p.w_opt.detach().clone(), float(p.last['dist']))
+            del p
+    finally:
+        global_config.use_cuda_graphs = True
+    d = rel_l2(res['graph'][0], res['eager'][0])
+    print('w_opt after 50 steps, graph (no sync) vs eager (sync every step): rel-L2', d, 'dist', res['graph'][1], res['eager'][1])
+    assert d < 2e-3 and abs(res['graph'][1] / res['eager'][1] - 1) < 2e-2
