@@ -193,6 +193,26 @@ int spi_tc_error(void);
 /* w [g][o][taps][i] -> wt [g][i][taps reversed][o]: weights of the data-gradient convolution (F.conv2d backward w.r.t. input). */
 int spi_conv_weight_flip_transpose(const float* w, float* wt, int g, int o, int taps, int i, cudaStream_t stream);
 
+/* ---- conv engine, second generation (spi_b200/csrc/conv_tc2.cu): halo-patch implicit GEMM on tcgen05 + TMEM + TMA ----------
+ * Replaces the cuDNN calls behind `_conv2d_wrapper` (eg3d/torch_utils/ops/conv2d_resample.py:30-43, :114-128) for the three
+ * convolution forms the generator, the super-resolution module and the VGG extractors issue, forward and data-gradient:
+ *   spi_conv2d_tc2               stride-1 'same' correlation, k = 1 or 3 (fused SynthesisLayer / bias_act epilogue as spi_conv2d_tc)
+ *   spi_conv_transpose2d_s2_tc2  stride-2 transposed 3x3 convolution, no padding: [n,h,w,ci] -> [n,2h+1,2w+1,co]
+ *                                (y[2iy+ky, 2ix+kx, o] += x[iy,ix,i] * w[g][o][ky*3+kx][i]; conv2d_resample.py:117)
+ *   spi_conv2d_s2_tc2            stride-2 3x3 correlation, no padding: [n,2h+1,2w+1,ci] -> [n,h,w,co] (data gradient of the former)
+ * All tensors channels-last fp32, w [g][co][taps][ci] with g = n when per_sample else 1; ci, co multiples of 32.
+ * flags bit 0: raw fp32 bits (truncation) instead of round-to-nearest TF32 on load.  Pipeline time-outs raise spi_tc_error(). */
+int spi_conv_tc2_supported(int ci, int co);
+int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int k, int per_sample,
+                   const float* bias, const float* noise, const float* noise_strength, int act, float slope, float gain, float clamp,
+                   int flags, cudaStream_t stream);
+int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
+                                cudaStream_t stream);
+int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
+                      cudaStream_t stream);
+/* w [g][o][taps][i] -> wt [g][i][taps'][o], taps' reversed when `reverse` (stride-1 data gradient) else kept (stride-2 forms). */
+int spi_conv_weight_transpose(const float* w, float* wt, int g, int o, int taps, int i, int reverse, cudaStream_t stream);
+
 /* ---- stage-1 noise-buffer regulariser + re-normalisation: spi/training/projectors/mirror_projector.py:107-115,128-131 (same loops
  *      in w_projector.py / w_plus_projector.py), all buffers in one launch each.
  * table: device array of `count` records {float* x; long long out_off; int size; int pad} describing square fp32 [size,size]

@@ -1,0 +1,245 @@
+"""Correctness + timing of the second-generation conv engine (spi_b200/csrc/conv_tc2.cu) against fp64 references and cuDNN TF32.
+Not a benchmark of the product path; run under gpurun:  python tools/bench_conv2.py [--probe] [--time]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import torch.nn.functional as F
+
+from spi_b200 import _lib
+
+L = _lib.load()
+CL = torch.channels_last
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+
+
+def conv_s1(x, w, per_sample, k, flags=0, bias=None, noise=None, strength=None, act=0, slope=0.2, gain=1.0, clamp=-1.0):
+    n, ci, h, wd = x.shape
+    co = w.shape[1]
+    y = torch.empty(n, co, h, wd, device=x.device, memory_format=CL)
+    _lib.check(L.spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), n, h, wd, ci, co, k, int(per_sample), _lib.ptr(bias), _lib.ptr(noise),
+                                _lib.ptr(strength), act, slope, gain, clamp, flags, _lib.stream()))
+    return y
+
+
+def conv_t2(x, w, per_sample, flags=0):
+    n, ci, h, wd = x.shape
+    co = w.shape[1]
+    y = torch.empty(n, co, 2 * h + 1, 2 * wd + 1, device=x.device, memory_format=CL)
+    _lib.check(L.spi_conv_transpose2d_s2_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), flags, _lib.stream()))
+    return y
+
+
+def conv_s2(x, w, per_sample, flags=0):
+    n, ci, hi, wi = x.shape
+    h, wd = (hi - 1) // 2, (wi - 1) // 2
+    co = w.shape[1]
+    y = torch.empty(n, co, h, wd, device=x.device, memory_format=CL)
+    _lib.check(L.spi_conv2d_s2_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), flags, _lib.stream()))
+    return y
+
+
+def time_ms(fn, iters=7, reps=10):
+    """Device time per call: `reps` back-to-back calls captured in one CUDA graph (no host launch / tensor-map encoding time between
+    them -- a single eager call of a 0.1 ms kernel is dominated by it), median over `iters` replays, L2 flushed before each replay."""
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+    ts = []
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / reps)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def make(n, ci, co, h, wd, k, per_sample, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, ci, h, wd, generator=g).cuda().contiguous(memory_format=CL)
+    G = n if per_sample else 1
+    w = (torch.randn(G, co, k * k, ci, generator=g) / (k * k * ci) ** 0.5).cuda()          # [G][O][taps][I]
+    w_oikk = w.view(G, co, k, k, ci).permute(0, 1, 4, 2, 3)                                  # logical [G,O,I,kh,kw]
+    return x, w, w_oikk
+
+
+def check_s1(n, ci, co, h, wd, k, per_sample, flags):
+    x, w, wl = make(n, ci, co, h, wd, k, per_sample)
+    y = conv_s1(x, w, per_sample, k, flags)
+    err = L.spi_tc_error()
+    ref = torch.cat([F.conv2d(x[i:i + 1].double(), wl[i if per_sample else 0].double(), padding=k // 2) for i in range(n)])
+    return rel(y, ref), err
+
+
+def check_t2(n, ci, co, h, wd, per_sample, flags):
+    x, w, wl = make(n, ci, co, h, wd, 3, per_sample)
+    y = conv_t2(x, w, per_sample, flags)
+    err = L.spi_tc_error()
+    # conv_transpose2d weight is [I, O, kh, kw] with y[o, 2iy+ky, 2ix+kx] += x[i, iy, ix] * W[i, o, ky, kx]
+    ref = torch.cat([F.conv_transpose2d(x[i:i + 1].double(), wl[i if per_sample else 0].double().permute(1, 0, 2, 3), stride=2) for i in range(n)])
+    return rel(y, ref), err
+
+
+def check_s2(n, ci, co, h, wd, per_sample, flags):
+    x, w, wl = make(n, ci, co, 2 * h + 1, 2 * wd + 1, 3, per_sample)
+    y = conv_s2(x, w, per_sample, flags)
+    err = L.spi_tc_error()
+    ref = torch.cat([F.conv2d(x[i:i + 1].double(), wl[i if per_sample else 0].double(), stride=2) for i in range(n)])
+    return rel(y, ref), err
+
+
+def probe():
+    print('== descriptor-semantics probe: flags 0 = base offset 0, flags 2 = base offset from the tap shift', flush=True)
+    for flags in (0, 2):
+        for case in ((1, 32, 32, 16, 16, 3, False), (1, 32, 32, 16, 16, 1, False), (2, 64, 128, 40, 56, 3, True), (1, 128, 96, 64, 64, 1, True),
+                     (3, 96, 320, 24, 16, 3, False), (1, 256, 256, 64, 64, 3, True), (1, 512, 512, 4, 4, 3, True), (1, 512, 512, 8, 8, 3, True),
+                     (1, 64, 64, 256, 256, 3, False), (1, 32, 256, 20, 8, 3, False)):
+            try:
+                e, err = check_s1(*case, flags)
+                print(f'  s1 flags={flags} {case}: rel-L2 {e:.2e} err-flag {err}', flush=True)
+            except Exception as ex:
+                print(f'  s1 flags={flags} {case}: EXC {ex}', flush=True)
+    for best in (0, 2):
+      for case in ((1, 32, 32, 16, 16, False), (2, 64, 128, 20, 28, True), (1, 512, 512, 4, 4, True), (1, 256, 128, 64, 64, False), (2, 32, 256, 33, 17, True)):
+        for name, fn in (('t2', check_t2), ('s2', check_s2)):
+            try:
+                e, err = fn(*case, best)
+                print(f'  {name} flags={best} {case}: rel-L2 {e:.2e} err-flag {err}', flush=True)
+            except Exception as ex:
+                print(f'  {name} flags={best} {case}: EXC {ex}', flush=True)
+    # fused epilogue
+    g = torch.Generator().manual_seed(7)
+    n, ci, co, h = 2, 64, 96, 40
+    x, w, wl = make(n, ci, co, h, h, 3, False, seed=7)
+    b, nz, st = torch.randn(co, generator=g).cuda(), torch.randn(h, h, generator=g).cuda(), torch.tensor(0.7).cuda()
+    y = conv_s1(x, w, False, 3, 0, bias=b, noise=nz, strength=st, act=2, gain=2 ** 0.5, clamp=1.5)
+    ref = F.conv2d(x.double(), wl[0].double(), padding=1) + (nz.double() * 0.7) + b.double().view(1, -1, 1, 1)
+    ref = (F.leaky_relu(ref, 0.2) * 2 ** 0.5).clamp(-1.5, 1.5)
+    print(f'  fused epilogue rel-L2 {rel(y, ref):.2e} err-flag {L.spi_tc_error()}', flush=True)
+
+
+def timing():
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    print('== timing (L2 flushed between launches; TFLOP/s = 2*N*H*W*taps*Ci*Co / t)', flush=True)
+    for (n, ci, co, h, k) in ((1, 128, 128, 512, 3), (1, 256, 256, 256, 3), (1, 512, 512, 64, 3), (1, 128, 128, 256, 3), (1, 256, 256, 128, 3),
+                              (4, 128, 128, 512, 3), (1, 512, 512, 32, 3), (1, 512, 512, 16, 3), (1, 128, 96, 256, 1), (1, 64, 64, 256, 3),
+                              (1, 512, 512, 32, 3)):
+        x, w, wl = make(n, ci, co, h, h, k, False)
+        wc = wl[0].contiguous(memory_format=CL)
+        gf = 2 * n * h * h * k * k * ci * co / 1e9
+        t2 = time_ms(lambda: conv_s1(x, w, False, k))
+        tc = time_ms(lambda: F.conv2d(x, wc, padding=k // 2))
+        t1 = None
+        if h >= 16:
+            w5 = w.view(1, co, k, k, ci)
+            y1 = torch.empty(n, co, h, h, device='cuda', memory_format=CL)
+            t1 = time_ms(lambda: L.spi_conv2d_tc(_lib.ptr(x), _lib.ptr(w5), _lib.ptr(y1), n, h, h, ci, co, k, k, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0,
+                                                 _lib.stream()))
+        print(f'  s1 {n}x{ci}->{co} @{h}^2 k{k} ({gf:.1f} GF): tc2 {t2:.3f} ms {gf / t2:.0f} TF/s | cuDNN {tc:.3f} ms {gf / tc:.0f} TF/s'
+              + (f' | tc05(v1) {t1:.3f} ms {gf / t1:.0f} TF/s' if t1 else '') + f' | err {L.spi_tc_error()}', flush=True)
+    for (n, ci, co, h) in ((1, 256, 128, 256), (1, 512, 256, 64), (1, 256, 128, 128), (1, 32, 256, 128), (4, 256, 128, 256)):
+        x, w, wl = make(n, ci, co, h, h, 3, False)
+        wt = wl[0].permute(1, 0, 2, 3).contiguous(memory_format=CL)
+        gf = 2 * n * h * h * 9 * ci * co / 1e9
+        t2 = time_ms(lambda: conv_t2(x, w, False))
+        tc = time_ms(lambda: F.conv_transpose2d(x, wt, stride=2))
+        print(f'  t2 {n}x{ci}->{co} @{h}^2 -> {2 * h + 1}^2 ({gf:.1f} GF): tc2 {t2:.3f} ms {gf / t2:.0f} TF/s | cuDNN {tc:.3f} ms {gf / tc:.0f} TF/s | err {L.spi_tc_error()}', flush=True)
+        x2, w2, wl2 = make(n, co, ci, 2 * h + 1, 2 * h + 1, 3, False)
+        wc2 = wl2[0].contiguous(memory_format=CL)
+        t2 = time_ms(lambda: conv_s2(x2, w2, False))
+        tc = time_ms(lambda: F.conv2d(x2, wc2, stride=2))
+        print(f'  s2 {n}x{co}->{ci} @{2 * h + 1}^2 -> {h}^2 ({gf:.1f} GF): tc2 {t2:.3f} ms {gf / t2:.0f} TF/s | cuDNN {tc:.3f} ms {gf / tc:.0f} TF/s | err {L.spi_tc_error()}', flush=True)
+
+
+def one():
+    """A few launches of the 128->128 @512^2 layer (ncu target) and timing of the debug variants (flags 4: one M tile per CTA,
+    8: every tap reads the unshifted column -- wrong results, aligned descriptors --, 16: no output store)."""
+    x, w, wl = make(1, 128, 128, 512, 512, 3, False)
+    gf = 2 * 512 * 512 * 9 * 128 * 128 / 1e9
+    for flags in (0, 4, 8, 16, 24, 28):
+        t = time_ms(lambda: conv_s1(x, w, False, 3, flags))
+        print(f'  flags {flags}: {t:.3f} ms {gf / t:.0f} TF/s err {L.spi_tc_error()}', flush=True)
+    x, w, wl = make(1, 256, 256, 256, 256, 3, False)
+    for flags in (0, 4, 8, 16):
+        t = time_ms(lambda: conv_s1(x, w, False, 3, flags))
+        print(f'  256->256@256 flags {flags}: {t:.3f} ms {gf / t:.0f} TF/s err {L.spi_tc_error()}', flush=True)
+
+
+def time3():
+    """Three big layers only, each engine 2 warm-up + graph of 4 (ncu target: per-launch durations)."""
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    for (n, ci, co, h, k) in ((1, 128, 128, 512, 3), (1, 256, 256, 256, 3)):
+        x, w, wl = make(n, ci, co, h, h, k, False)
+        wc = wl[0].contiguous(memory_format=CL)
+        w5 = w.view(1, co, k, k, ci)
+        y1 = torch.empty(n, co, h, h, device='cuda', memory_format=CL)
+        gf = 2 * n * h * h * k * k * ci * co / 1e9
+        for name, fn in (('tc2', lambda: conv_s1(x, w, False, k)), ('cudnn', lambda: F.conv2d(x, wc, padding=k // 2)),
+                         ('v1', lambda: L.spi_conv2d_tc(_lib.ptr(x), _lib.ptr(w5), _lib.ptr(y1), n, h, h, ci, co, k, k, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0, _lib.stream()))):
+            t = time_ms(fn, iters=2, reps=4)
+            print(f'{name} {ci}->{co}@{h}: {t:.3f} ms {gf / t:.0f} TF/s', flush=True)
+
+
+def reps_study():
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    n, ci, co, h, k = 1, 128, 128, 512, 3
+    x, w, wl = make(n, ci, co, h, h, k, False)
+    wc = wl[0].contiguous(memory_format=CL)
+    w5 = w.view(1, co, k, k, ci)
+    y1 = torch.empty(n, co, h, h, device='cuda', memory_format=CL)
+    y2 = torch.empty(n, co, h, h, device='cuda', memory_format=CL)
+
+    def tc2_fixed():
+        _lib.check(L.spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y2), n, h, h, ci, co, k, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0, _lib.stream()))
+    for name, fn in (('tc2', lambda: conv_s1(x, w, False, k)), ('tc2-fixed-y', tc2_fixed), ('cudnn', lambda: F.conv2d(x, wc, padding=k // 2)),
+                     ('v1', lambda: L.spi_conv2d_tc(_lib.ptr(x), _lib.ptr(w5), _lib.ptr(y1), n, h, h, ci, co, k, k, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0, _lib.stream()))):
+        for reps in (1, 4, 16, 64):
+            t = time_ms(fn, iters=5, reps=reps)
+            print(f'{name} reps={reps}: {t * 1e3:.1f} us per launch', flush=True)
+        # eager back-to-back, total wall on device
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        print(f'{name} eager x50: {e0.elapsed_time(e1) / 50 * 1e3:.1f} us per launch', flush=True)
+
+
+if __name__ == '__main__':
+    if '--reps' in sys.argv:
+        reps_study()
+        sys.exit(0)
+    if '--time3' in sys.argv:
+        time3()
+        sys.exit(0)
+    if '--one' in sys.argv:
+        one()
+        sys.exit(0)
+    if '--probe' in sys.argv or len(sys.argv) == 1:
+        probe()
+    if '--time' in sys.argv or len(sys.argv) == 1:
+        timing()
