@@ -210,6 +210,12 @@ int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float* y, int n,
                                 cudaStream_t stream);
 int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
                       cudaStream_t stream);
+/* Weight gradients of the same convolutions (spi_b200/csrc/conv_wgrad_tc2.cu; replaces cuDNN's wgrad behind the autograd of
+ * `_conv2d_wrapper`, conv2d_resample.py:30-43).  mode 0: y = spi_conv2d_tc2(x, w), dy [n,h,w,co] -> dw [g][co][k*k][ci];
+ * mode 1: y = spi_conv_transpose2d_s2_tc2(x, w), dy [n,2h+1,2w+1,co] -> dw TRANSPOSED [g][ci][9][co].  g = n when per_sample (one
+ * gradient per image) else 1 (summed over the batch); dw is overwritten; partial sums are combined with fp32 reduce-adds. */
+int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
+                       cudaStream_t stream);
 /* w [g][o][taps][i] -> wt [g][i][taps'][o], taps' reversed when `reverse` (stride-1 data gradient) else kept (stride-2 forms). */
 int spi_conv_weight_transpose(const float* w, float* wt, int g, int o, int taps, int i, int reverse, cudaStream_t stream);
 

@@ -59,6 +59,7 @@ _SIGS = {
     'spi_conv_transpose2d_s2_tc2': [c_void_p] * 3 + [c_int] * 7 + [c_void_p],
     'spi_conv2d_s2_tc2': [c_void_p] * 3 + [c_int] * 7 + [c_void_p],
     'spi_conv_weight_transpose': [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p],
+    'spi_conv_wgrad_tc2': [c_void_p] * 3 + [c_int] * 8 + [c_void_p],
 }
 
 EXPORTS = sorted(list(_SIGS) + ['spi_last_error', 'spi_launch_count', 'spi_reset_launch_count', 'spi_abi_version'])

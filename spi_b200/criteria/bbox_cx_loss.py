@@ -64,7 +64,7 @@ class VGG19(torch.nn.Module):
             m = mods[k]
             if isinstance(m, torch.nn.Conv2d):
                 relu = k + 1 < len(mods) and isinstance(mods[k + 1], torch.nn.ReLU)
-                X = bias_act.bias_act(conv_engine.conv2d(X, m.weight, padding=1), m.bias, act=('relu' if relu else 'linear'), gain=1)
+                X = conv_engine.vgg_conv(X, m, act=('relu' if relu else 'linear'))
                 k += 2 if relu else 1
             else:
                 X = maxpool2x2(X) if isinstance(m, torch.nn.MaxPool2d) else m(X)

@@ -68,7 +68,7 @@ class BaseNet(nn.Module):
         fused_relu = False
         for i, layer in enumerate(self.layers, 1):
             if isinstance(layer, nn.Conv2d):       # conv -> (+bias, ReLU) in one epilogue pass
-                x = bias_act.bias_act(conv_engine.conv2d(x, layer.weight, padding=1), layer.bias, act='relu', gain=1)
+                x = conv_engine.vgg_conv(x, layer, act='relu')
                 fused_relu = True
             elif isinstance(layer, nn.ReLU) and fused_relu:
                 fused_relu = False

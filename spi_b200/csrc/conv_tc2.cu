@@ -10,15 +10,16 @@
 // bandwidth at 96-128 B/clk/SM): the A operand of ALL taps of a 32-channel chunk is ONE halo patch.  A CTA owns MT (1 or 2) M tiles
 // of 16 rows x 8 pixels side by side; the patch [R rows][PX pixels][32 ch] (R <= 18, PX = 16 or 24) is fetched by one TMA box load
 // (out-of-bounds texels zero-filled: padding is free) and lands as R*PX rows of 128 bytes in the SWIZZLE_128B pattern.  Because an
-// M tile is 8 pixels wide and PX is a multiple of 8, the 8-row groups of the tile for tap (dy, dx) start at
-// patch + ((g + dy) * PX + 8 s + dx) * 128: a uniform stride of PX * 128 bytes (a multiple of the 1024-byte swizzle atom) -- exactly
-// what a K-major shared-memory matrix descriptor expresses (SBO = PX * 128).  The nine taps are nine descriptors into the same
+// M tile is 8 pixels wide, the 8-row groups of the tile for tap (dy, dx) start at patch + ((g + dy) * PX + 8 s + dx) * 128: a uniform
+// stride of PX * 128 bytes -- exactly what a K-major shared-memory matrix descriptor expresses (SBO = PX * 128).  The unit applies the
+// swizzle to absolute shared-memory address bits (measured: profiles/r2_conv2_probe.txt), so neither the tap shift nor a pitch that
+// is not a multiple of the 1024-byte atom disturbs the pattern TMA wrote: PX is just the tile width plus the halo (18 for 3x3).  The nine taps are nine descriptors into the same
 // patch; A traffic drops from 9 x 16 KB to 27 KB per M tile and chunk, and each B (weight) tile is used by MT M tiles.
 // 3x3, Cout tile 128, MT = 2: (55 + 147) KB per 4608 MMA cycles = 44 B/clk/SM.
 //
 // Warp roles (256 threads, persistent CTAs, static round-robin over tiles):
 //   warp 0  patch producer (one lane): empty_a -> TMA box load of the next (view, chunk) patch -> full_a          (2 buffers)
-//   warp 1  weight producer (one lane): empty_b -> TMA load of the [BN x 32] weight tile of (tap, chunk) -> full_b (4 stages)
+//   warp 1  weight producer (one lane): empty_b -> TMA load of the [BN x 32] weight tile of (tap, chunk) -> full_b (4-8 stages)
 //   warp 2  MMA issuer (one lane): per weight stage MT x 4 tcgen05.mma.kind::tf32 (K = 8), commit -> empty_b; after the last tap of
 //           a patch commit -> empty_a; after the last k-block commit -> tfull[buf]
 //   warp 3  allocates / frees tensor memory (512 columns: MT accumulators of BN columns, double-buffered)
@@ -34,9 +35,7 @@ namespace {
 using namespace tc05;
 
 constexpr int NT2 = 256;
-constexpr int PATCH_MAX = 18 * 24 * 128;      // bytes of the largest halo patch
-constexpr int BST = 5;                        // weight stages
-constexpr int B_MAX = 128 * 128;              // bytes of one weight stage (BN <= 128 rows of 128 B)
+constexpr int BST = 8;                        // most weight stages
 constexpr int STG_BYTES = 128 * 128;          // epilogue staging tile (128 pixels x 32 channels)
 constexpr int MAXV = 4, MAXP = 4, MAXT = 9;
 
@@ -52,18 +51,20 @@ struct Conv2Args {
     CUtensorMap wmap;
     Program prog[MAXP];
     int nprog, total;
-    int n, ci, co, bn, tiles_o, mt, px, patch_bytes, per_sample, dbg;
+    int n, ci, co, bn, tiles_o, mt, px, patch_bytes, per_sample, dbg, splitk, cps, npb, patch_stride, nbst, b_stride, sm_b, sm_stg;
     const float* bias; const float* noise; const float* noise_strength;
     int noise_w, out_h, out_w;
     int act; float slope, gain, clamp;
     int* err;
 };
 
-constexpr int SM_PATCH = 0;
-constexpr int SM_B = 2 * PATCH_MAX;
-constexpr int SM_STG = SM_B + BST * B_MAX;
-constexpr int SM_BAR = SM_STG + 2 * STG_BYTES;
-constexpr int SM_TOTAL = SM_BAR + 256 + MAXP * MAXV * MAXT * 16 + 64 + 1024;
+// Shared memory: [barriers + step tables: 4 KB][patch ring: npb x patch_stride][weight stages: nbst x b_stride][staging: 2 x 16 KB];
+// the three data regions are sized per launch (plan_smem) from the patch and weight-tile sizes.
+constexpr int SM_BAR = 0;
+constexpr int SM_PATCH = 4096;
+constexpr int MAXPB = 8;                       // patch ring depth (smaller patches -> more buffers)
+constexpr int SM_TOTAL = 227 * 1024;           // everything an SM can give one CTA
+constexpr int SM_DATA = SM_TOTAL - 1024 - SM_PATCH;
 
 // D[tmem] (+)= A[smem] * B[smem], descriptors handed over as 32-bit halves (no 64-bit arithmetic on the issuing thread)
 __device__ __forceinline__ void mma_lohi(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
@@ -73,7 +74,14 @@ __device__ __forceinline__ void mma_lohi(uint32_t tmem_d, uint32_t alo, uint32_t
         : "memory");
 }
 
-struct TileCoord { int q, n, ty, tx, ot; };
+// TMA reduce-store: global[box] += shared tile (fp32 add performed by the L2), used by the split-K partial sums
+__device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
+struct TileCoord { int q, n, ty, tx, ot, ks; };
 __device__ __forceinline__ TileCoord decode_tile(const Conv2Args& a, int t) {
     TileCoord c;
     c.q = 0;
@@ -82,6 +90,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Conv2Args& a, int t) {
     const Program& P = a.prog[c.q];
     int r = t - P.tile_begin;
     c.ot = r % a.tiles_o; r /= a.tiles_o;
+    c.ks = r % a.splitk; r /= a.splitk;
     c.tx = r % P.tiles_x; r /= P.tiles_x;
     c.ty = r % P.tiles_y; c.n = r / P.tiles_y;
     return c;
@@ -92,8 +101,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
     uint8_t* sm = raw + (base - smem_u32(raw));
     uint64_t* full_a = reinterpret_cast<uint64_t*>(sm + SM_BAR);
-    uint64_t* empty_a = full_a + 2;
-    uint64_t* full_b = empty_a + 2;
+    uint64_t* empty_a = full_a + MAXPB;
+    uint64_t* full_b = empty_a + MAXPB;
     uint64_t* empty_b = full_b + BST;
     uint64_t* tfull = empty_b + BST;
     uint64_t* tempty = tfull + 2;
@@ -102,8 +111,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // per-program step list {A offset inside the patch (16-byte units), weight tap, flags, patch x/y origin}: the hot loops read it
     // with one LDS instead of chasing the kernel parameters through constant-memory loads
-    int4* steps = reinterpret_cast<int4*>(sm + SM_BAR + 256);           // [MAXP][MAXV * MAXT]
-    int* nsteps = reinterpret_cast<int*>(sm + SM_BAR + 256 + MAXP * MAXV * MAXT * 16);
+    int4* steps = reinterpret_cast<int4*>(sm + SM_BAR + 512);           // [MAXP][MAXV * MAXT]
+    int* nsteps = reinterpret_cast<int*>(sm + SM_BAR + 512 + MAXP * MAXV * MAXT * 16);
     if (tid < MAXP) {
         int cnt = 0;
         if (tid < a.nprog) {
@@ -119,7 +128,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
         nsteps[tid] = cnt;
     }
     if (tid == 0) {
-        for (int s = 0; s < 2; s++) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 1); }
+        for (int s = 0; s < MAXPB; s++) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 1); }
         for (int s = 0; s < BST; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         fence_mbar_init();
         for (int i = 0; i < MAXV; i++) tma_prefetch_desc(&a.amap[i]);
@@ -142,15 +152,16 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                 const int4* st = steps + c.q * MAXV * MAXT;
                 const int ns = nsteps[c.q];
                 const int x0 = c.tx * a.mt * 8, y0 = c.ty * 16;
-                for (int cc = 0; cc < cchunks; cc++)
+                const int c1 = min(cchunks, (c.ks + 1) * a.cps);
+                for (int cc = c.ks * a.cps; cc < c1; cc++)
                     for (int j = 0; j < ns; j++) {
                         const int4 sp = st[j];
                         if (!(sp.z & 1)) continue;
                         const int ox = (int)(short)(sp.w & 0xffff), oy = (int)(short)((unsigned)sp.w >> 16);
                         if (!mbar_wait_bounded(&empty_a[pb], ph ^ 1)) { atomicExch(a.err, 11); return; }
                         mbar_expect_tx(&full_a[pb], (uint32_t)a.patch_bytes);
-                        tma_load_4d(sm + SM_PATCH + pb * PATCH_MAX, &a.amap[(sp.z >> 2) & 3], cc * 32, x0 + ox, y0 + oy, c.n, &full_a[pb]);
-                        pb ^= 1; if (!pb) ph ^= 1;
+                        tma_load_4d(sm + SM_PATCH + pb * a.patch_stride, &a.amap[(sp.z >> 2) & 3], cc * 32, x0 + ox, y0 + oy, c.n, &full_a[pb]);
+                        if (++pb == a.npb) { pb = 0; ph ^= 1; }
                     }
             }
         }
@@ -162,13 +173,14 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                 const int4* st = steps + c.q * MAXV * MAXT;
                 const int ns = nsteps[c.q];
                 const int wrow = (a.per_sample ? c.n * a.co : 0) + c.ot * a.bn;
-                for (int cc = 0; cc < cchunks; cc++)
+                const int c1 = min(cchunks, (c.ks + 1) * a.cps);
+                for (int cc = c.ks * a.cps; cc < c1; cc++)
                     for (int j = 0; j < ns; j++) {
                         const int wtap = st[j].y;
                         if (!mbar_wait_bounded(&empty_b[s], ph ^ 1)) { atomicExch(a.err, 12); return; }
                         mbar_expect_tx(&full_b[s], b_bytes);
-                        tma_load_3d(sm + SM_B + s * B_MAX, &a.wmap, cc * 32, wtap, wrow, &full_b[s]);
-                        if (++s == BST) { s = 0; ph ^= 1; }
+                        tma_load_3d(sm + a.sm_b + s * a.b_stride, &a.wmap, cc * 32, wtap, wrow, &full_b[s]);
+                        if (++s == a.nbst) { s = 0; ph ^= 1; }
                     }
             }
         }
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             const uint32_t a_hi = (((uint32_t)a.px * 128u) >> 4) | (1u << 14) | (2u << 29);
             const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
             const uint32_t pa_lo0 = (smem_u32(sm + SM_PATCH) >> 4) | (1u << 16);
-            const uint32_t bb_lo0 = (smem_u32(sm + SM_B) >> 4) | (1u << 16);
+            const uint32_t bb_lo0 = (smem_u32(sm + a.sm_b) >> 4) | (1u << 16);
             const int mt = a.mt;
             int s = 0, pb = 0, local = 0; uint32_t ph = 0, pph = 0;
             for (int t = blockIdx.x; t < a.total; t += gridDim.x, local++) {
@@ -191,7 +203,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                 fence_after();
                 const uint32_t dcol = tm + buf * 256;
                 uint32_t acc = 0;
-                for (int cc = 0; cc < cchunks; cc++) {
+                const int c1 = min(cchunks, (c.ks + 1) * a.cps);
+                for (int cc = c.ks * a.cps; cc < c1; cc++) {
                     int4 sp = st[0];
                     for (int j = 0; j < ns; j++) {
                         const int4 cur = sp;
@@ -201,8 +214,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                         }
                         if (!mbar_wait_bounded(&full_b[s], ph)) { atomicExch(a.err, 15); return; }
                         fence_after();
-                        const uint32_t alo = pa_lo0 + (uint32_t)(pb * (PATCH_MAX >> 4)) + (uint32_t)cur.x;
-                        const uint32_t blo = bb_lo0 + (uint32_t)(s * (B_MAX >> 4));
+                        const uint32_t alo = pa_lo0 + (uint32_t)(pb * (a.patch_stride >> 4)) + (uint32_t)cur.x;
+                        const uint32_t blo = bb_lo0 + (uint32_t)(s * (a.b_stride >> 4));
                         mma_lohi(dcol, alo, a_hi, blo, b_hi, idesc, acc);
                         mma_lohi(dcol, alo + 2, a_hi, blo + 2, b_hi, idesc, 1u);
                         mma_lohi(dcol, alo + 4, a_hi, blo + 4, b_hi, idesc, 1u);
@@ -215,10 +228,10 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                         }
                         acc = 1;
                         commit(&empty_b[s]);
-                        if (++s == BST) { s = 0; ph ^= 1; }
+                        if (++s == a.nbst) { s = 0; ph ^= 1; }
                         if (cur.z & 2) {
                             commit(&empty_a[pb]);
-                            pb ^= 1; if (!pb) pph ^= 1;
+                            if (++pb == a.npb) { pb = 0; pph ^= 1; }
                         }
                     }
                 }
@@ -231,7 +244,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
         const int py_in = row >> 3, px_in = row & 7;
         const bool leader = (warp == 4 && lane == 0);
         const float strength = a.noise ? (a.noise_strength ? *a.noise_strength : 1.f) : 0.f;
-        uint8_t* sC = sm + SM_STG;
+        uint8_t* sC = sm + a.sm_stg;
         int local = 0, cidx = 0;
         for (int t = blockIdx.x; t < a.total; t += gridDim.x, local++) {
             const TileCoord c = decode_tile(a, t);
@@ -278,7 +291,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                     fence_async_smem();
                     named_bar_sync(1, 128);
                     if (leader && !(a.dbg & 16)) {
-                        tma_store_4d(&a.omap[P.omap], stg, o0, xo, yo, c.n);
+                        if (a.splitk > 1) tma_reduce_add_4d(&a.omap[P.omap], stg, o0, xo, yo, c.n);
+                        else tma_store_4d(&a.omap[P.omap], stg, o0, xo, yo, c.n);
                         tma_commit_group();
                     }
                 }
@@ -347,6 +361,28 @@ bool map_image(CUtensorMap* m, const float* ptr, int c, long long wv, long long 
 
 int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 96 == 0 && co <= 96 ? 96 : (co % 64 == 0 && co < 128 ? 64 : (co > 128 ? 128 : (co + 31) / 32 * 32))); }
 
+// Small feature maps cannot fill 148 SMs with 256-pixel x 128-channel tiles: narrow the Cout tile to 64 and split the Cin chunks of
+// every tile over `splitk` CTAs.  Partial sums meet in the output through TMA reduce-adds, so the output is zeroed first and no fused
+// epilogue is possible (`allow_split` is false when the caller asked for one).  `tiles_pn` = pixel tiles x images.
+void plan_tiles(Conv2Args& a, int tiles_pn, bool allow_split, float* y, size_t y_bytes, cudaStream_t stream) {
+    const int cchunks = a.ci / 32, sms = spi_num_sms();
+    if (a.bn == 128 && (long long)tiles_pn * a.tiles_o * (allow_split ? cchunks : 1) < sms) { a.bn = 64; a.tiles_o = cdiv(a.co, a.bn); }
+    const int tiles = tiles_pn * a.tiles_o;
+    a.splitk = 1; a.cps = cchunks;
+    if (!allow_split || tiles >= sms * 3 / 4 || cchunks < 2) return;
+    double best = (double)tiles / ((double)cdiv(tiles, sms) * sms);
+    for (int cps = cchunks - 1; cps >= 1; cps--) {
+        const int s = cdiv(cchunks, cps);
+        if (s > 32) break;
+        if (cdiv(cchunks, s) != cps) continue;
+        const long long items = (long long)tiles * s;
+        const double eff = (double)items / ((double)cdiv(items, sms) * sms);
+        if (eff > best + 1e-9) { best = eff; a.splitk = s; a.cps = cps; }
+        if (eff >= 0.8) break;
+    }
+    if (a.splitk > 1) cudaMemsetAsync(y, 0, y_bytes, stream);
+}
+
 int launch2(Conv2Args& a, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
@@ -357,6 +393,19 @@ int launch2(Conv2Args& a, cudaStream_t stream) {
         configured = true;
     }
     a.err = spi_tc_err_flag();
+    {   // shared-memory plan: weight stages first (they turn over once per tap), then as many patch buffers as still fit
+        const int P = (a.patch_bytes + 1023) & ~1023, B = (a.bn * 128 + 1023) & ~1023;
+        int taps = 0;
+        for (int v = 0; v < a.prog[0].nviews; v++) taps += a.prog[0].views[v].ntaps;
+        a.npb = taps <= 2 ? 4 : 2;                       // 1x1 layers: a patch lasts one or two MMAs batches, the ring must be deeper
+        a.nbst = (SM_DATA - 2 * STG_BYTES - a.npb * P) / B;
+        if (a.nbst > BST) a.nbst = BST;
+        if (a.nbst < 2) { spi_set_error("spi_conv_tc2: shared-memory plan failed (patch %d B, weight tile %d B)", P, B); return SPI_ERR_ARG; }
+        while (a.npb < 4 && SM_DATA - 2 * STG_BYTES - a.nbst * B - (a.npb + 1) * P >= 0) a.npb++;
+        a.patch_stride = P; a.b_stride = B;
+        a.sm_b = SM_PATCH + a.npb * P;
+        a.sm_stg = a.sm_b + a.nbst * B;
+    }
     const int sms = spi_num_sms();
     const int grid = a.total < sms ? a.total : sms;
     conv_tc2_kernel<<<grid, NT2, SM_TOTAL, stream>>>(a);
@@ -365,12 +414,20 @@ int launch2(Conv2Args& a, cudaStream_t stream) {
     return SPI_OK;
 }
 
-void common_args(Conv2Args& a, int n, int ci, int co, int per_sample, int wv_out, int flags) {
+// Tile shape.  Cout % 256 == 0 and a map large enough to fill the chip: one 128-pixel M tile x 256 output channels (an MMA of N = 256
+// reads 96 B/clk of operands from shared memory against 128 B/clk at N = 128: the weight-tile re-read is what bounds N = 128);
+// otherwise two M tiles x (at most) 128 channels, which halves the weight traffic per pixel instead.
+void common_args(Conv2Args& a, int n, int ci, int co, int per_sample, int wv_out, int hv_out, int flags) {
     memset(&a, 0, sizeof(a));
     a.n = n; a.ci = ci; a.co = co; a.per_sample = per_sample ? 1 : 0;
-    a.bn = pick_bn(co);
+    const long long t256 = (long long)cdiv(wv_out, 8) * cdiv(hv_out, 16) * n * (co / 256);
+    if (co % 256 == 0 && t256 >= spi_num_sms() * 3 / 4 && !(flags & 128)) {
+        a.bn = 256; a.mt = 1;
+    } else {
+        a.bn = pick_bn(co);
+        a.mt = (wv_out > 8 && !(flags & 4)) ? 2 : 1;
+    }
     a.tiles_o = cdiv(co, a.bn);
-    a.mt = (wv_out > 8 && !(flags & 4)) ? 2 : 1;
     a.dbg = flags;
     a.gain = 1.f; a.clamp = -1.f;
 }
@@ -400,11 +457,13 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
     SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "spi_conv2d_tc2: tensors must be 16-byte aligned");
     const int rnd = (flags & 1) ? 0 : 1;
     Conv2Args a;
-    common_args(a, n, ci, co, per_sample, wd, flags);
+    common_args(a, n, ci, co, per_sample, wd, h, flags);
     const int halo = k / 2;
-    a.px = a.mt * 8 + (halo ? 8 : 0);
+    a.px = a.mt * 8 + (halo ? ((flags & 64) ? 8 : 2 * halo) : 0);
     const int rows = 16 + 2 * halo;
     a.patch_bytes = rows * a.px * 128;
+    const bool epi = bias || noise || act != 0 || gain != 1.f || clamp >= 0.f;
+    plan_tiles(a, cdiv(wd, a.mt * 8) * cdiv(h, 16) * n, !epi && !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
     if (!map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) ||
         !map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0) ||
         !map_weights(a, w, k * k, per_sample ? n : 1, rnd)) {
@@ -420,7 +479,7 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
     for (int ky = 0; ky < k; ky++)
         for (int kx = 0; kx < k; kx++) V.taps[ky * k + kx] = Tap{ky, (flags & 8) ? 0 : kx, ky * k + kx};
     a.nprog = 1;
-    a.total = P.tiles_x * P.tiles_y * a.tiles_o * n;
+    a.total = P.tiles_x * P.tiles_y * a.tiles_o * n * a.splitk;
     a.bias = bias; a.noise = noise; a.noise_strength = noise_strength; a.noise_w = wd; a.out_h = h; a.out_w = wd;
     a.act = act; a.slope = slope; a.gain = gain; a.clamp = clamp;
     return launch2(a, stream);
@@ -436,10 +495,15 @@ extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float
     const int rnd = (flags & 1) ? 0 : 1;
     const int ho = 2 * h + 1, wo = 2 * wd + 1;
     Conv2Args a;
-    common_args(a, n, ci, co, per_sample, wd + 1, flags);
-    a.px = a.mt * 8 + 8;
+    common_args(a, n, ci, co, per_sample, wd + 1, h + 1, flags);
+    a.px = a.mt * 8 + ((flags & 64) ? 8 : 1);
     const int rows = 17;
     a.patch_bytes = rows * a.px * 128;
+    {
+        int tp = 0;
+        for (int q = 0; q < 4; q++) tp += cdiv(wd + 1 - (q & 1), a.mt * 8) * cdiv(h + 1 - (q >> 1), 16) * n;
+        plan_tiles(a, tp, !(flags & 32), y, (size_t)n * ho * wo * co * 4, stream);
+    }
     bool ok = map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) &&
               map_weights(a, w, 9, per_sample ? n : 1, rnd);
     for (int i = 1; i < MAXV; i++) a.amap[i] = a.amap[0];
@@ -453,7 +517,7 @@ extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float
         P.nviews = 1; P.omap = q; P.fuse_epilogue = 0;
         P.tiles_x = cdiv(wr, a.mt * 8); P.tiles_y = cdiv(hr, 16);
         P.tile_begin = begin;
-        begin += P.tiles_x * P.tiles_y * a.tiles_o * n;
+        begin += P.tiles_x * P.tiles_y * a.tiles_o * n * a.splitk;
         View& V = P.views[0];
         V.amap = 0; V.oy = -1; V.ox = -1; V.ntaps = 0;
         for (int ky = py; ky < 3; ky += 2)
@@ -474,10 +538,11 @@ extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n
     const int rnd = (flags & 1) ? 0 : 1;
     const int hi = 2 * h + 1, wi = 2 * wd + 1;
     Conv2Args a;
-    common_args(a, n, ci, co, per_sample, wd, flags);
-    a.px = a.mt * 8 + 8;
+    common_args(a, n, ci, co, per_sample, wd, h, flags);
+    a.px = a.mt * 8 + ((flags & 64) ? 8 : 1);
     const int rows = 17;
     a.patch_bytes = rows * a.px * 128;
+    plan_tiles(a, cdiv(wd, a.mt * 8) * cdiv(h, 16) * n, !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
     bool ok = map_weights(a, w, 9, per_sample ? n : 1, rnd) &&
               map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0);
     Program& P = a.prog[0];
@@ -494,7 +559,7 @@ extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n
     }
     if (!ok) { spi_set_error("spi_conv2d_s2_tc2: cuTensorMapEncodeTiled failed"); return SPI_ERR_CUDA; }
     a.nprog = 1;
-    a.total = P.tiles_x * P.tiles_y * a.tiles_o * n;
+    a.total = P.tiles_x * P.tiles_y * a.tiles_o * n * a.splitk;
     return launch2(a, stream);
 }
 

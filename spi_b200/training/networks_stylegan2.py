@@ -50,9 +50,11 @@ def _batched_resample_conv(x, w, f, up, padding, flip_weight, epilogue=None):
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True, blur_epilogue=None):
+                     flip_weight=True, fused_modconv=True, blur_epilogue=None, conv_epilogue=None):
     """networks_stylegan2.py:34-91.  x [N,I,H,W], weight [O,I,kh,kw], styles [N,I].  `blur_epilogue` (up = 2, fused branch only):
-    the caller's noise / bias / activation pass, applied inside the FIR kernel that ends the up-sampling convolution."""
+    the caller's noise / bias / activation pass, applied inside the FIR kernel that ends the up-sampling convolution.  `conv_epilogue`
+    (up = 1, fused branch only; keyword arguments of `conv_engine.conv2d_bias_act`): the same pass applied inside the convolution's
+    accumulator read-out."""
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
     misc.assert_shape(weight, [out_channels, in_channels, kh, kw])
@@ -66,14 +68,19 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
             # the stride-2 transposed convolution consumes [I,O,kh,kw] channels-last weights with the taps reversed when
             # flip_weight is set (conv2d_resample.py:38-40,117): modulate_weights writes them like that directly
             pre = bool(flip_weight) and (kh > 1 or kw > 1)
-            w = modulate_weights(weight, styles, demodulate, layout='ihwo', flip=pre)
+            # cuDNN's transposed convolution wants [I][kh][kw][O]; this library's engine reads [O][kh][kw][I] for every form
+            up_layout = 'ohwi' if (conv_engine.ENGINE == 'tc2' and in_channels % 32 == 0 and out_channels % 32 == 0) else 'ihwo'
+            w = modulate_weights(weight, styles, demodulate, layout=up_layout, flip=pre)
             x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight and not pre, epilogue=blur_epilogue)
             if blur_epilogue is not None:
                 assert noise is None
                 return x
         else:
-            w = modulate_weights(weight, styles, demodulate, layout='ohwi')
-            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight)
+            w = modulate_weights(weight, styles, demodulate, layout='ohwi', flip=not flip_weight and (kh > 1 or kw > 1))
+            if conv_epilogue is not None:
+                assert noise is None
+                return conv_engine.conv2d_bias_act(x, w, **conv_epilogue)
+            x = _batched_resample_conv(x, w, resample_filter, up, padding, True)
         if noise is not None:
             x = x + noise
         return x
@@ -217,6 +224,13 @@ class SynthesisLayer(torch.nn.Module):
                 epi.update(noise_const=self.noise_const, noise_strength=self.noise_strength)
             return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=None, up=self.up, padding=self.padding,
                                     resample_filter=self.resample_filter, flip_weight=False, fused_modconv=True, blur_epilogue=epi)
+        if self.up == 1 and fused_modconv and noise is None and x.dtype == torch.float32 and self.padding == self.weight.shape[-1] // 2:
+            # non-resampling layer: conv -> (constant noise) + bias + lrelu*gain + clamp in the convolution's own epilogue
+            epi = dict(b=self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
+            if fuse_noise:
+                epi.update(noise_const=self.noise_const, noise_strength=self.noise_strength)
+            return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=None, up=1, padding=self.padding,
+                                    resample_filter=self.resample_filter, flip_weight=True, fused_modconv=True, conv_epilogue=epi)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                              resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         if fuse_noise:      # + noise_const*noise_strength + bias -> lrelu*gain -> clamp in one pass
@@ -243,6 +257,9 @@ class ToRGBLayer(torch.nn.Module):
         if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
             w = w[:1]
         styles = self.affine(w) * self.weight_gain
+        if fused_modconv and x.dtype == torch.float32:
+            epi = dict(b=self.bias.to(x.dtype), act='linear', clamp=self.conv_clamp)
+            return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=True, conv_epilogue=epi)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
 

@@ -108,6 +108,93 @@ def check_s2(n, ci, co, h, wd, per_sample, flags):
     return rel(y, ref), err
 
 
+def wgrad(x, dy, co, ci, k, per_sample, mode):
+    n, _, h, wd = x.shape
+    g = n if per_sample else 1
+    dw = torch.empty((g, co, k * k, ci) if mode == 0 else (g, ci, k * k, co), device=x.device)
+    _lib.check(L.spi_conv_wgrad_tc2(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), n, h, wd, ci, co, k, int(per_sample), mode, _lib.stream()))
+    return dw
+
+
+def check_wgrad(n, ci, co, h, wd, k, per_sample, mode):
+    """mode 0: stride-1 conv; mode 1: stride-2 transposed conv.  Reference: autograd of the fp64 convolution."""
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(n, ci, h, wd, generator=gen).cuda().contiguous(memory_format=CL)
+    G = n if per_sample else 1
+    w = (torch.randn(G, co, ci, k, k, generator=gen) / (k * k * ci) ** 0.5).cuda().double().requires_grad_(True)
+    if mode == 0:
+        y = torch.cat([F.conv2d(x[i:i + 1].double(), w[i if per_sample else 0], padding=k // 2) for i in range(n)])
+    else:
+        y = torch.cat([F.conv_transpose2d(x[i:i + 1].double(), w[i if per_sample else 0].permute(1, 0, 2, 3), stride=2) for i in range(n)])
+    dy = torch.randn(y.shape, generator=gen).cuda().contiguous(memory_format=CL)
+    y.backward(dy.double())
+    dw = wgrad(x, dy, co, ci, k, per_sample, mode)
+    err = L.spi_tc_error()
+    ref = w.grad                                                   # [G, O, I, kh, kw]
+    mine = dw.view(G, co, k, k, ci).permute(0, 1, 4, 2, 3) if mode == 0 else dw.view(G, ci, k, k, co).permute(0, 4, 1, 2, 3)
+    return rel(mine, ref), err
+
+
+def debug_wgrad():
+    """Smallest case (one item, one tile): dump the accumulators and compare every stage against a direct evaluation."""
+    import ctypes
+    L.spi_conv_wgrad_tc2_debug_dump.argtypes = [ctypes.c_void_p]
+    L.spi_conv_wgrad_tc2_debug_dump.restype = None
+    n, ci, co, h, wd, k = 1, 32, 32, 16, 8, 3
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(n, ci, h, wd, generator=gen).cuda().contiguous(memory_format=CL)
+    dy = torch.randn(n, co, h, wd, generator=gen).cuda().contiguous(memory_format=CL)
+    # reference dw[o][ky][kx][i] = sum_p dy[p, o] * x[p + (ky-1, kx-1), i]
+    xp = F.pad(x.double(), (1, 1, 1, 1))
+    ref = torch.zeros(co, 3, 3, ci, dtype=torch.float64, device='cuda')
+    for ky in range(3):
+        for kx in range(3):
+            ref[:, ky, kx, :] = torch.einsum('ohw,ihw->oi', dy[0].double(), xp[0, :, ky:ky + h, kx:kx + wd])
+    for flags in (0, 32, 16, 48):
+        dump = torch.full((9 * 128 * 32,), float('nan'), device='cuda')
+        L.spi_conv_wgrad_tc2_debug_dump(dump.data_ptr())
+        dw = torch.full((1, co, 9, ci), 7.0, device='cuda')
+        _lib.check(L.spi_conv_wgrad_tc2(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), n, h, wd, ci, co, k, 0, flags, _lib.stream()))
+        err = L.spi_tc_error()
+        L.spi_conv_wgrad_tc2_debug_dump(None)
+        d = dump.view(9, 128, 32)[:, :co, :]                       # [tap][o][i]
+        dref = ref.view(co, 9, ci).permute(1, 0, 2)
+        print(f'  flags {flags}: err {err} | dump finite {bool(torch.isfinite(d).all())} absmax {float(d.abs().max()):.3f} ref absmax {float(dref.abs().max()):.3f} '
+              f'rel(dump, ref) {rel(d, dref):.3e} | dw absmax {float(dw.abs().max()):.3f} rel(dw, ref) {rel(dw.view(co, 9, ci), ref.view(co, 9, ci)):.3e}', flush=True)
+        for tap in (0, 4, 8):
+            print(f'     tap {tap}: rel {rel(d[tap], dref[tap]):.3e}  dump[0,:4] {d[tap, 0, :4].tolist()}  ref[0,:4] {dref[tap, 0, :4].tolist()}', flush=True)
+
+
+def probe_wgrad():
+    print('== weight gradient (MN-major operands, kx taps folded into N)', flush=True)
+    for case in ((1, 32, 32, 16, 8, 3, False, 0), (1, 32, 128, 16, 16, 3, False, 0), (2, 64, 128, 40, 56, 3, True, 0), (2, 64, 96, 24, 24, 1, False, 0),
+                 (3, 96, 320, 24, 16, 3, False, 0), (1, 512, 512, 4, 4, 3, True, 0), (1, 128, 128, 128, 128, 3, False, 0),
+                 (1, 32, 32, 16, 8, 3, False, 1), (2, 64, 128, 20, 28, 3, True, 1), (1, 256, 128, 64, 64, 3, False, 1), (1, 512, 512, 4, 4, 3, True, 1)):
+        try:
+            e, err = check_wgrad(*case)
+            print(f'  wgrad {case}: rel-L2 {e:.2e} err-flag {err}', flush=True)
+        except Exception as ex:
+            print(f'  wgrad {case}: EXC {ex}', flush=True)
+
+
+def time_wgrad():
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    print('== wgrad timing', flush=True)
+    for (n, ci, co, h, k, mode) in ((1, 128, 128, 512, 3, 0), (1, 256, 256, 256, 3, 0), (1, 512, 512, 64, 3, 0), (4, 128, 128, 512, 3, 0), (1, 128, 96, 256, 1, 0),
+                                    (1, 512, 512, 16, 3, 0), (1, 256, 128, 256, 3, 1), (1, 512, 256, 64, 3, 1), (4, 256, 128, 256, 3, 1)):
+        x, w, wl = make(n, ci, co, h, h, k, False)
+        oh = h if mode == 0 else 2 * h + 1
+        dy = torch.randn(n, co, oh, oh, device='cuda').contiguous(memory_format=CL)
+        gf = 2 * n * h * h * k * k * ci * co / 1e9
+        t2 = time_ms(lambda: wgrad(x, dy, co, ci, k, False, mode))
+        wc = (wl[0] if mode == 0 else wl[0].permute(1, 0, 2, 3)).contiguous(memory_format=CL)
+        tc = time_ms(lambda: torch.ops.aten.convolution_backward(dy, x, wc, None, [1, 1] if mode == 0 else [2, 2], [k // 2, k // 2] if mode == 0 else [0, 0],
+                                                                 [1, 1], mode == 1, [0, 0], 1, [False, True, False]))
+        print(f'  wgrad mode {mode} {n}x{ci}->{co} @{h}^2 k{k} ({gf:.1f} GF): tc2 {t2:.3f} ms {gf / t2:.0f} TF/s | cuDNN {tc:.3f} ms {gf / tc:.0f} TF/s | err {L.spi_tc_error()}',
+              flush=True)
+
+
 def probe():
     print('== descriptor-semantics probe: flags 0 = base offset 0, flags 2 = base offset from the tap shift', flush=True)
     for flags in (0, 2):
@@ -177,11 +264,11 @@ def one():
     8: every tap reads the unshifted column -- wrong results, aligned descriptors --, 16: no output store)."""
     x, w, wl = make(1, 128, 128, 512, 512, 3, False)
     gf = 2 * 512 * 512 * 9 * 128 * 128 / 1e9
-    for flags in (0, 4, 8, 16, 24, 28):
+    for flags in (0, 4, 64):
         t = time_ms(lambda: conv_s1(x, w, False, 3, flags))
         print(f'  flags {flags}: {t:.3f} ms {gf / t:.0f} TF/s err {L.spi_tc_error()}', flush=True)
     x, w, wl = make(1, 256, 256, 256, 256, 3, False)
-    for flags in (0, 4, 8, 16):
+    for flags in (0, 128, 64, 192):
         t = time_ms(lambda: conv_s1(x, w, False, 3, flags))
         print(f'  256->256@256 flags {flags}: {t:.3f} ms {gf / t:.0f} TF/s err {L.spi_tc_error()}', flush=True)
 
@@ -238,6 +325,13 @@ if __name__ == '__main__':
         sys.exit(0)
     if '--one' in sys.argv:
         one()
+        sys.exit(0)
+    if '--wgrad-debug' in sys.argv:
+        debug_wgrad()
+        sys.exit(0)
+    if '--wgrad' in sys.argv:
+        probe_wgrad()
+        time_wgrad()
         sys.exit(0)
     if '--probe' in sys.argv or len(sys.argv) == 1:
         probe()

@@ -14,11 +14,11 @@ def main():
     from spi_b200.configs import global_config
     global_config.use_cuda_graphs = '--graphs' in sys.argv
     job = bench.OursJob('cuda:0', bench.synthetic_inputs())
-    for kind in ['mir'] * 3 + ['rot'] * 4:
-        job.step(kind)
+    for item in [('mir', i) for i in range(3)] + [('rot', i) for i in range(4)]:
+        job.step(item)
     torch.cuda.synchronize()
-    for name, kinds in (('mir x4', ['mir'] * 4), ('rot cycle (4 it)', ['rot'] * 4)):
-        job.i_rot = 0
+    tag = os.environ.get('SPI_CONV_ENGINE', 'tc2')
+    for name, kinds in (('mir x4', [('mir', i) for i in range(4)]), ('rot cycle (4 it)', [('rot', i) for i in range(4)])):
         with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
             for k in kinds:
                 job.step(k)
@@ -32,7 +32,7 @@ def main():
         for e in ev[:45]:
             print(f'{e.device_time_total / 1e3:9.3f} ms {100 * e.device_time_total / tot:5.1f}%  n={e.count:5d}  {e.key[:110]}')
         os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-        with open(os.path.join(ROOT, 'gpurun_out', 'prof_' + name.split()[0] + '.txt'), 'w') as f:
+        with open(os.path.join(ROOT, 'gpurun_out', 'prof_' + tag + '_' + name.split()[0] + '.txt'), 'w') as f:
             f.write(f'total device time {tot / 1e3:.2f} ms over {len(kinds)} iterations; kernels launched: {sum(e.count for e in ev)}\n')
             for e in ev:
                 f.write(f'{e.device_time_total / 1e3:9.3f} ms {100 * e.device_time_total / tot:5.1f}%  n={e.count:5d}  {e.key[:160]}\n')
