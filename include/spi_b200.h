@@ -216,6 +216,13 @@ int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, in
  * gradient per image) else 1 (summed over the batch); dw is overwritten; partial sums are combined with fp32 reduce-adds. */
 int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
                        cudaStream_t stream);
+/* 1x1 convolution onto at most 4 output channels (the RGB heads of the super-resolution ToRGB layers, networks_stylegan2.py:503-518):
+ * a streaming op (1.5 FLOP/byte), plain coalesced kernels (spi_b200/csrc/conv_rgb.cu).  x [n][pixels][ci] (ci a multiple of 128, <= 512),
+ * y / dy [n][pixels][co], w / dw [g][co][ci], g = n when per_sample else 1.
+ * which = 0: y = x w^T (a = x, b = w, c = y); 1: dx = dy w (a = dy, b = w, c = dx); 2: dw = dy^T x (a = x, b = dy, c = dw, overwritten). */
+int spi_conv1x1_rgb_supported(int ci, int co);
+int spi_conv1x1_rgb(int which, const float* a, const float* b, float* c, long long pixels, int n, int ci, int co, int per_sample,
+                    cudaStream_t stream);
 /* w [g][o][taps][i] -> wt [g][i][taps'][o], taps' reversed when `reverse` (stride-1 data gradient) else kept (stride-2 forms). */
 int spi_conv_weight_transpose(const float* w, float* wt, int g, int o, int taps, int i, int reverse, cudaStream_t stream);
 

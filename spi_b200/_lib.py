@@ -60,6 +60,8 @@ _SIGS = {
     'spi_conv2d_s2_tc2': [c_void_p] * 3 + [c_int] * 7 + [c_void_p],
     'spi_conv_weight_transpose': [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p],
     'spi_conv_wgrad_tc2': [c_void_p] * 3 + [c_int] * 8 + [c_void_p],
+    'spi_conv1x1_rgb_supported': [c_int] * 2,
+    'spi_conv1x1_rgb': [c_int] + [c_void_p] * 3 + [c_ll] + [c_int] * 4 + [c_void_p],
 }
 
 EXPORTS = sorted(list(_SIGS) + ['spi_last_error', 'spi_launch_count', 'spi_reset_launch_count', 'spi_abi_version'])

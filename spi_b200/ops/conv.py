@@ -52,9 +52,11 @@ def tc2_form(x, w5, stride, padding, transpose):
     if ENGINE != 'tc2' or x.dtype != torch.float32 or w5.dtype != torch.float32:
         return None
     o, i, kh, kw = w5.shape[1:]
+    st, pd = _pair(stride), _pair(padding)
+    if kh == kw == 1 and o <= 4 and i % 128 == 0 and i <= 512 and not transpose and st == [1, 1] and pd == [0, 0]:
+        return 'rgb'             # RGB heads: a streaming 1x1 contraction (spi_b200/csrc/conv_rgb.cu)
     if i % 32 or o % 32 or kh != kw:
         return None
-    st, pd = _pair(stride), _pair(padding)
     if not transpose and st == [1, 1] and kh in (1, 3) and pd == [kh // 2, kh // 2]:
         return 's1'
     if transpose and st == [2, 2] and kh == 3 and pd == [0, 0]:
@@ -114,8 +116,19 @@ def _cl(t):
     return t if t.is_contiguous(memory_format=CL) else t.contiguous(memory_format=CL)
 
 
+def rgb_conv(which, a, b, n, pixels, ci, co, per_sample, out):
+    with _lib.timed('conv_rgb', (pixels * n * (ci + co)) * 4):
+        _lib.check(_lib.load().spi_conv1x1_rgb(which, _lib.ptr(a), _lib.ptr(b), _lib.ptr(out), pixels, n, ci, co, int(per_sample), _lib.stream()))
+    return out
+
+
 def _tc2_forward(form, x, w5, epilogue=None):
     per_sample = w5.shape[0] > 1
+    if form == 'rgb':
+        n, ci, h, wd = x.shape
+        wk = w5.reshape(w5.shape[0], w5.shape[1], ci).contiguous()
+        y = torch.empty(n, wk.shape[1], h, wd, device=x.device, dtype=torch.float32, memory_format=CL)
+        return rgb_conv(0, x, wk, n, h * wd, ci, wk.shape[1], per_sample, y), wk
     wk = _ohwi(w5)
     k = w5.shape[-1]
     wk = wk.view(wk.shape[0], wk.shape[1], k * k, wk.shape[-1])
@@ -124,12 +137,32 @@ def _tc2_forward(form, x, w5, epilogue=None):
     return tc2_t2(x, wk, per_sample), wk
 
 
-def _tc2_input_grad(form, gy, wk):
+_WT_CACHE = {}      # transposed copies of FROZEN weights (the VGG extractors), keyed by storage address + version
+
+
+def _wT(wk, reverse, frozen):
+    if not frozen:
+        return tc2_wT(wk, reverse)
+    key = (wk.data_ptr(), wk._version, tuple(wk.shape), bool(reverse))
+    hit = _WT_CACHE.get(key)
+    if hit is None:
+        if len(_WT_CACHE) > 256:
+            _WT_CACHE.clear()
+        hit = _WT_CACHE[key] = (tc2_wT(wk, reverse), wk)        # keeps wk alive: its address cannot be recycled while the entry exists
+    return hit[0]
+
+
+def _tc2_input_grad(form, gy, wk, frozen=False):
     per_sample = wk.shape[0] > 1
+    if form == 'rgb':
+        n, co, h, wd = gy.shape
+        ci = wk.shape[2]
+        gx = torch.empty(n, ci, h, wd, device=gy.device, dtype=torch.float32, memory_format=CL)
+        return rgb_conv(1, gy, wk, n, h * wd, ci, co, per_sample, gx)
     if form == 's1':
         k = int(round(wk.shape[2] ** 0.5))
-        return tc2_s1(gy, tc2_wT(wk, True), k, per_sample)
-    return tc2_s2(gy, tc2_wT(wk, False), per_sample)
+        return tc2_s1(gy, _wT(wk, True, frozen), k, per_sample)
+    return tc2_s2(gy, _wT(wk, False, frozen), per_sample)
 
 
 def _weight_grad(form, gy, x, w5, stride, padding, transpose):
@@ -137,6 +170,9 @@ def _weight_grad(form, gy, x, w5, stride, padding, transpose):
     g = w5.shape[0]
     n = x.shape[0]
     o, i, kh, kw = w5.shape[1:]
+    if form == 'rgb':
+        gw = torch.empty(g, o, i, device=x.device, dtype=torch.float32)
+        return rgb_conv(2, x, gy, n, x.shape[2] * x.shape[3], i, o, g > 1, gw).view(g, o, i, 1, 1)
     if WGRAD_ENGINE == 'tc2' and form is not None:
         h, wd = x.shape[2], x.shape[3]
         mode = 0 if form == 's1' else 1
@@ -205,7 +241,7 @@ class _PerSampleConv(torch.autograd.Function):
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gy = _cl(gy)
         if form is not None:
-            gx = _tc2_input_grad(form, gy, wk) if need_x else None
+            gx = _tc2_input_grad(form, gy, wk, frozen=not need_w) if need_x else None
             gw = _weight_grad(form, gy, x, w, stride, padding, transpose) if need_w else None
             return gx, gw, None, None, None
         _cudnn_flags()
@@ -270,7 +306,7 @@ class _ConvBiasActNoise(torch.autograd.Function):
                     pix = dpre.sum([0, 1])
                     dn = pix * strength if need_n else None
                     ds = (pix * nc).sum() if need_s else None
-        gx = _tc2_input_grad('s1', dpre, wk) if ctx.needs_input_grad[0] else None
+        gx = _tc2_input_grad('s1', dpre, wk, frozen=not ctx.needs_input_grad[1]) if ctx.needs_input_grad[0] else None
         k = w.shape[-1]
         gw = _weight_grad('s1', dpre, x, w, 1, k // 2, False) if ctx.needs_input_grad[1] else None
         return gx, gw, db, dn, ds, None

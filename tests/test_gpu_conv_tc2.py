@@ -179,3 +179,21 @@ def test_repeatability(lib, n, ci, co, h, k, split):
              clamp=3.0)
     fs = [E.tc2_s1(x, wk, k, False, e, allow_split=False) for _ in range(3)]
     assert torch.equal(fs[0], fs[1]) and torch.equal(fs[0], fs[2])
+
+
+@pytest.mark.parametrize('n,ci,h,per_sample', [(1, 128, 64, False), (2, 256, 40, True), (4, 128, 32, False)])
+def test_rgb_head_1x1_conv(lib, n, ci, h, per_sample):
+    """The Cout = 3 ToRGB convolutions of the super-resolution blocks (streaming kernels, spi_b200/csrc/conv_rgb.cu): y, dx, dw in fp32."""
+    from spi_b200.ops import conv as E
+    gen, x, w = _mk(n, ci, 3, h, h, 1, per_sample, 3 + n + ci)
+    xg, wg = x.clone().requires_grad_(True), w.clone().requires_grad_(True)
+    assert E.tc2_form(xg, wg, 1, 0, False) == 'rgb'
+    before = lib.spi_launch_count()
+    y = E.conv2d_per_sample(xg, wg, padding=0)
+    gy = torch.randn(y.shape, generator=gen).cuda().contiguous(memory_format=CL)
+    y.backward(gy)
+    assert lib.spi_launch_count() >= before + 3
+    xr, wr = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    yr = torch.cat([F.conv2d(xr[i:i + 1], wr[i if per_sample else 0]) for i in range(n)])
+    yr.backward(gy.double())
+    assert rel_l2(y, yr) < 1e-5 and rel_l2(xg.grad, xr.grad) < 1e-5 and rel_l2(wg.grad, wr.grad) < 1e-4

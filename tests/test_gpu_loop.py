@@ -333,7 +333,7 @@ def test_graph_replay_of_rotbbox_iterations_equals_the_eager_body(gen_sd, lpips_
     for k, ((lp_e, g_e, a_e), (lp_g, g_g, a_g)) in enumerate(zip(results['eager'], results['graph'])):
         eg = rel_l2(g_g, g_e)
         print(f'iteration {k}: lpips eager {lp_e:.6f} graph {lp_g:.6f}  exp_avg (gradient) rel-L2 {eg:.2e}  param rel-L2 {rel_l2(a_g, a_e):.2e}')
-        assert abs(lp_g / lp_e - 1) < 1e-4
+        assert abs(lp_g / lp_e - 1) < (1e-4 if k == 0 else 1e-3)          # later iterations inherit the parameter noise of the earlier ones
         # float atomics reorder sums between runs (plane-gradient REDs of the renderer; reduce-add partial sums of the split small layers
         # and of the weight gradients in the conv engine): 1e-6 relative on activations, amplified to ~2e-4 on the parameter gradient of
         # this network (measured 2.4e-4; 1.1e-5 with the deterministic cuDNN arm); later iterations start from parameters that already
