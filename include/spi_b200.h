@@ -226,6 +226,22 @@ int spi_conv1x1_rgb(int which, const float* a, const float* b, float* c, long lo
 /* w [g][o][taps][i] -> wt [g][i][taps'][o], taps' reversed when `reverse` (stride-1 data gradient) else kept (stride-2 forms). */
 int spi_conv_weight_transpose(const float* w, float* wt, int g, int o, int taps, int i, int reverse, cudaStream_t stream);
 
+/* ---- mirror-view contextual loss, spi/criteria/bbox_cx_loss.py (spi_b200/csrc/boxcx.cu) ---------------------------------------------
+ * spi_roi_align: torchvision.ops.roi_align(input, rois, output_size=pooled, spatial_scale=1, sampling_ratio=-1, aligned=False) as called at
+ *   bbox_cx_loss.py:47-57; in [n,c,h,w] fp32 with element strides[4], rois [k][5] = (batch index, x1, y1, x2, y2), out [k,c,pooled,pooled]
+ *   contiguous.  spi_roi_align_backward ACCUMULATES the gradient into gin (same strides; the caller zeroes it).
+ * spi_cx_rows_forward: S [b,m,n] cosine similarities -> the chain of bbox_cx_loss.py:116-131,176: d = 1 - S, relative distance to the row
+ *   minimum (+1e-5, clamp +-10), w = exp((1 - d~) / band_width), cx = w / rowsum, colmax[b,j] = max_i cx[b,i,j]; stats [b,m,2] keeps the
+ *   row minimum and row sum for the backward pass.  n <= 2048.
+ * spi_cx_rows_backward: gcol [b,n] = dL/dcolmax -> dS [b,m,n]. */
+int spi_roi_align(const float* in, const float* rois, float* out, int n, int c, int h, int w, const long long* strides, int k, int pooled,
+                  cudaStream_t stream);
+int spi_roi_align_backward(const float* gout, const float* rois, float* gin, int n, int c, int h, int w, const long long* strides, int k, int pooled,
+                           cudaStream_t stream);
+int spi_cx_rows_forward(const float* S, int b, int m, int n, float band_width, float* stats, float* colmax, cudaStream_t stream);
+int spi_cx_rows_backward(const float* S, int b, int m, int n, float band_width, const float* stats, const float* colmax, const float* gcol,
+                         float* dS, cudaStream_t stream);
+
 /* ---- stage-1 noise-buffer regulariser + re-normalisation: spi/training/projectors/mirror_projector.py:107-115,128-131 (same loops
  *      in w_projector.py / w_plus_projector.py), all buffers in one launch each.
  * table: device array of `count` records {float* x; long long out_off; int size; int pad} describing square fp32 [size,size]

@@ -61,6 +61,10 @@ _SIGS = {
     'spi_conv_weight_transpose': [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p],
     'spi_conv_wgrad_tc2': [c_void_p] * 3 + [c_int] * 8 + [c_void_p],
     'spi_conv1x1_rgb_supported': [c_int] * 2,
+    'spi_roi_align': [c_void_p] * 3 + [c_int] * 4 + [c_void_p] + [c_int] * 2 + [c_void_p],
+    'spi_roi_align_backward': [c_void_p] * 3 + [c_int] * 4 + [c_void_p] + [c_int] * 2 + [c_void_p],
+    'spi_cx_rows_forward': [c_void_p] + [c_int] * 3 + [c_float] + [c_void_p] * 3,
+    'spi_cx_rows_backward': [c_void_p] + [c_int] * 3 + [c_float] + [c_void_p] * 5,
     'spi_conv1x1_rgb': [c_int] + [c_void_p] * 3 + [c_ll] + [c_int] * 4 + [c_void_p],
 }
 

@@ -5,11 +5,76 @@ features (conv engine), centred cosine distance, relative distance, CX, -log mea
 """
 import torch
 import torch.nn.functional as F
-from torchvision.ops import roi_align
 
+from .. import _lib
 from ..ops import conv as conv_engine
 from ..ops.resize import downsample2x, maxpool2x2
-from ..torch_utils.ops import bias_act
+
+
+class _RoiAlign(torch.autograd.Function):
+    """torchvision.ops.roi_align(x, rois, output_size, spatial_scale=1, sampling_ratio=-1, aligned=False) (bbox_cx_loss.py:47-57) on
+    `spi_roi_align` / `spi_roi_align_backward`."""
+
+    @staticmethod
+    def forward(ctx, x, rois, size):
+        n, c, h, w = x.shape
+        rois = rois.contiguous().float()
+        out = torch.empty(rois.shape[0], c, size, size, device=x.device, dtype=torch.float32)
+        _lib.check(_lib.load().spi_roi_align(_lib.ptr(x), _lib.ptr(rois), _lib.ptr(out), n, c, h, w, _lib.strides4(x), rois.shape[0], size, _lib.stream()))
+        ctx.save_for_backward(rois)
+        ctx.meta = (x.shape, size)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (rois,) = ctx.saved_tensors
+        shape, size = ctx.meta
+        gin = torch.zeros(shape, device=g.device, dtype=torch.float32)
+        g = g.contiguous()
+        _lib.check(_lib.load().spi_roi_align_backward(_lib.ptr(g), _lib.ptr(rois), _lib.ptr(gin), shape[0], shape[1], shape[2], shape[3],
+                                                      _lib.strides4(gin), rois.shape[0], size, _lib.stream()))
+        return gin, None, None
+
+
+def roi_align(x, boxes, output_size):
+    if not x.is_cuda or x.dtype != torch.float32:
+        raise RuntimeError('spi_b200 roi_align: x must be a float32 CUDA tensor (no CPU path in this build)')
+    return _RoiAlign.apply(x, boxes, int(output_size))
+
+
+class _CXRows(torch.autograd.Function):
+    """compute_relative_distance + compute_cx + max over dim 1 (bbox_cx_loss.py:116-131,176) of a [B, M, N] cosine-similarity matrix in one
+    pass forward and one backward (`spi_cx_rows_forward/backward`): returns colmax [B, N] = max_i cx[b, i, j]."""
+
+    @staticmethod
+    def forward(ctx, sim, band_width):
+        b, m, n = sim.shape
+        sim = sim.contiguous()
+        stats = torch.empty(b, m, 2, device=sim.device, dtype=torch.float32)
+        colmax = torch.empty(b, n, device=sim.device, dtype=torch.float32)
+        _lib.check(_lib.load().spi_cx_rows_forward(_lib.ptr(sim), b, m, n, float(band_width), _lib.ptr(stats), _lib.ptr(colmax), _lib.stream()))
+        ctx.save_for_backward(sim, stats, colmax)
+        ctx.band_width = float(band_width)
+        return colmax
+
+    @staticmethod
+    def backward(ctx, g):
+        sim, stats, colmax = ctx.saved_tensors
+        b, m, n = sim.shape
+        dsim = torch.empty_like(sim)
+        g = g.contiguous()
+        _lib.check(_lib.load().spi_cx_rows_backward(_lib.ptr(sim), b, m, n, ctx.band_width, _lib.ptr(stats), _lib.ptr(colmax), _lib.ptr(g),
+                                                    _lib.ptr(dsim), _lib.stream()))
+        return dsim, None
+
+
+def cosine_similarity_matrix(x, y):
+    """The similarity half of compute_cosine_distance (bbox_cx_loss.py:93-113): centred on y's channel means, unit-normalised, [N, HW_x, HW_y]."""
+    y_mu = y.mean(dim=(0, 2, 3), keepdim=True)
+    x_n = F.normalize(x - y_mu, p=2, dim=1)
+    y_n = F.normalize(y - y_mu, p=2, dim=1)
+    N, C = x.shape[:2]
+    return torch.bmm(x_n.reshape(N, C, -1).transpose(1, 2), y_n.reshape(N, C, -1))
 
 
 def get_landmark_bbox(lm, scale=1):
@@ -121,7 +186,11 @@ class BoxCXLoss(torch.nn.Module):
         loss = 0
         for _x, _y in ((gt_mouth, fake_mouth), (gt_l_eye, fake_l_eye), (gt_r_eye, fake_r_eye)):
             fx, fy = self.vgg_model(_x), self.vgg_model(_y)
-            cx = compute_cx(compute_relative_distance(compute_cosine_distance(fx, fy)), self.band_width)
-            cx = torch.mean(torch.max(cx, dim=1)[0], dim=1)
+            if fx.shape[2] * fx.shape[3] <= 2048:
+                # 1 - S, relative distance, exp, row normalisation and the column maximum in one pass over the [B,1600,1600] matrix
+                cx = _CXRows.apply(cosine_similarity_matrix(fx, fy), self.band_width).mean(dim=1)
+            else:
+                cx = compute_cx(compute_relative_distance(compute_cosine_distance(fx, fy)), self.band_width)
+                cx = torch.mean(torch.max(cx, dim=1)[0], dim=1)
             loss = loss + torch.mean(-torch.log(cx + 1e-5))
         return loss * 0.1
