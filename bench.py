@@ -122,28 +122,55 @@ class ClockSampler:
 
 
 class KernelTimer:
-    """CUDA events around tagged launches, recorded on the launching (current) stream."""
+    """CUDA events around tagged launches, recorded on the launching (current) stream.
 
-    def __init__(self):
-        self.open, self.spans = {}, {}
+    graph mode: the events are created `external` and recorded DURING CUDA-graph capture, so that they become event-record nodes of the
+    captured iteration; every replay re-records them and `collect()` reads the spans afterwards.  The kernel durations then come from the
+    very configuration that is timed (no host launch latency between the bracketing events and the kernel, which inflates the spans of
+    small kernels in an eager pass).  eager mode: plain events around each call."""
 
-    def start(self, tag, units=1):
-        e = torch.cuda.Event(enable_timing=True)
+    def __init__(self, graph_mode=False):
+        self.open, self.spans, self.graph_mode, self.captured, self.owner = {}, {}, graph_mode, [], None
+        self.wants_detail = True
+
+    def _event(self, capturing):
+        return torch.cuda.Event(enable_timing=True, external=True) if capturing else torch.cuda.Event(enable_timing=True)
+
+    def start(self, tag, units=1, detail=None):
+        cap = torch.cuda.is_current_stream_capturing()
+        if self.graph_mode and not cap:
+            self.open[tag] = None            # warm-up call of a graph that is about to be captured: not measured
+            return
+        e = self._event(cap)
         e.record()
-        self.open[tag] = (e, units)
+        self.open[tag] = (e, units, cap, detail)
 
     def stop(self, tag):
-        e0, units = self.open.pop(tag)
-        e1 = torch.cuda.Event(enable_timing=True)
+        o = self.open.pop(tag)
+        if o is None:
+            return
+        e0, units, cap, detail = o
+        e1 = self._event(cap)
         e1.record()
-        self.spans.setdefault(tag, []).append((e0, e1, units))
+        tags = [tag] + ([f'{tag}|{detail}'] if detail else [])
+        for tg in tags:
+            if cap:
+                self.captured.append((self.owner, tg, e0, e1, units))
+            else:
+                self.spans.setdefault(tg, []).append(((e0, e1), units))
+
+    def collect(self, owner):
+        """After a replay of the graph captured under `owner` (and a synchronize): read the spans that graph recorded."""
+        for own, tag, e0, e1, units in self.captured:
+            if own == owner:
+                self.spans.setdefault(tag, []).append((e0.elapsed_time(e1), units))
 
     def summary(self, tag):
         sp = self.spans.get(tag, [])
         if not sp:
             return None
-        ms = [a.elapsed_time(b) for a, b, _ in sp]
-        units = [u for _, _, u in sp]
+        ms = [(a[0].elapsed_time(a[1]) if isinstance(a, tuple) else a) for a, _ in sp]
+        units = [u for _, u in sp]
         per = sorted(m / max(u, 1) for m, u in zip(ms, units))
         # median over launches: one descheduled launch on a shared box must not move the figure
         return {'launches': len(sp), 'ms_total': float(sum(ms)), 'ms_per_unit': float(per[len(per) // 2]), 'ms_per_unit_mean': float(sum(ms) / sum(units)),
@@ -350,8 +377,12 @@ def run_ours(args):
         e2e = {'value': world * k / (ms2 / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4, 'ms_per_step': ms2 / k,
                'per_rank_it_s': [k / (m / 1e3) for m in per_rank2]}
     # launches inside a replayed graph do not pass through the library's host entry points: count them from one eager pass of
-    # the same K steps, which also times the tagged kernels with CUDA events on the launching stream
+    # the same K steps (which also times the tagged kernels with CUDA events on the launching stream: the fallback figures)
     from spi_b200.configs import global_config
+
+    def kind_of(item):
+        return 'mir' if item[0] == 'mir' else ('rot_heavy' if item[1] % 4 == 0 else 'rot_light')
+
     global_config.use_cuda_graphs = False
     timer = KernelTimer()
     R.KERNEL_TIMER = timer
@@ -366,9 +397,40 @@ def run_ours(args):
     torch.cuda.synchronize()
     eager_ms = ee0.elapsed_time(ee1)
     launches = _lib.launch_count()
+    global_config.use_cuda_graphs = True
+    timing_source = 'eager pass of the same K steps (CUDA events around each call; includes the host launch latency of small kernels)'
+    step_ms = eager_ms
+    # preferred: the same events recorded as nodes of the captured iterations, read after each replay of the K timed steps
+    try:
+        gt = KernelTimer(graph_mode=True)
+        R.KERNEL_TIMER = gt
+        _lib.KERNEL_TIMER = gt
+        job.coach._graphs = {}
+        job.proj._graph = None
+        for item in [('mir', 0), ('rot', 0), ('rot', 1)]:          # capture each iteration kind again, now with the event nodes
+            gt.owner = kind_of(item)
+            job.step(item)
+        torch.cuda.synchronize()
+        gt.spans = {}
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        tot = 0.0
+        for item in sched:
+            g0.record()
+            job.step(item)
+            g1.record()
+            torch.cuda.synchronize()
+            tot += g0.elapsed_time(g1)
+            gt.collect(kind_of(item))
+        if gt.summary('render_bwd') and gt.summary('conv'):
+            timer, step_ms = gt, tot
+            timing_source = 'event-record nodes inside the captured CUDA graphs, read after each replay of the same K steps'
+    except Exception as ex:          # external events unsupported: keep the eager figures
+        timing_source += f' [graph-node events unavailable: {type(ex).__name__}]'
+        job.coach._graphs = {}
+        job.proj._graph = None
     R.KERNEL_TIMER = None
     _lib.KERNEL_TIMER = None
-    global_config.use_cuda_graphs = True
+    eager_ms = step_ms
     peak, peak_src = measured_peaks()
     rf, rb = timer.summary('render_fwd'), timer.summary('render_bwd')
     roofline = None
@@ -382,8 +444,8 @@ def run_ours(args):
         roofline = {'kernel': 'render backward (spi_render_backward*, spi_b200/csrc/raymarch_tc_bwd.cuh)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
                     'frac': ach / peak, 'traffic': tr_b, 'traffic_source': tr_b_src,
                     'peak_source': peak_src, 'algorithmic_bytes_per_image': bytes_per_img,
-                    'ms_per_image': rb['ms_per_unit'], 'launches_timed': rb['launches'],
-                    'share_of_eager_step_time': rb['ms_total'] / eager_ms,
+                    'ms_per_image': rb['ms_per_unit'], 'launches_timed': rb['launches'], 'kernel_timing': timing_source,
+                    'share_of_step_time': rb['ms_total'] / eager_ms,
                     'tensor_view': {'tf32_tflops_3x_issued': 3 * gf_bwd / rb['ms_per_unit'], 'fp32_equivalent_tflops': gf_bwd / rb['ms_per_unit'],
                                     'tf32_peak_tflops': tf32_peak, 'frac_3x_issued': 3 * gf_bwd / rb['ms_per_unit'] / tf32_peak,
                                     'note': 'decoder GEMMs (fwd recompute + dH + dF) = %.1f GF/img, issued 3x as TF32 (hi*hi + lo*hi + hi*lo); peak = measured bf16 / 2' % gf_bwd},
@@ -395,7 +457,7 @@ def run_ours(args):
                                       'frac_of_hbm_peak': fb / (rf['ms_per_unit'] * 1e-3) / 1e9 / peak, 'algorithmic_bytes_per_image': fb,
                                       'traffic': tr_f, 'traffic_source': tr_f_src, 'tf32_tflops_3x_issued': 3 * gf_fwd / rf['ms_per_unit'],
                                       'frac_3x_issued_of_tf32_peak': 3 * gf_fwd / rf['ms_per_unit'] / tf32_peak, 'launches_timed': rf['launches'],
-                                      'share_of_eager_step_time': rf['ms_total'] / eager_ms}
+                                      'share_of_step_time': rf['ms_total'] / eager_ms}
     # streaming / tensor kernels of this library, same eager pass: achieved = bytes (flops) the call must move / CUDA-event time
     streaming = {}
     for tag in ('bias_act', 'upfirdn2d', 'adam', 'warp'):
@@ -403,27 +465,49 @@ def run_ours(args):
         if sm:
             gbs = sm['units'] / (sm['ms_total'] * 1e-3) / 1e9
             streaming[tag] = {'launches': sm['launches'], 'achieved_GBps': gbs, 'frac_of_hbm_peak': gbs / peak, 'ms_total': sm['ms_total'],
-                              'share_of_eager_step_time': sm['ms_total'] / eager_ms}
+                              'share_of_step_time': sm['ms_total'] / eager_ms}
     cv = timer.summary('conv')
     conv = None
     if cv:
         tfs = cv['units'] / (cv['ms_total'] * 1e-3) / 1e12
         conv = {'launches': cv['launches'], 'achieved_TFLOPs': tfs, 'tf32_peak_tflops': bf16_peak() / 2.0, 'frac_of_tf32_peak': tfs / (bf16_peak() / 2.0),
-                'ms_total': cv['ms_total'], 'share_of_eager_step_time': cv['ms_total'] / eager_ms}
+                'ms_total': cv['ms_total'], 'share_of_step_time': cv['ms_total'] / eager_ms}
+        shapes = []
+        for tg in timer.spans:
+            if tg.startswith('conv|'):
+                sm = timer.summary(tg)
+                shapes.append((sm['ms_total'], tg[5:], sm['launches'], sm['units'] / (sm['ms_total'] * 1e-3) / 1e12))
+        shapes.sort(reverse=True)
+        conv['by_shape_top'] = [{'call': nm, 'launches': ln, 'ms_total': round(ms_, 3), 'TFLOPs': round(tf_, 1)} for ms_, nm, ln, tf_ in shapes[:16]]
     if roofline is not None:
+        render_view = roofline
+        if conv is not None and conv['ms_total'] > rb['ms_total']:
+            # the conv engine (spi_conv2d_tc2 / _transpose2d_s2 / _s2 / _wgrad_tc2) holds the largest share of the step: it is the
+            # dominant kernel family and it is tensor-bound; the renderer's HBM view is kept beside it
+            tr_c, tr_c_src = traffic_from_profiles('conv')
+            roofline = {'kernel': 'conv engine: conv_tc2_kernel + conv_wgrad_tc2_kernel (spi_b200/csrc/conv_tc2.cu, conv_wgrad_tc2.cu), every dense convolution of the step',
+                        'bound': 'tensor', 'achieved': conv['achieved_TFLOPs'], 'peak': conv['tf32_peak_tflops'], 'unit': 'TFLOP/s',
+                        'frac': conv['frac_of_tf32_peak'], 'traffic': tr_c, 'traffic_source': tr_c_src,
+                        'peak_source': 'measured (MEASURED_PEAKS.json bf16_tflops_sustained / 2: TF32 runs at half the bf16 rate; sustained figure, the kernels are timed inside the step)',
+                        'algorithmic_flops_per_step': cv['units'] / k, 'launches_timed': cv['launches'], 'kernel_timing': timing_source,
+                        'share_of_step_time': conv['share_of_step_time'],
+                        'note': 'achieved = 2*N*H*W*taps*Ci*Co summed over every convolution call (forward, data gradient, weight gradient; 4x4 ... 512x512 maps) '
+                                '/ the sum of their event-timed durations, which include the zero-fill of split layers; large layers alone reach 560-650 TFLOP/s '
+                                '(profiles/r2_bench_conv_engine.txt)',
+                        'render_backward': render_view}
         roofline['streaming_kernels'] = streaming
         roofline['conv_engine'] = conv
         dg = timer.summary('render_dec_grads')
-        roofline['decoder_grad_gemms_ms_per_image_eager'] = dg['ms_per_unit'] if dg else None
+        roofline['decoder_grad_gemms_ms_per_image'] = dg['ms_per_unit'] if dg else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(job, sched)
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': k, 'warmup': len(warm), 'ms_per_step': ms / k,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (TF32 tensor-core contractions)',
-                'data': 'synthetic', 'impl': 'ours',
+                'data': 'synthetic', 'impl': 'ours', 'conv_engine': os.environ.get('SPI_CONV_ENGINE', 'tc2'),
                 'config': {'workload': 'configs[1]: single 512^2 image per GPU, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
-                           'execution': 'each iteration replayed as a captured CUDA graph; roofline kernels timed with CUDA events in an eager pass of the same K steps',
+                           'execution': 'each iteration replayed as a captured CUDA graph; roofline kernels timed with CUDA events: ' + timing_source,
                            'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': mix_text(sched),
                            'dedup': 'views of one iteration share w_pivot: the camera-independent tri-plane backbone is evaluated once per iteration and the SR net is skipped for the depth-only views (identical results, tests/test_gpu_loop.py::test_shared_backbone_equals_per_view_evaluation); global_config.share_backbone=False restores the literal structure',
                            'l2_policy': 'per-step working set (weights + activations, > 1 GB) exceeds the 126 MB L2', 'images_per_gpu': 1},

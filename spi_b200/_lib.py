@@ -139,12 +139,15 @@ KERNEL_TIMER = None
 
 
 class timed:
-    def __init__(self, tag, units=1):
-        self.tag, self.units = tag, units
+    def __init__(self, tag, units=1, detail=None):
+        self.tag, self.units, self.detail = tag, units, detail
 
     def __enter__(self):
         if KERNEL_TIMER is not None:
-            KERNEL_TIMER.start(self.tag, self.units)
+            if self.detail is not None and getattr(KERNEL_TIMER, 'wants_detail', False):
+                KERNEL_TIMER.start(self.tag, self.units, detail=self.detail)
+            else:
+                KERNEL_TIMER.start(self.tag, self.units)
 
     def __exit__(self, *exc):
         if KERNEL_TIMER is not None:

@@ -244,6 +244,10 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
         const int py_in = row >> 3, px_in = row & 7;
         const bool leader = (warp == 4 && lane == 0);
         const float strength = a.noise ? (a.noise_strength ? *a.noise_strength : 1.f) : 0.f;
+        // epilogue constants in registers: act(r) = max(r, r * neg) covers linear (neg 1), relu (0) and lrelu (slope); clamp off = +inf
+        const float neg = a.act == 1 ? 0.f : (a.act == 2 ? a.slope : 1.f);
+        const float gain = a.gain, cl = a.clamp >= 0.f ? a.clamp : __int_as_float(0x7f800000);
+        float* sbias = reinterpret_cast<float*>(sm + SM_BAR + 3072);          // bias of the tile's BN output channels (<= 256 floats)
         uint8_t* sC = sm + a.sm_stg;
         int local = 0, cidx = 0;
         for (int t = blockIdx.x; t < a.total; t += gridDim.x, local++) {
@@ -252,10 +256,17 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             const int buf = local & 1;
             if (!mbar_wait_bounded(&tfull[buf], (local >> 1) & 1)) { atomicExch(a.err, 16); break; }
             fence_after();
+            const bool fuse = P.fuse_epilogue != 0;
+            if (fuse) {          // read by everybody after the first barrier of the chunk loop; the previous tile's readers are past their last barrier
+                for (int o = row; o < a.bn; o += 128) {
+                    const int og = c.ot * a.bn + o;
+                    sbias[o] = (a.bias && og < a.co) ? __ldg(a.bias + og) : 0.f;
+                }
+            }
             for (int m = 0; m < a.mt; m++) {
                 const int xo = (c.tx * a.mt + m) * 8, yo = c.ty * 16;
                 float nz = 0.f;
-                if (P.fuse_epilogue && a.noise) {
+                if (fuse && a.noise) {
                     const int py = yo + py_in, px = xo + px_in;
                     if (py < a.out_h && px < a.out_w) nz = a.noise[py * a.noise_w + px] * strength;
                 }
@@ -270,23 +281,20 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                     if (leader) tma_wait_group_read<1>();          // the staging buffer written two chunks ago has been drained
                     named_bar_sync(1, 128);
                     uint8_t* stg = sC + (cidx & 1) * STG_BYTES;
+                    if (fuse) {
+                        const float4* b4 = reinterpret_cast<const float4*>(sbias + cb * 32);
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        float e[4];
+                        for (int j = 0; j < 8; j++) {
+                            const float4 bb = b4[j];                    // same address for the whole warp: one broadcast LDS.128
+                            float e[4] = {v[4 * j] + (nz + bb.x), v[4 * j + 1] + (nz + bb.y), v[4 * j + 2] + (nz + bb.z), v[4 * j + 3] + (nz + bb.w)};
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            float r = v[4 * j + k];
-                            if (P.fuse_epilogue) {
-                                r += nz;
-                                if (a.bias) r += __ldg(a.bias + o0 + 4 * j + k);
-                                if (a.act == 1) r = fmaxf(r, 0.f);
-                                else if (a.act == 2) r = r < 0.f ? r * a.slope : r;
-                                r *= a.gain;
-                                if (a.clamp >= 0.f) r = fminf(fmaxf(r, -a.clamp), a.clamp);
-                            }
-                            e[k] = r;
+                            for (int k = 0; k < 4; k++) e[k] = fminf(fmaxf(fmaxf(e[k], e[k] * neg) * gain, -cl), cl);
+                            *reinterpret_cast<float4*>(stg + swz(row, j)) = make_float4(e[0], e[1], e[2], e[3]);
                         }
-                        *reinterpret_cast<float4*>(stg + swz(row, j)) = make_float4(e[0], e[1], e[2], e[3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; j++)
+                            *reinterpret_cast<float4*>(stg + swz(row, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                     }
                     fence_async_smem();
                     named_bar_sync(1, 128);

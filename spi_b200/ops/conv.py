@@ -76,7 +76,7 @@ def tc2_s1(x, wk, k, per_sample, epilogue=None, allow_split=True):
     y = torch.empty(n, co, h, wd, device=x.device, dtype=torch.float32, memory_format=CL)
     e = epilogue or {}
     flags = (0 if allow_split else 32) | TC2_FLAGS
-    with _lib.timed('conv', 2 * n * h * wd * k * k * ci * co):
+    with _lib.timed('conv', 2 * n * h * wd * k * k * ci * co, detail=f's1 k{k} {n}x{ci}->{co} @{h}x{wd}' + (' +epilogue' if epilogue else '')):
         _lib.check(_lib.load().spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, k, int(per_sample), _lib.ptr(e.get('b')),
                                               _lib.ptr(e.get('noise')), _lib.ptr(e.get('strength')), int(e.get('act', 0)), float(e.get('slope', 0.2)),
                                               float(e.get('gain', 1.0)), float(e.get('clamp', -1.0)), flags, _lib.stream()))
@@ -88,7 +88,7 @@ def tc2_t2(x, wk, per_sample):
     n, ci, h, wd = x.shape
     co = wk.shape[1]
     y = torch.empty(n, co, 2 * h + 1, 2 * wd + 1, device=x.device, dtype=torch.float32, memory_format=CL)
-    with _lib.timed('conv', 2 * n * h * wd * 9 * ci * co):
+    with _lib.timed('conv', 2 * n * h * wd * 9 * ci * co, detail=f't2 {n}x{ci}->{co} @{h}x{wd}'):
         _lib.check(_lib.load().spi_conv_transpose2d_s2_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), 0, _lib.stream()))
     return y
 
@@ -99,7 +99,7 @@ def tc2_s2(x, wk, per_sample):
     h, wd = (hi - 1) // 2, (wi - 1) // 2
     co = wk.shape[1]
     y = torch.empty(n, co, h, wd, device=x.device, dtype=torch.float32, memory_format=CL)
-    with _lib.timed('conv', 2 * n * h * wd * 9 * ci * co):
+    with _lib.timed('conv', 2 * n * h * wd * 9 * ci * co, detail=f's2 {n}x{ci}->{co} ->{h}x{wd}'):
         _lib.check(_lib.load().spi_conv2d_s2_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), 0, _lib.stream()))
     return y
 
@@ -178,7 +178,7 @@ def _weight_grad(form, gy, x, w5, stride, padding, transpose):
         mode = 0 if form == 's1' else 1
         # mode 0 writes [G][O][taps][I]; mode 1 (transposed convolution: the roles of x and dy swap) writes [G][I][taps][O]
         gw = torch.empty((g, o, kh, kw, i) if mode == 0 else (g, i, kh, kw, o), device=x.device, dtype=torch.float32)
-        with _lib.timed('conv', 2 * n * h * wd * kh * kw * i * o):
+        with _lib.timed('conv', 2 * n * h * wd * kh * kw * i * o, detail=f'wgrad{mode} k{kh} {n}x{i}->{o} @{h}x{wd}'):
             _lib.check(_lib.load().spi_conv_wgrad_tc2(_lib.ptr(x), _lib.ptr(gy), _lib.ptr(gw), n, h, wd, i, o, kh, int(g > 1), mode, _lib.stream()))
         return gw.permute(0, 1, 4, 2, 3) if mode == 0 else gw.permute(0, 4, 1, 2, 3)
     _cudnn_flags()

@@ -289,6 +289,33 @@ def time3():
             print(f'{name} {ci}->{co}@{h}: {t:.3f} ms {gf / t:.0f} TF/s', flush=True)
 
 
+def small_study():
+    """Small feature maps (VGG conv3-5, backbone b16-b64): where do 20-30 us per launch go?  flags 4 = one M tile per CTA, 32 = no split."""
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+    for (n, ci, co, h) in ((1, 512, 512, 32), (1, 512, 512, 16), (1, 256, 256, 64), (1, 512, 512, 64), (1, 128, 128, 128), (1, 64, 64, 256)):
+        x, w, wl = make(n, ci, co, h, h, 3, False)
+        wc = wl[0].contiguous(memory_format=CL)
+        gf = 2 * n * h * h * 9 * ci * co / 1e9
+        y = torch.empty(n, co, h, h, device='cuda', memory_format=CL)
+        res = []
+        for flags in (0, 4, 32, 36):
+            def fn():
+                _lib.check(L.spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), n, h, h, ci, co, 3, 0, None, None, None, 0, 0.2, 1.0, -1.0, flags, _lib.stream()))
+            res.append(f'flags {flags}: {time_ms(fn, iters=5, reps=20) * 1e3:.1f} us')
+        tz = time_ms(lambda: y.zero_(), iters=5, reps=20) * 1e3
+        tc = time_ms(lambda: F.conv2d(x, wc, padding=1), iters=5, reps=20) * 1e3
+        print(f'  {ci}->{co} @{h}^2 ({gf:.1f} GF): ' + ' | '.join(res) + f' | zero_ alone {tz:.1f} us | cuDNN {tc:.1f} us', flush=True)
+    # fused epilogue cost on the big layer
+    for (n, ci, co, h) in ((1, 128, 128, 512), (4, 128, 128, 512), (4, 256, 256, 256)):
+        x, w, wl = make(n, ci, co, h, h, 3, False)
+        b, nz, st = torch.randn(co, device='cuda'), torch.randn(h, h, device='cuda'), torch.tensor(0.7, device='cuda')
+        gf = 2 * n * h * h * 9 * ci * co / 1e9
+        t0 = time_ms(lambda: conv_s1(x, w, False, 3))
+        t1 = time_ms(lambda: conv_s1(x, w, False, 3, 0, bias=b, noise=nz, strength=st, act=2, gain=1.41, clamp=256.0))
+        print(f'  {n}x{ci}->{co} @{h}^2: plain {t0:.3f} ms {gf / t0:.0f} TF/s | fused epilogue {t1:.3f} ms {gf / t1:.0f} TF/s', flush=True)
+
+
 def reps_study():
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
@@ -317,6 +344,9 @@ def reps_study():
 
 
 if __name__ == '__main__':
+    if '--small' in sys.argv:
+        small_study()
+        sys.exit(0)
     if '--reps' in sys.argv:
         reps_study()
         sys.exit(0)
