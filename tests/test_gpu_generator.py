@@ -46,6 +46,23 @@ def test_synthesis_golden(product_G, golden):
     assert abs(out['image'].double().square().sum().item() / float(g['image_sqsum']) - 1) < 2e-3
 
 
+def test_synthesis_golden_at_the_bench_depth_resolution(product_G, golden):
+    """Same check at 32 coarse + 32 importance samples -- the configuration bench.py times (the tcgen05 two-round renderer path) -- against
+    the reference's own synthesis at that setting (oracle/make_golden_32.py)."""
+    import copy
+    g = golden('synthesis_32')
+    G = copy.deepcopy(product_G)
+    G.rendering_kwargs = dict(G.rendering_kwargs, depth_resolution=32, depth_resolution_importance=32)
+    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=32, depth_resolution_importance=32)
+    jit, u = OG.make_render_noise(1, 128 * 128, rk, seed=7)
+    G.renderer.inject_noise(jit.cuda(), u.cuda())
+    out = G.synthesis(T(g['ws']).cuda(), T(g['c']).cuda(), noise_mode='const')
+    errs = (rel_l2(out['image_raw'], g['image_raw']), rel_l2(out['image_depth'], g['image_depth']), rel_l2(out['image'][:, :, 1::4, 2::4], g['image_sub']))
+    print('32+32 synthesis rel-L2 (image_raw, image_depth, image):', errs)
+    assert max(errs) < RENDER_TOL
+    assert abs(out['image'].double().square().sum().item() / float(g['image_sqsum']) - 1) < 2e-3
+
+
 def test_sample_mixed_golden(product_G, golden):
     g = golden('synthesis')
     pts = T(g['sm_pts']).cuda()
@@ -105,6 +122,53 @@ def test_rotate_golden(golden):
     assert bad < 2e-3
     assert rel_l2(wr[:, :, 2::8, 3::8], ref_r) < 2e-2
     assert abs(wm.double().sum().item() / float(g['rot_mask_sum']) - 1) < 2e-3
+
+
+def test_rotate_decisions_are_exact_where_the_oracle_is_decisive():
+    """Depth-guided warp (rotate.py:92-116): the in-bounds test and the |d - z| < EPS test are discontinuous, so a comparison with a
+    tolerance hides real errors.  Here the reference's chain is evaluated in float64 to find, per pixel, how far it is from either
+    threshold; wherever that margin exceeds 1e-4 (float32 arithmetic cannot flip it) the kernel's 0/1 mask must be torch.equal to the
+    oracle's, and the warped colours agree to 1e-3 rel-L2 (north_star).  Pixels inside the margin are counted, not compared."""
+    import torch.nn.functional as F
+    from spi_b200.utils.rotate import rotate
+    n, res, eps = 4, 512, 5e-2
+    c = weights.canonical_camera(0.3).repeat(n, 1)
+    rand = torch.rand(n, 2, generator=torch.Generator().manual_seed(8))
+    tcam = OGeo.sample_surrounding_camera(c[:1], rand, yaw_range=0.2, pitch_range=0.1)
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, 128), torch.linspace(-1, 1, 128), indexing='ij')
+    sdepth = (2.7 - 0.35 * torch.exp(-(xx ** 2 + yy ** 2) * 2.5))[None, None].repeat(n, 1, 1, 1)
+    tdepth = (2.7 - 0.33 * torch.exp(-((xx - 0.05) ** 2 + yy ** 2) * 2.3))[None, None].repeat(n, 1, 1, 1) + 0.02 * torch.sin(7 * xx)[None, None]
+    img = weights.target_image().repeat(n, 1, 1, 1)
+    fm = OGeo.face_mask(weights.parsing_mask()).float().repeat(n, 1, 1, 1)
+    # float64 evaluation of the oracle's own expressions (oracle/geometry.py::rotate), keeping the intermediates
+    D = torch.float64
+    tex, tin = tcam[:, :16].reshape(n, 4, 4).to(D), tcam[:, 16:].reshape(n, 3, 3).to(D)
+    gex, gin = c[:, :16].reshape(n, 4, 4).to(D), c[:, 16:].reshape(n, 3, 3).to(D)
+    up = lambda d: F.interpolate(d.to(D).reshape(n, 1, 128, 128), (res, res), mode='bilinear', align_corners=False).reshape(n, res, res)
+    td, gd = up(tdepth), up(sdepth)
+    uv, z = OGeo.project(OGeo.unproject(td, tex, tin, res), gex, gin)
+    grid = 2 * uv.reshape(n, res, res, 2) - 1
+    inb = ~((grid[..., 0] < -1) | (grid[..., 0] > 1) | (grid[..., 1] < -1) | (grid[..., 1] > 1))
+    src_d = F.grid_sample(gd.reshape(n, 1, res, res), grid, align_corners=False).reshape(n, res, res)
+    diff = (src_d - z.reshape(n, res, res)).abs()
+    decision = (diff < eps) & inb
+    margin = torch.minimum((diff - eps).abs(), (grid.abs() - 1).abs().amin(dim=-1))
+    robust = margin > 1e-4
+    ref_rgb = F.grid_sample(img.to(D), grid, align_corners=False) * decision.unsqueeze(1)
+    ref_m = F.grid_sample(fm.to(D), grid, align_corners=False)
+    # kernel, without and with the source mask
+    wr0, wm0 = rotate(tcam.cuda(), tdepth.cuda(), img.cuda(), c.cuda(), sdepth.cuda(), src_mask=None, EPS=eps)
+    wr1, wm1 = rotate(tcam.cuda(), tdepth.cuda(), img.cuda(), c.cuda(), sdepth.cuda(), src_mask=fm.cuda(), EPS=eps)
+    frac = 1 - robust.double().mean().item()
+    print(f'pixels within 1e-4 of a threshold: {frac:.2e}; mask coverage {decision.double().mean().item():.3f}')
+    assert frac < 5e-3 and 0.05 < decision.double().mean().item() < 0.999
+    m0 = wm0[:, 0].cpu()
+    assert set(m0.unique().tolist()) <= {0.0, 1.0}
+    assert torch.equal(m0[robust] > 0.5, decision[robust])                     # bit-exact decisions
+    rb = robust.unsqueeze(1).expand(-1, 3, -1, -1)
+    assert rel_l2(wr0.cpu()[rb], ref_rgb[rb]) < 1e-3
+    assert rel_l2(wm1[:, 0].cpu()[robust], (ref_m[:, 0] * decision)[robust]) < 1e-5
+    assert rel_l2(wr1.cpu()[rb], (ref_rgb * ref_m)[rb]) < 1e-3
 
 
 def test_adam_matches_torch():

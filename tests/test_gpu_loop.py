@@ -133,6 +133,38 @@ def test_coach_step_golden(kind, golden, gen_sd, lpips_mod, cx_mod):
     assert rel_l2(w.grad, g[f'{kind}_wgrad']) < 5e-2
 
 
+def test_pti_step_golden_at_the_bench_depth_resolution(golden, gen_sd, lpips_mod, cx_mod):
+    """One PTI iteration at 32 + 32 samples per ray (the bench configuration) against the gradients the reference recorded at that setting
+    (tests/golden/steps_32.npz, oracle/make_golden_32.py)."""
+    from spi_b200.utils import load_utils
+    g = golden('steps_32')
+    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=32, depth_resolution_importance=32)
+    old = load_utils.DEPTH_OVERRIDE
+    load_utils.DEPTH_OVERRIDE = (32, 32)
+    try:
+        coach = make_coach('pti', gen_sd, lpips_mod, cx_mod)
+    finally:
+        load_utils.DEPTH_OVERRIDE = old
+    assert coach.G.rendering_kwargs['depth_resolution'] == 32
+    src = OL.NoiseSource(200)
+    image, camera = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
+    w = weights.w_pivot(5).cuda().requires_grad_(True)
+    jit, u = src.render(1, 128 * 128, rk)
+    coach.G.renderer.inject_noise(jit.cuda(), u.cuda())
+    lp, stepped = coach.train_step(w, camera, image)
+    assert stepped and abs(float(lp) / float(g['pti_lpips']) - 1) < 5e-3
+    params = dict(coach.G.named_parameters())
+    errs = {}
+    for k in ('decoder.net.0.weight', 'decoder.net.2.bias', 'superresolution.block1.conv1.weight', 'backbone.synthesis.b4.const',
+              'backbone.synthesis.b64.conv0.affine.weight', 'backbone.synthesis.b256.torgb.weight'):
+        grad = params[k].grad.reshape(-1)
+        sub = grad[::max(1, grad.numel() // 4096)]
+        errs[k] = (rel_l2(sub, g[f'pti_grad_{k}']), abs(float(grad.double().norm()) / float(g[f'pti_gradnorm_{k}']) - 1))
+    print('32+32 PTI step grad (rel-L2 of subsample, norm ratio - 1):', errs, 'dws', rel_l2(w.grad, g['pti_wgrad']))
+    assert max(e[0] for e in errs.values()) < 5e-2 and max(e[1] for e in errs.values()) < 3e-2
+    assert rel_l2(w.grad, g['pti_wgrad']) < 5e-2
+
+
 def test_mirror_projector_two_steps_golden(golden, gen_sd, lpips_mod):
     """Stage 1 ('mir'): two optimiser steps from the same draws as the reference run; w_opt must agree."""
     from spi_b200.training.projectors._common import LatentProjector
