@@ -161,8 +161,11 @@ def test_pti_step_golden_at_the_bench_depth_resolution(golden, gen_sd, lpips_mod
         sub = grad[::max(1, grad.numel() // 4096)]
         errs[k] = (rel_l2(sub, g[f'pti_grad_{k}']), abs(float(grad.double().norm()) / float(g[f'pti_gradnorm_{k}']) - 1))
     print('32+32 PTI step grad (rel-L2 of subsample, norm ratio - 1):', errs, 'dws', rel_l2(w.grad, g['pti_wgrad']))
-    assert max(e[0] for e in errs.values()) < 5e-2 and max(e[1] for e in errs.values()) < 3e-2
-    assert rel_l2(w.grad, g['pti_wgrad']) < 5e-2
+    # measured on B200 (TF32 contractions, 3xTF32 decoder): 0.9-1.3e-3 on every tensor except the 4x4 constant (1.3e-2: the whole
+    # network's rounding noise lands on 8192 values), norms within 9e-4, d/dws 1.2e-3
+    assert max(e[0] for e in errs.values()) < 3e-2 and max(e[1] for e in errs.values()) < 5e-3
+    assert max(e[0] for k, e in errs.items() if k != 'backbone.synthesis.b4.const') < 5e-3
+    assert rel_l2(w.grad, g['pti_wgrad']) < 5e-3
 
 
 def test_mirror_projector_two_steps_golden(golden, gen_sd, lpips_mod):

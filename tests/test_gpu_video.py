@@ -44,6 +44,27 @@ def test_orbit_clip_equals_frame_by_frame_rendering(product_G):
     assert float((frames[0].float() - frames[F // 2].float()).abs().mean()) > 0.5        # the camera does move
 
 
+def test_orbit_frames_match_the_oracle(product_G, gen_sd):
+    """Frames of the batched clip against the CPU oracle's `synthesis` at the same orbit cameras (pinned to the reference's pose
+    expressions in tests/test_postprocess.py) and the same ray-jitter draws: uint8 frames within one grey level, float images 1e-3."""
+    from oracle import generator as OG
+    from spi_b200.utils.video_utils import orbit_cameras, render_orbit
+    G = product_G
+    ws = weights.w_pivot(5).cuda()
+    F, B = 4, 4
+    jit, u, r = _draws(G, F, 11)
+    G.renderer.inject_noise(jit, u)
+    frames, _ = render_orbit(G, ws, w_frames=F, batch=B)
+    cams, _ = orbit_cameras(F, device='cuda')
+    rk = {**OG.RENDERING_DEFAULTS, **dict(G.rendering_kwargs)}
+    for i in (0, 2):
+        ref = OG.synthesis(gen_sd, ws.cpu(), cams[i:i + 1].cpu(), rk, jitter=jit[i:i + 1].cpu(), u=u[i * r:(i + 1) * r].cpu())['image']
+        ref8 = (ref * 127.5 + 128).clamp(0, 255).to(torch.uint8)[0].permute(1, 2, 0)
+        d = (frames[i].cpu().int() - ref8.int()).abs()
+        print(f'frame {i}: max |d| {int(d.max())}, pixels differing {float((d > 0).float().mean()):.4f}')
+        assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.02
+
+
 def test_orbit_depth_clip_and_video_file(product_G):
     from spi_b200.utils.video_utils import gen_interp_video, render_orbit
     cv2 = pytest.importorskip('cv2')
