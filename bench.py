@@ -38,6 +38,11 @@ def parse():
     ap.add_argument('--warmup', type=int, default=6)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cpu-budget-s', type=float, default=420.0, help='wall budget of the timed part of the reference leg')
+    ap.add_argument('--config', type=int, default=1, choices=[1, 2, 3, 4],
+                    help='BASELINE.json configs[i]: 1 mir->RotBbox (headline), 2 sg->pti (PTI baseline), 3 = 1 with a distinct image AND camera per rank, '
+                         '4 = 1 at --depth/--nrr (ray-march stress; default 48+48 = "96 depth samples")')
+    ap.add_argument('--depth', type=int, nargs=2, default=None, metavar=('DC', 'DF'), help='coarse / importance samples per ray (config 4)')
+    ap.add_argument('--nrr', type=int, default=128, help='neural_rendering_resolution (config 4)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     return ap.parse_args()
@@ -45,8 +50,23 @@ def parse():
 
 # ----------------------------------------------------------------------------- synthetic inputs (no oracle import here)
 
-def synthetic_inputs(seed=4):
-    """Target image, camera (yaw 0.3 so the mirror branch is active), parsing mask, landmarks -- host tensors."""
+YAWS = (0.3, -0.25, 0.4, -0.35, 0.5, -0.45, 0.6, -0.55)      # config 3: one camera per rank, |yaw| >= 0.2 keeps the mirror branch active
+
+
+def workload(args):
+    """(first_inv_type, G_1_type, (dc, df), nrr, text) of BASELINE.json configs[args.config]."""
+    depth = tuple(args.depth) if args.depth else ((48, 48) if args.config == 4 else DEPTH)
+    nrr = args.nrr if args.config == 4 else 128
+    if args.config == 2:
+        return 'sg', 'pti', depth, nrr, 'configs[2] PTI baseline: single 512^2 image per GPU, first_inv_type=sg -> G_1_type=pti'
+    txt = {1: 'configs[1]: single 512^2 image per GPU, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
+           3: 'configs[3]: one independent 512^2 image AND camera per GPU, first_inv_type=mir -> G_1_type=RotBbox, full SPI losses',
+           4: f'configs[4]: ray-march stress, {depth[0]}+{depth[1]} samples per ray, neural_rendering_resolution {nrr}, mir -> RotBbox'}[args.config]
+    return 'mir', 'RotBbox', depth, nrr, txt
+
+
+def synthetic_inputs(seed=4, yaw=0.3):
+    """Target image, camera (|yaw| >= 0.2 so the mirror branch is active), parsing mask, landmarks -- host tensors."""
     g = torch.Generator().manual_seed(seed)
     low = torch.randn(1, 3, 16, 16, generator=g)
     img = torch.nn.functional.interpolate(low, size=(512, 512), mode='bicubic', align_corners=False)
@@ -70,7 +90,7 @@ def synthetic_inputs(seed=4):
     q = np.linspace(0, 2 * np.pi, 21)[:20]
     pts[48:68] = np.stack([128 + 25 * np.cos(q), 185 + 9 * np.sin(q)], 1)
     from spi_b200.utils.camera_utils import cal_canonical_c
-    return dict(img=img, c=cal_canonical_c(0.3, 0.0, 1, 'cpu'), mask=m[None, None], lm=torch.from_numpy(pts)[None])
+    return dict(img=img, c=cal_canonical_c(yaw, 0.0, 1, 'cpu'), mask=m[None, None], lm=torch.from_numpy(pts)[None])
 
 
 class ClockSampler:
@@ -217,33 +237,44 @@ def render_fwd_bytes(dc, df, res=128):
 class OursJob:
     """mir projector followed by the RotBbox coach on one image, driven step by step through the public classes."""
 
-    def __init__(self, device, data):
+    def __init__(self, device, data, first='mir', stage2='RotBbox', depth=DEPTH, nrr=128):
         from spi_b200.configs import global_config, hyperparameters as hp, paths_config
         from spi_b200.criteria.bbox_cx_loss import BoxCXLoss
         from spi_b200.criteria.lpips.lpips import LPIPS
+        from spi_b200.training.coaches.pti_coach import SingleIDCoach
         from spi_b200.training.coaches.rot_bbox_cx_coach import RotBboxCoach, SPIState
         from spi_b200.training.projectors._common import LatentProjector
         from spi_b200.utils import load_utils
         global_config.device = device
         paths_config.EG3D_PATH = 'synthetic:0'
-        load_utils.DEPTH_OVERRIDE = DEPTH
-        hp.first_inv_type, hp.G_1_type = 'mir', 'RotBbox'
+        load_utils.DEPTH_OVERRIDE = tuple(depth)
+        self.first, self.stage2 = first, stage2
+        hp.first_inv_type, hp.G_1_type = first, stage2
         hp.pt_rot_lambda, hp.pt_mirror_rot_lambda, hp.pt_depth_lambda, hp.pt_tv_lambda = 0.1, 0.05, 1.0, 0.0
         hp.LPIPS_value_threshold = -1.0          # early exit disabled so every timed step does the full work
         torch.manual_seed(1)
         self.lpips = LPIPS(net_type='vgg').to(device).eval()
+        for l in self.lpips.lin:          # LPIPS lin weights are non-negative (SURVEY.md §8c: seeded U[0,1)); the sg stand-in takes their square root
+            l[1].weight.data.abs_()
         torch.manual_seed(2)
         self.cx = BoxCXLoss().to(device).eval()
-        coach = RotBboxCoach.__new__(RotBboxCoach)
+        cls = RotBboxCoach if stage2 == 'RotBbox' else SingleIDCoach
+        coach = cls.__new__(cls)
         coach.use_wandb, coach.data_loader, coach.w_pivots, coach.image_counter = False, None, {}, 0
         coach.lpips_loss, coach.box_cx_loss = self.lpips, self.cx
         coach.restart_training()
+        for g_ in (coach.G, coach.original_G):
+            g_.neural_rendering_resolution = nrr
         self.coach, self.SPIState, self.LatentProjector = coach, SPIState, LatentProjector
         self.device = device
         self.host = data
         self.pinned = {k: v.pin_memory() for k, v in data.items()}
         self.upload()
-        self.proj = LatentProjector(coach.G, self.dev['img'], self.dev['c'], 'mir', lpips_func=self.lpips, num_steps=500, w_avg_samples=600)
+        vgg = None
+        if first == 'sg':          # vgg16.pt stand-in: same trunk as LPIPS; its lin weights enter under a square root, so they must be >= 0
+            vgg = load_utils.load_sg_vgg(device).load_weights(self.lpips.net.layers.state_dict(), [l[1].weight.detach() for l in self.lpips.lin])
+        self.proj = LatentProjector(coach.G, self.dev['img'], self.dev['c'], first, lpips_func=self.lpips, vgg16=vgg, num_steps=500, w_avg_samples=600)
+        self.proj.G.neural_rendering_resolution = nrr
         self.state = SPIState(self.dev['img'], self.dev['c'], self.dev['mask'], self.dev['lm'])
         self.w_pivot = None
         self.i_mir = 0
@@ -268,7 +299,10 @@ class OursJob:
         else:
             if self.w_pivot is None:
                 self.w_pivot = self.proj.result().detach().clone().requires_grad_(True)
-            res, _ = self.coach.train_step(idx, self.state, self.w_pivot)
+            if self.stage2 == 'RotBbox':
+                res, _ = self.coach.train_step(idx, self.state, self.w_pivot)
+            else:
+                res, _ = self.coach.train_step(self.w_pivot, self.dev['c'], self.dev['img'])
         if e2e:
             return float(res)          # device -> host read of the step's loss
         return res
@@ -298,9 +332,11 @@ def mix_of(sched):
     return n_mir, heavy, light
 
 
-def mix_text(sched):
+def mix_text(sched, first='mir', stage2='RotBbox'):
     n_mir, heavy, light = mix_of(sched)
-    return f'{n_mir} mir + {heavy + light} RotBbox iterations ({heavy} with i%4==0: rot + mirror + depth branches, {light} plain)'
+    if stage2 != 'RotBbox':
+        return f'{n_mir} {first} + {heavy + light} {stage2} iterations'
+    return f'{n_mir} {first} + {heavy + light} RotBbox iterations ({heavy} with i%4==0: rot + mirror + depth branches, {light} plain)'
 
 
 def traffic_from_profiles(kernel):
@@ -330,8 +366,9 @@ def run_ours(args):
         dist.init_process_group('nccl', device_id=torch.device(device))
         torch.set_num_threads(max(1, (os.cpu_count() or 8) // world))     # N ranks share the host cores
     _lib.load()
-    data = synthetic_inputs(seed=4 + rank)       # one independent image per rank
-    job = OursJob(device, data)
+    first, stage2, depth, nrr, wtext = workload(args)
+    data = synthetic_inputs(seed=4 + rank, yaw=YAWS[rank % len(YAWS)] if args.config == 3 else 0.3)       # one independent image per rank
+    job = OursJob(device, data, first, stage2, depth, nrr)
     k, w = max(1, args.steps), max(0, args.warmup)
     sched = schedule(k)
     # warm-up: at least W iterations and at least one of every iteration kind (each kind is captured as a CUDA graph on first use)
@@ -366,7 +403,9 @@ def run_ours(args):
         return ms, per_rank, clocks
 
     for item in warm:
-        job.step(item)
+        last = job.step(item)
+    if not bool(torch.isfinite(last if not isinstance(last, dict) else last['dist']).all()):
+        raise SystemExit('bench.py: non-finite loss after the warm-up iterations')
     ms, per_rank, clocks = timed(e2e=False)
     value = world * k / (ms / 1e3)
     e2e = None
@@ -381,7 +420,7 @@ def run_ours(args):
     from spi_b200.configs import global_config
 
     def kind_of(item):
-        return 'mir' if item[0] == 'mir' else ('rot_heavy' if item[1] % 4 == 0 else 'rot_light')
+        return 'mir' if item[0] == 'mir' else ('rot_heavy' if (item[1] % 4 == 0 and stage2 == 'RotBbox') else 'rot_light')
 
     global_config.use_cuda_graphs = False
     timer = KernelTimer()
@@ -435,10 +474,10 @@ def run_ours(args):
     rf, rb = timer.summary('render_fwd'), timer.summary('render_bwd')
     roofline = None
     if rb:
-        bytes_per_img = render_bwd_bytes(*DEPTH)
+        bytes_per_img = render_bwd_bytes(*depth, res=nrr)
         ach = bytes_per_img / (rb['ms_per_unit'] * 1e-3) / 1e9
         tf32_peak = bf16_peak() / 2.0
-        gf_bwd, gf_fwd = render_gflop(*DEPTH)
+        gf_bwd, gf_fwd = render_gflop(*depth, res=nrr)
         tr_b, tr_b_src = traffic_from_profiles('render_bwd')
         tr_f, tr_f_src = traffic_from_profiles('render_fwd')
         roofline = {'kernel': 'render backward (spi_render_backward*, spi_b200/csrc/raymarch_tc_bwd.cuh)', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
@@ -452,7 +491,7 @@ def run_ours(args):
                     'note': 'arithmetic intensity ~340 FLOP/B and 12 x 128-byte texel lines gathered AND scattered per sample: '
                             'the kernel is L2-gather / issue bound, the HBM fraction is reported because the contract asks for it'}
         if rf:
-            fb = render_fwd_bytes(*DEPTH)
+            fb = render_fwd_bytes(*depth, res=nrr)
             roofline['render_fwd'] = {'ms_per_image': rf['ms_per_unit'], 'achieved_GBps': fb / (rf['ms_per_unit'] * 1e-3) / 1e9,
                                       'frac_of_hbm_peak': fb / (rf['ms_per_unit'] * 1e-3) / 1e9 / peak, 'algorithmic_bytes_per_image': fb,
                                       'traffic': tr_f, 'traffic_source': tr_f_src, 'tf32_tflops_3x_issued': 3 * gf_fwd / rf['ms_per_unit'],
@@ -501,14 +540,14 @@ def run_ours(args):
         roofline['decoder_grad_gemms_ms_per_image'] = dg['ms_per_unit'] if dg else None
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(job, sched)
+        cpu = cpu_baseline(job, sched, first, stage2, depth, nrr)
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': k, 'warmup': len(warm), 'ms_per_step': ms / k,
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (TF32 tensor-core contractions)',
                 'data': 'synthetic', 'impl': 'ours', 'conv_engine': os.environ.get('SPI_CONV_ENGINE', 'tc2'),
-                'config': {'workload': 'configs[1]: single 512^2 image per GPU, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
+                'config': {'workload': wtext,
                            'execution': 'each iteration replayed as a captured CUDA graph; roofline kernels timed with CUDA events: ' + timing_source,
-                           'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': mix_text(sched),
+                           'depth_samples': f'{depth[0]}+{depth[1]}', 'neural_rendering_resolution': nrr, 'step_mix': mix_text(sched, first, stage2),
                            'dedup': 'views of one iteration share w_pivot: the camera-independent tri-plane backbone is evaluated once per iteration and the SR net is skipped for the depth-only views (identical results, tests/test_gpu_loop.py::test_shared_backbone_equals_per_view_evaluation); global_config.share_backbone=False restores the literal structure',
                            'l2_policy': 'per-step working set (weights + activations, > 1 GB) exceeds the 126 MB L2', 'images_per_gpu': 1},
                 'per_rank_it_s': [k / (m / 1e3) for m in per_rank],
@@ -521,7 +560,7 @@ def run_ours(args):
 
 # ----------------------------------------------------------------------------- CPU arm (oracle port of the reference)
 
-def oracle_job(job_or_none, rank=0):
+def oracle_job(job_or_none, rank=0, depth=DEPTH, yaw=0.3):
     """Build the oracle Projector / Coach on the same weights and inputs as the GPU job."""
     from oracle import loops as OL
     from oracle import generator as OG
@@ -535,38 +574,45 @@ def oracle_job(job_or_none, rank=0):
         from spi_b200.criteria.bbox_cx_loss import BoxCXLoss
         from spi_b200.criteria.lpips.lpips import LPIPS
         from spi_b200.utils import load_utils
-        load_utils.DEPTH_OVERRIDE = DEPTH
+        load_utils.DEPTH_OVERRIDE = tuple(depth)
         sd = load_utils.build_generator(device='cpu', seed=0).state_dict()
         torch.manual_seed(1)
         lp = LPIPS(net_type='vgg')
+        for l in lp.lin:
+            l[1].weight.data.abs_()
         torch.manual_seed(2)
         cx = BoxCXLoss()
         vgg, lin = lp.net.layers.state_dict(), [l[1].weight.detach() for l in lp.lin]
         vgg19 = cx.vgg_model.slice1.state_dict()
-        data = synthetic_inputs(seed=4 + rank)
+        data = synthetic_inputs(seed=4 + rank, yaw=yaw)
     nets = {'vgg16': vgg, 'lin': lin, 'vgg19': vgg19}
-    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=DEPTH[0], depth_resolution_importance=DEPTH[1])
+    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=depth[0], depth_resolution_importance=depth[1])
     return OL, sd, nets, rk, data
 
 
-def cpu_baseline(job, sched):
+def cpu_baseline(job, sched, first='mir', stage2='RotBbox', depth=DEPTH, nrr=128):
     """The oracle (CPU restatement of the reference, kind='port') on the host cores: ONE iteration of each kind of the timed
     schedule (mir, RotBbox i%4==0, RotBbox plain) is timed and the three are weighted by the schedule's own mix, so the figure is
     the same workload `value` measures (and the one `--impl reference` runs in full)."""
+    if nrr != 128:
+        return {'value': None, 'unit': UNIT, 'cores': 0, 'kind': 'port', 'sample': 'the oracle covers neural_rendering_resolution = 128 only (load_utils.py:31)'}
     torch.set_num_threads(os.cpu_count() or 1)
-    OL, sd, nets, rk, data = oracle_job(job)
+    OL, sd, nets, rk, data = oracle_job(job, depth=depth)
     w = torch.randn(1, 14, 512, generator=torch.Generator().manual_seed(5)) * 0.5
-    coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind='RotBbox', rk=rk, noise=OL.NoiseSource(0))
-    proj = OL.Projector(sd, data['img'], data['c'], nets, kind='mir', num_steps=500, rk=rk, noise=OL.NoiseSource(1), w_avg_samples=600)
+    coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind=stage2, rk=rk, noise=OL.NoiseSource(0))
+    proj = OL.Projector(sd, data['img'], data['c'], nets, kind=first, num_steps=500, rk=rk, noise=OL.NoiseSource(1), w_avg_samples=600)
     n_mir, heavy, light = mix_of(sched)
     t = {}
     t0 = time.perf_counter(); coach.step(1); t['light'] = time.perf_counter() - t0
     t0 = time.perf_counter(); proj.step(25); t['mir'] = time.perf_counter() - t0
-    t0 = time.perf_counter(); coach.step(4); t['heavy'] = time.perf_counter() - t0
+    if stage2 == 'RotBbox':
+        t0 = time.perf_counter(); coach.step(4); t['heavy'] = time.perf_counter() - t0
+    else:
+        t['heavy'] = t['light']
     total = n_mir * t['mir'] + heavy * t['heavy'] + light * t['light']
     return {'value': len(sched) / total, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': f"one iteration of each kind timed once (mir {t['mir']:.2f} s, RotBbox i%4==0 {t['heavy']:.2f} s, RotBbox plain {t['light']:.2f} s), "
-                      f'weighted by the timed schedule ({mix_text(sched)}); depth 32+32, oracle/loops.py on torch CPU fp32'}
+            'sample': f"one iteration of each kind timed once ({first} {t['mir']:.2f} s, {stage2} i%4==0 {t['heavy']:.2f} s, {stage2} plain {t['light']:.2f} s), "
+                      f'weighted by the timed schedule ({mix_text(sched, first, stage2)}); depth {depth[0]}+{depth[1]}, oracle/loops.py on torch CPU fp32'}
 
 
 def interleave(sched):
@@ -590,11 +636,15 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count() or 1)
-    OL, sd, nets, rk, data = oracle_job(None)
+    first, stage2, depth, nrr, wtext = workload(args)
+    if nrr != 128:
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU oracle covers neural_rendering_resolution = 128 only (load_utils.py:31)'}), flush=True)
+        return
+    OL, sd, nets, rk, data = oracle_job(None, depth=depth, yaw=YAWS[0] if args.config == 3 else 0.3)
     t_all = time.perf_counter()
-    proj = OL.Projector(sd, data['img'], data['c'], nets, kind='mir', num_steps=500, rk=rk, noise=OL.NoiseSource(1), w_avg_samples=600)
+    proj = OL.Projector(sd, data['img'], data['c'], nets, kind=first, num_steps=500, rk=rk, noise=OL.NoiseSource(1), w_avg_samples=600)
     w = proj.result().clone()
-    coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind='RotBbox', rk=rk, noise=OL.NoiseSource(2))
+    coach = OL.Coach(sd, w, data['img'], data['c'], data['mask'], data['lm'], nets, kind=stage2, rk=rk, noise=OL.NoiseSource(2))
     n_warm = max(0, args.warmup)
     for j in range(n_warm):                         # warm-up: plain iterations (allocator, thread pool, oneDNN primitive caches)
         if j % 3 == 0:
@@ -618,11 +668,11 @@ def run_reference(args):
     value = n / dt
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': n, 'warmup': n_warm, 'ms_per_step': dt / n * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
-            'config': {'workload': 'configs[1]: single 512^2 image, first_inv_type=mir -> G_1_type=RotBbox (rot 0.1, mirror 0.05, depth 1)',
-                       'depth_samples': '32+32', 'neural_rendering_resolution': 128, 'step_mix': mix_text(ran),
+            'config': {'workload': wtext,
+                       'depth_samples': f'{depth[0]}+{depth[1]}', 'neural_rendering_resolution': nrr, 'step_mix': mix_text(ran, first, stage2),
                        'truncated_by_budget': n < len(sched)},
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
-                             'sample': f'{mix_text(ran)}, {dt:.1f} s wall, setup + {n_warm} warm-up iterations ({t0 - t_all:.1f} s) excluded'},
+                             'sample': f'{mix_text(ran, first, stage2)}, {dt:.1f} s wall, setup + {n_warm} warm-up iterations ({t0 - t_all:.1f} s) excluded'},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
 

@@ -36,7 +36,7 @@ constexpr int SMW_P = UST * U_BYTES;          // patch ring: (total - U) / patch
 constexpr int SMW_PREGION = 96 * 1024;        // 96 KB of patches (2 x 36 KB halo patches, or 5 x 16 KB for 1x1)
 constexpr int SMW_BAR = SMW_P + SMW_PREGION;
 constexpr int SMW_TOTAL = SMW_BAR + 1024 + 1024;
-constexpr int MAXWV = 4, MAXWM = 9, MAXWO = 9, MAXPS = 5;
+constexpr int MAXWV = 4, MAXWM = 3, MAXWO = 9, MAXPS = 5;
 
 struct WMma { int dy, dx, n, dcol; };                     // patch row / pixel shift, N (32 x taps in the instruction), accumulator column
 struct WView { int vmap, oy, ox, nmma; WMma mma[MAXWM]; };
@@ -50,8 +50,7 @@ struct WgradArgs {
     int nviews, nouts;
     int n, groups, imgs_per_group, tiles_x, tiles_y, tiles_per_group, tiles_per_item, splits;
     int mblocks, cchunks, uchunks_total;      // 128-blocks of U channels, 32-chunks of V channels, 32-chunks of U channels
-    int px, patch_bytes, nps, patch_stride, dbg;
-    float* dump;
+    int px, patch_bytes, nps, patch_stride;
     int* err;
 };
 
@@ -195,12 +194,8 @@ __global__ void __launch_bounds__(NTW, 1) conv_wgrad_tc2_kernel(const __grid_con
                     *reinterpret_cast<float4*>(stg + swz(row, j)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
                 fence_async_smem();
                 named_bar_sync(1, 128);
-                if (a.dump && blockIdx.x == 0) {            // debug: raw accumulators of item 0, [out block][channel row][32]
-                    for (int j = 0; j < 32; j++) a.dump[(k * 128 + row) * 32 + j] = v[j];
-                }
                 if (leader) {
-                    if (a.dbg & 16) tma_store_4d(&a.omap, stg, cc * 32, a.outs[k].tap, mb * 128, g);
-                    else tma_reduce_add_4d_w(&a.omap, stg, cc * 32, a.outs[k].tap, mb * 128, g);
+                    tma_reduce_add_4d_w(&a.omap, stg, cc * 32, a.outs[k].tap, mb * 128, g);
                     tma_commit_group();
                 }
             }
@@ -252,12 +247,8 @@ bool map_img(CUtensorMap* m, const float* ptr, int c, long long wv, long long hv
 //                   mode 1: y = stride-2 transposed 3x3 convolution of x [N][H][W][Ci] (spi_conv_transpose2d_s2_tc2); dy [N][2H+1][2W+1][Co];
 //                           dw is written TRANSPOSED as [G][Ci][9][Co]  (U = x, V = the four parity views of dy).
 // G = N when per_sample (one gradient per image), else 1 (summed over the batch).  dw is overwritten.
-static float* g_wgrad_dump = nullptr;
-extern "C" void spi_conv_wgrad_tc2_debug_dump(float* buf) { g_wgrad_dump = buf; }
-
-extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode_flags,
+extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
                                   cudaStream_t stream) {
-    const int mode = mode_flags & 1;
     SPI_CHECK_ARG(x && dy && dw, "spi_conv_wgrad_tc2: null tensor");
     SPI_CHECK_ARG(ci % 32 == 0 && co % 32 == 0 && ci >= 32 && co >= 32, "spi_conv_wgrad_tc2: channel counts must be multiples of 32 (ci=%d co=%d)", ci, co);
     SPI_CHECK_ARG((mode == 0 && (k == 1 || k == 3)) || (mode == 1 && k == 3), "spi_conv_wgrad_tc2: unsupported mode %d / k %d", mode, k);
@@ -271,7 +262,6 @@ extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, in
     const float* U = mode == 0 ? dy : x;
     const float* V = mode == 0 ? x : dy;
     a.n = n; a.groups = groups; a.imgs_per_group = n / groups;
-    a.dbg = mode_flags; a.dump = g_wgrad_dump;
     a.tiles_x = cdiv(wd, 8); a.tiles_y = cdiv(h, 16);
     a.tiles_per_group = a.tiles_x * a.tiles_y * a.imgs_per_group;
     a.mblocks = cdiv(cu, 128); a.cchunks = cv / 32; a.uchunks_total = cu / 32;
@@ -292,11 +282,7 @@ extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, in
         WView& v = a.views[0];
         v.vmap = 0; v.oy = -halo; v.ox = -halo; v.nmma = 0;
         for (int ky = 0; ky < k; ky++) {
-            if (mode_flags & 32) {             // debug: one instruction per tap (N = 32), no folding of the kx taps into N
-                for (int kx = 0; kx < k; kx++) v.mma[v.nmma++] = WMma{ky, kx, 32, ky * 32 * k + kx * 32};
-            } else {
-                v.mma[v.nmma++] = WMma{ky, 0, 32 * k, ky * 32 * k};
-            }
+            v.mma[v.nmma++] = WMma{ky, 0, 32 * k, ky * 32 * k};          // the k taps of this row in one instruction (N = 32 k)
             for (int kx = 0; kx < k; kx++) a.outs[a.nouts++] = WOut{ky * 32 * k + kx * 32, ky * k + kx};
         }
     } else {
@@ -341,7 +327,7 @@ extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, in
         }
         configured = true;
     }
-    if (!(mode_flags & 16)) cudaMemsetAsync(dw, 0, (size_t)groups * cu * taps * cv * 4, stream);
+    cudaMemsetAsync(dw, 0, (size_t)groups * cu * taps * cv * 4, stream);
     conv_wgrad_tc2_kernel<<<columns * a.splits, NTW, SMW_TOTAL, stream>>>(a);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("spi_conv_wgrad_tc2");

@@ -135,36 +135,6 @@ def check_wgrad(n, ci, co, h, wd, k, per_sample, mode):
     return rel(mine, ref), err
 
 
-def debug_wgrad():
-    """Smallest case (one item, one tile): dump the accumulators and compare every stage against a direct evaluation."""
-    import ctypes
-    L.spi_conv_wgrad_tc2_debug_dump.argtypes = [ctypes.c_void_p]
-    L.spi_conv_wgrad_tc2_debug_dump.restype = None
-    n, ci, co, h, wd, k = 1, 32, 32, 16, 8, 3
-    gen = torch.Generator().manual_seed(11)
-    x = torch.randn(n, ci, h, wd, generator=gen).cuda().contiguous(memory_format=CL)
-    dy = torch.randn(n, co, h, wd, generator=gen).cuda().contiguous(memory_format=CL)
-    # reference dw[o][ky][kx][i] = sum_p dy[p, o] * x[p + (ky-1, kx-1), i]
-    xp = F.pad(x.double(), (1, 1, 1, 1))
-    ref = torch.zeros(co, 3, 3, ci, dtype=torch.float64, device='cuda')
-    for ky in range(3):
-        for kx in range(3):
-            ref[:, ky, kx, :] = torch.einsum('ohw,ihw->oi', dy[0].double(), xp[0, :, ky:ky + h, kx:kx + wd])
-    for flags in (0, 32, 16, 48):
-        dump = torch.full((9 * 128 * 32,), float('nan'), device='cuda')
-        L.spi_conv_wgrad_tc2_debug_dump(dump.data_ptr())
-        dw = torch.full((1, co, 9, ci), 7.0, device='cuda')
-        _lib.check(L.spi_conv_wgrad_tc2(_lib.ptr(x), _lib.ptr(dy), _lib.ptr(dw), n, h, wd, ci, co, k, 0, flags, _lib.stream()))
-        err = L.spi_tc_error()
-        L.spi_conv_wgrad_tc2_debug_dump(None)
-        d = dump.view(9, 128, 32)[:, :co, :]                       # [tap][o][i]
-        dref = ref.view(co, 9, ci).permute(1, 0, 2)
-        print(f'  flags {flags}: err {err} | dump finite {bool(torch.isfinite(d).all())} absmax {float(d.abs().max()):.3f} ref absmax {float(dref.abs().max()):.3f} '
-              f'rel(dump, ref) {rel(d, dref):.3e} | dw absmax {float(dw.abs().max()):.3f} rel(dw, ref) {rel(dw.view(co, 9, ci), ref.view(co, 9, ci)):.3e}', flush=True)
-        for tap in (0, 4, 8):
-            print(f'     tap {tap}: rel {rel(d[tap], dref[tap]):.3e}  dump[0,:4] {d[tap, 0, :4].tolist()}  ref[0,:4] {dref[tap, 0, :4].tolist()}', flush=True)
-
-
 def probe_wgrad():
     print('== weight gradient (MN-major operands, kx taps folded into N)', flush=True)
     for case in ((1, 32, 32, 16, 8, 3, False, 0), (1, 32, 128, 16, 16, 3, False, 0), (2, 64, 128, 40, 56, 3, True, 0), (2, 64, 96, 24, 24, 1, False, 0),
@@ -316,6 +286,22 @@ def small_study():
         print(f'  {n}x{ci}->{co} @{h}^2: plain {t0:.3f} ms {gf / t0:.0f} TF/s | fused epilogue {t1:.3f} ms {gf / t1:.0f} TF/s', flush=True)
 
 
+def ncu_target():
+    """Three launches each of the big-layer forward, weight-gradient and N = 256 kernels (ncu --set full target)."""
+    x, w, wl = make(1, 128, 128, 512, 512, 3, False)
+    dy = torch.randn(1, 128, 512, 512, device='cuda').contiguous(memory_format=CL)
+    y = torch.empty(1, 128, 512, 512, device='cuda', memory_format=CL)
+    for _ in range(3):
+        _lib.check(L.spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), 1, 512, 512, 128, 128, 3, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0, _lib.stream()))
+    for _ in range(3):
+        wgrad(x, dy, 128, 128, 3, False, 0)
+    x2, w2, _ = make(4, 256, 256, 256, 256, 3, False)
+    y2 = torch.empty(4, 256, 256, 256, device='cuda', memory_format=CL)
+    for _ in range(3):
+        _lib.check(L.spi_conv2d_tc2(_lib.ptr(x2), _lib.ptr(w2), _lib.ptr(y2), 4, 256, 256, 256, 256, 3, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0, _lib.stream()))
+    torch.cuda.synchronize()
+
+
 def reps_study():
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
@@ -344,6 +330,9 @@ def reps_study():
 
 
 if __name__ == '__main__':
+    if '--ncu-target' in sys.argv:
+        ncu_target()
+        sys.exit(0)
     if '--small' in sys.argv:
         small_study()
         sys.exit(0)
@@ -355,9 +344,6 @@ if __name__ == '__main__':
         sys.exit(0)
     if '--one' in sys.argv:
         one()
-        sys.exit(0)
-    if '--wgrad-debug' in sys.argv:
-        debug_wgrad()
         sys.exit(0)
     if '--wgrad' in sys.argv:
         probe_wgrad()
