@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             named_bar_sync(1, 128);
             if (leader) mbar_arrive(&tempty[buf]);
         }
-        if (leader) tma_wait_all();
+        if (leader) tma_wait_group_read<0>();      // the staging tiles have been read; the stores themselves complete with the grid (as CUTLASS' tma_store_wait<0>)
     }
     fence_before();
     __syncthreads();
@@ -425,11 +425,13 @@ int launch2(Conv2Args& a, cudaStream_t stream) {
 // Tile shape.  Cout % 256 == 0 and a map large enough to fill the chip: one 128-pixel M tile x 256 output channels (an MMA of N = 256
 // reads 96 B/clk of operands from shared memory against 128 B/clk at N = 128: the weight-tile re-read is what bounds N = 128);
 // otherwise two M tiles x (at most) 128 channels, which halves the weight traffic per pixel instead.
-void common_args(Conv2Args& a, int n, int ci, int co, int per_sample, int wv_out, int hv_out, int flags) {
+void common_args(Conv2Args& a, int n, int ci, int co, int per_sample, int wv_out, int hv_out, int flags, bool allow_split = true) {
     memset(&a, 0, sizeof(a));
     a.n = n; a.ci = ci; a.co = co; a.per_sample = per_sample ? 1 : 0;
     const long long t256 = (long long)cdiv(wv_out, 8) * cdiv(hv_out, 16) * n * (co / 256);
-    if (co % 256 == 0 && t256 >= spi_num_sms() * 3 / 4 && !(flags & 128)) {
+    // (small maps reach the chip-filling tile count by splitting Cin, which the caller must allow: no fused epilogue then)
+    const bool fill = t256 >= spi_num_sms() * 3 / 4 || (allow_split && !(flags & 32) && t256 * (ci / 32) >= spi_num_sms() / 2 && t256 >= 8);
+    if (co % 256 == 0 && fill && !(flags & 128)) {
         a.bn = 256; a.mt = 1;
     } else {
         a.bn = pick_bn(co);
@@ -465,12 +467,12 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
     SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "spi_conv2d_tc2: tensors must be 16-byte aligned");
     const int rnd = (flags & 1) ? 0 : 1;
     Conv2Args a;
-    common_args(a, n, ci, co, per_sample, wd, h, flags);
+    const bool epi = bias || noise || act != 0 || gain != 1.f || clamp >= 0.f;
+    common_args(a, n, ci, co, per_sample, wd, h, flags, !epi);
     const int halo = k / 2;
     a.px = a.mt * 8 + (halo ? ((flags & 64) ? 8 : 2 * halo) : 0);
     const int rows = 16 + 2 * halo;
     a.patch_bytes = rows * a.px * 128;
-    const bool epi = bias || noise || act != 0 || gain != 1.f || clamp >= 0.f;
     plan_tiles(a, cdiv(wd, a.mt * 8) * cdiv(h, 16) * n, !epi && !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
     if (!map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) ||
         !map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0) ||

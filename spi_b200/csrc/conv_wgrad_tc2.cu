@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NTW, 1) conv_wgrad_tc2_kernel(const __grid_con
                     tma_commit_group();
                 }
             }
-            if (leader) tma_wait_all();
+            if (leader) tma_wait_group_read<0>();      // the staging tiles have been read; the stores themselves complete with the grid (as CUTLASS' tma_store_wait<0>)
         }
     }
     fence_before();
