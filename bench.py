@@ -505,6 +505,13 @@ def run_ours(args):
             gbs = sm['units'] / (sm['ms_total'] * 1e-3) / 1e9
             streaming[tag] = {'launches': sm['launches'], 'achieved_GBps': gbs, 'frac_of_hbm_peak': gbs / peak, 'ms_total': sm['ms_total'],
                               'share_of_step_time': sm['ms_total'] / eager_ms}
+            det = []
+            for tg in timer.spans:
+                if tg.startswith(tag + '|'):
+                    d_ = timer.summary(tg)
+                    det.append((d_['ms_total'], tg[len(tag) + 1:], d_['launches'], d_['units'] / (d_['ms_total'] * 1e-3) / 1e9))
+            det.sort(reverse=True)
+            streaming[tag]['by_shape_top'] = [{'call': nm, 'launches': ln, 'ms_total': round(ms_, 3), 'GBps': round(gb_, 0)} for ms_, nm, ln, gb_ in det[:8]]
     cv = timer.summary('conv')
     conv = None
     if cv:

@@ -78,7 +78,7 @@ def _plugin_bias_act(x, b, xref, yref, dy, grad, dim, act_idx, alpha, gain, clam
             raise RuntimeError('xref/yref/dy must have the same shape and layout as x')
     has_b = b is not None and b.numel() > 0
     nbytes = x.numel() * x.element_size() * (2 + (xref is not None) + (yref is not None) + (dy is not None))
-    with _lib.timed('bias_act', nbytes):
+    with _lib.timed('bias_act', nbytes, detail=f'grad{grad} act{act_idx} {tuple(x.shape)}'):
         _lib.check(_lib.load().spi_bias_act(
         _lib.ptr(x), _lib.ptr(b), _lib.ptr(xref), _lib.ptr(yref), _lib.ptr(dy), _lib.ptr(y), x.numel(),
             b.numel() if has_b else 1, x.stride(dim) if has_b else 1, _lib.dtype_code(x), grad, act_idx,
@@ -229,7 +229,7 @@ class _BlurBiasActNoise(torch.autograd.Function):
         y = torch.empty([n, c, oh, ow], dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
         nc = noise_const.contiguous() if noise_const is not None else None
         f = f.to(x.device).contiguous()
-        with _lib.timed('upfirdn2d', (x.numel() + y.numel()) * 4):
+        with _lib.timed('upfirdn2d', (x.numel() + y.numel()) * 4, detail=f'blur4+bias_act {tuple(x.shape)}'):
             _lib.check(_lib.load().spi_blur4_bias_act_noise(
                 _lib.ptr(x), _lib.ptr(f), _lib.ptr(y), _lib.ptr(b.contiguous()), _lib.ptr(nc), _lib.ptr(noise_strength), n, c, ih, iw,
                 _lib.strides4(x), _lib.strides4(y), padx0, padx1, pady0, pady1, int(bool(flip)), float(fir_gain), spec.cuda_idx, alpha,

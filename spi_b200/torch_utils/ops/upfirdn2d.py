@@ -77,7 +77,7 @@ def _plugin_upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, 
     if y.numel() == 0:
         return y
     f = f.to(x.device).contiguous()
-    with _lib.timed('upfirdn2d', (x.numel() + y.numel()) * x.element_size()):
+    with _lib.timed('upfirdn2d', (x.numel() + y.numel()) * x.element_size(), detail=f'up{upx} down{downx} f{fw} {tuple(x.shape)}->{oh}x{ow}'):
         _lib.check(_lib.load().spi_upfirdn2d(
             _lib.ptr(x), _lib.ptr(f), _lib.ptr(y), _lib.dtype_code(x), n, c, ih, iw, _lib.strides4(x), _lib.strides4(y),
             fh, fw, upx, upy, downx, downy, padx0, padx1, pady0, pady1, int(bool(flip)), float(gain), _lib.stream()))
