@@ -35,7 +35,7 @@ namespace {
 using namespace tc05;
 
 constexpr int NT2 = 256;
-constexpr int BST = 8;                        // most weight stages
+constexpr int BST = 16;                       // most weight stages
 constexpr int STG_BYTES = 128 * 128;          // epilogue staging tile (128 pixels x 32 channels)
 constexpr int MAXV = 4, MAXP = 4, MAXT = 9;
 
@@ -51,7 +51,7 @@ struct Conv2Args {
     CUtensorMap wmap;
     Program prog[MAXP];
     int nprog, total;
-    int n, ci, co, bn, tiles_o, mt, px, patch_bytes, per_sample, dbg, splitk, cps, npb, patch_stride, nbst, b_stride, sm_b, sm_stg;
+    int n, ci, co, bn, tiles_o, mt, px, patch_bytes, per_sample, dbg, splitk, cps, npb, patch_stride, nbst, b_stride, sm_b, sm_stg, pair;
     const float* bias; const float* noise; const float* noise_strength;
     int noise_w, out_h, out_w;
     int act; float slope, gain, clamp;
@@ -81,6 +81,48 @@ __device__ __forceinline__ void tma_reduce_add_4d(const void* tmap, const void* 
                  : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) helpers: two CTAs of a cluster on neighbouring SMs execute ONE M = 256 MMA; each holds its own 128 rows
+// of A and half of the B tile, the issuing (rank 0) CTA's barriers collect the TMA bytes of both, tcgen05.commit multicasts the
+// "stage free" / "accumulator ready" arrivals to both.  Shared-memory addresses of rank 1 differ from rank 0's by bit 24.
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const void* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tmap), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const void* tmap, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(tmap), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void mma_lohi_2sm(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}\n" ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrive (once the MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void commit_pair(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {          // arrive on rank 0's copy of the barrier from either CTA
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
 struct TileCoord { int q, n, ty, tx, ot, ks; };
 __device__ __forceinline__ TileCoord decode_tile(const Conv2Args& a, int t) {
     TileCoord c;
@@ -96,6 +138,7 @@ __device__ __forceinline__ TileCoord decode_tile(const Conv2Args& a, int t) {
     return c;
 }
 
+template <bool PAIR>
 __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant__ Conv2Args a) {
     extern __shared__ uint8_t raw[];
     const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
@@ -109,6 +152,10 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
     uint32_t* slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // PAIR: rank of this CTA in its pair, tile loop over pairs; each CTA owns ONE 8-pixel-wide M tile (a.mt == 1) at x + 8 * rank
+    const int rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int xmul = PAIR ? 16 : a.mt * 8;
     // per-program step list {A offset inside the patch (16-byte units), weight tap, flags, patch x/y origin}: the hot loops read it
     // with one LDS instead of chasing the kernel parameters through constant-memory loads
     int4* steps = reinterpret_cast<int4*>(sm + SM_BAR + 512);           // [MAXP][MAXV * MAXT]
@@ -129,29 +176,30 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
     }
     if (tid == 0) {
         for (int s = 0; s < MAXPB; s++) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
-        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&tfull[s], 1); mbar_init(&tempty[s], PAIR ? 2 : 1); }
         for (int s = 0; s < BST; s++) { mbar_init(&full_b[s], 1); mbar_init(&empty_b[s], 1); }
         fence_mbar_init();
         for (int i = 0; i < MAXV; i++) tma_prefetch_desc(&a.amap[i]);
         for (int i = 0; i < a.nprog; i++) tma_prefetch_desc(&a.omap[i]);
         tma_prefetch_desc(&a.wmap);
     }
-    if (warp == 3) { __syncwarp(); tmem_alloc(slot, 512); }
+    if (warp == 3) { __syncwarp(); if (PAIR) tmem_alloc_2sm(slot, 512); else tmem_alloc(slot, 512); }
     fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();          // both CTAs' barriers are initialised before any remote arrival / TMA signal
     fence_after();
     const uint32_t tm = *slot;
     const int cchunks = a.ci >> 5;
-    const uint32_t b_bytes = (uint32_t)a.bn * 128u;
+    const uint32_t b_bytes = (PAIR ? 64u : (uint32_t)a.bn) * 128u;
 
     if (warp == 0) {
         if (lane == 0) {
             int pb = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+            for (int t = tile0; t < a.total; t += tstride) {
                 const TileCoord c = decode_tile(a, t);
                 const int4* st = steps + c.q * MAXV * MAXT;
                 const int ns = nsteps[c.q];
-                const int x0 = c.tx * a.mt * 8, y0 = c.ty * 16;
+                const int x0 = c.tx * xmul + rank * 8, y0 = c.ty * 16;
                 const int c1 = min(cchunks, (c.ks + 1) * a.cps);
                 for (int cc = c.ks * a.cps; cc < c1; cc++)
                     for (int j = 0; j < ns; j++) {
@@ -159,8 +207,13 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                         if (!(sp.z & 1)) continue;
                         const int ox = (int)(short)(sp.w & 0xffff), oy = (int)(short)((unsigned)sp.w >> 16);
                         if (!mbar_wait_bounded(&empty_a[pb], ph ^ 1)) { atomicExch(a.err, 11); return; }
-                        mbar_expect_tx(&full_a[pb], (uint32_t)a.patch_bytes);
-                        tma_load_4d(sm + SM_PATCH + pb * a.patch_stride, &a.amap[(sp.z >> 2) & 3], cc * 32, x0 + ox, y0 + oy, c.n, &full_a[pb]);
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(&full_a[pb], 2u * (uint32_t)a.patch_bytes);      // both CTAs' patches land on rank 0's barrier
+                            tma_load_4d_2sm(sm + SM_PATCH + pb * a.patch_stride, &a.amap[(sp.z >> 2) & 3], cc * 32, x0 + ox, y0 + oy, c.n, &full_a[pb]);
+                        } else {
+                            mbar_expect_tx(&full_a[pb], (uint32_t)a.patch_bytes);
+                            tma_load_4d(sm + SM_PATCH + pb * a.patch_stride, &a.amap[(sp.z >> 2) & 3], cc * 32, x0 + ox, y0 + oy, c.n, &full_a[pb]);
+                        }
                         if (++pb == a.npb) { pb = 0; ph ^= 1; }
                     }
             }
@@ -168,25 +221,30 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0) {
             int s = 0; uint32_t ph = 0;
-            for (int t = blockIdx.x; t < a.total; t += gridDim.x) {
+            for (int t = tile0; t < a.total; t += tstride) {
                 const TileCoord c = decode_tile(a, t);
                 const int4* st = steps + c.q * MAXV * MAXT;
                 const int ns = nsteps[c.q];
-                const int wrow = (a.per_sample ? c.n * a.co : 0) + c.ot * a.bn;
+                const int wrow = (a.per_sample ? c.n * a.co : 0) + c.ot * a.bn + (PAIR ? rank * 64 : 0);
                 const int c1 = min(cchunks, (c.ks + 1) * a.cps);
                 for (int cc = c.ks * a.cps; cc < c1; cc++)
                     for (int j = 0; j < ns; j++) {
                         const int wtap = st[j].y;
                         if (!mbar_wait_bounded(&empty_b[s], ph ^ 1)) { atomicExch(a.err, 12); return; }
-                        mbar_expect_tx(&full_b[s], b_bytes);
-                        tma_load_3d(sm + a.sm_b + s * a.b_stride, &a.wmap, cc * 32, wtap, wrow, &full_b[s]);
+                        if (PAIR) {
+                            if (rank == 0) mbar_expect_tx(&full_b[s], 2u * b_bytes);
+                            tma_load_3d_2sm(sm + a.sm_b + s * a.b_stride, &a.wmap, cc * 32, wtap, wrow, &full_b[s]);
+                        } else {
+                            mbar_expect_tx(&full_b[s], b_bytes);
+                            tma_load_3d(sm + a.sm_b + s * a.b_stride, &a.wmap, cc * 32, wtap, wrow, &full_b[s]);
+                        }
                         if (++s == a.nbst) { s = 0; ph ^= 1; }
                     }
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
-            const uint32_t idesc = idesc_tf32(128, a.bn);
+        if (lane == 0 && rank == 0) {
+            const uint32_t idesc = idesc_tf32(PAIR ? 256 : 128, a.bn);
             // descriptor words: hi = SBO | version 1 | SWIZZLE_128B, lo = (address >> 4) | LBO 1; advancing an operand only adds to lo
             const uint32_t a_hi = (((uint32_t)a.px * 128u) >> 4) | (1u << 14) | (2u << 29);
             const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -194,7 +252,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             const uint32_t bb_lo0 = (smem_u32(sm + a.sm_b) >> 4) | (1u << 16);
             const int mt = a.mt;
             int s = 0, pb = 0, local = 0; uint32_t ph = 0, pph = 0;
-            for (int t = blockIdx.x; t < a.total; t += gridDim.x, local++) {
+            for (int t = tile0; t < a.total; t += tstride, local++) {
                 const TileCoord c = decode_tile(a, t);
                 const int4* st = steps + c.q * MAXV * MAXT;
                 const int ns = nsteps[c.q];
@@ -216,26 +274,33 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                         fence_after();
                         const uint32_t alo = pa_lo0 + (uint32_t)(pb * (a.patch_stride >> 4)) + (uint32_t)cur.x;
                         const uint32_t blo = bb_lo0 + (uint32_t)(s * (a.b_stride >> 4));
+                        if (PAIR) {
+                            mma_lohi_2sm(dcol, alo, a_hi, blo, b_hi, idesc, acc);
+                            mma_lohi_2sm(dcol, alo + 2, a_hi, blo + 2, b_hi, idesc, 1u);
+                            mma_lohi_2sm(dcol, alo + 4, a_hi, blo + 4, b_hi, idesc, 1u);
+                            mma_lohi_2sm(dcol, alo + 6, a_hi, blo + 6, b_hi, idesc, 1u);
+                        } else {
                         mma_lohi(dcol, alo, a_hi, blo, b_hi, idesc, acc);
                         mma_lohi(dcol, alo + 2, a_hi, blo + 2, b_hi, idesc, 1u);
                         mma_lohi(dcol, alo + 4, a_hi, blo + 4, b_hi, idesc, 1u);
                         mma_lohi(dcol, alo + 6, a_hi, blo + 6, b_hi, idesc, 1u);
-                        if (mt == 2) {
+                        }
+                        if (!PAIR && mt == 2) {
                             mma_lohi(dcol + 128, alo + 64, a_hi, blo, b_hi, idesc, acc);
                             mma_lohi(dcol + 128, alo + 66, a_hi, blo + 2, b_hi, idesc, 1u);
                             mma_lohi(dcol + 128, alo + 68, a_hi, blo + 4, b_hi, idesc, 1u);
                             mma_lohi(dcol + 128, alo + 70, a_hi, blo + 6, b_hi, idesc, 1u);
                         }
                         acc = 1;
-                        commit(&empty_b[s]);
+                        if (PAIR) commit_pair(&empty_b[s]); else commit(&empty_b[s]);
                         if (++s == a.nbst) { s = 0; ph ^= 1; }
                         if (cur.z & 2) {
-                            commit(&empty_a[pb]);
+                            if (PAIR) commit_pair(&empty_a[pb]); else commit(&empty_a[pb]);
                             if (++pb == a.npb) { pb = 0; pph ^= 1; }
                         }
                     }
                 }
-                commit(&tfull[buf]);
+                if (PAIR) commit_pair(&tfull[buf]); else commit(&tfull[buf]);
             }
         }
     } else if (warp >= 4) {
@@ -250,7 +315,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
         float* sbias = reinterpret_cast<float*>(sm + SM_BAR + 3072);          // bias of the tile's BN output channels (<= 256 floats)
         uint8_t* sC = sm + a.sm_stg;
         int local = 0, cidx = 0;
-        for (int t = blockIdx.x; t < a.total; t += gridDim.x, local++) {
+        for (int t = tile0; t < a.total; t += tstride, local++) {
             const TileCoord c = decode_tile(a, t);
             const Program& P = a.prog[c.q];
             const int buf = local & 1;
@@ -264,7 +329,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                 }
             }
             for (int m = 0; m < a.mt; m++) {
-                const int xo = (c.tx * a.mt + m) * 8, yo = c.ty * 16;
+                const int xo = PAIR ? c.tx * 16 + rank * 8 : (c.tx * a.mt + m) * 8, yo = c.ty * 16;
                 float nz = 0.f;
                 if (fuse && a.noise) {
                     const int py = yo + py_in, px = xo + px_in;
@@ -307,13 +372,14 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             }
             fence_before();
             named_bar_sync(1, 128);
-            if (leader) mbar_arrive(&tempty[buf]);
+            if (leader) { if (PAIR) mbar_arrive_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
         }
         if (leader) tma_wait_group_read<0>();      // the staging tiles have been read; the stores themselves complete with the grid (as CUTLASS' tma_store_wait<0>)
     }
     fence_before();
     __syncthreads();
-    if (warp == 3) { __syncwarp(); tmem_dealloc(tm, 512); }
+    if (PAIR) cluster_sync_all();          // no CTA of the pair leaves (or frees tensor memory) while the other may still signal it
+    if (warp == 3) { __syncwarp(); if (PAIR) tmem_dealloc_2sm(tm, 512); else tmem_dealloc(tm, 512); }
 }
 
 // w [G][O][T][I] -> wt [G][I][T'][O], T' = T-1-t when `reverse` (data gradient of a stride-1 'same' correlation) else t
@@ -394,7 +460,8 @@ void plan_tiles(Conv2Args& a, int tiles_pn, bool allow_split, float* y, size_t y
 int launch2(Conv2Args& a, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) {
+        if (cudaFuncSetAttribute(conv_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) != cudaSuccess) {
             spi_set_error("spi_conv_tc2: cannot reserve %d bytes of shared memory", SM_TOTAL);
             return SPI_ERR_CUDA;
         }
@@ -402,7 +469,7 @@ int launch2(Conv2Args& a, cudaStream_t stream) {
     }
     a.err = spi_tc_err_flag();
     {   // shared-memory plan: weight stages first (they turn over once per tap), then as many patch buffers as still fit
-        const int P = (a.patch_bytes + 1023) & ~1023, B = (a.bn * 128 + 1023) & ~1023;
+        const int P = (a.patch_bytes + 1023) & ~1023, B = ((a.pair ? 64 : a.bn) * 128 + 1023) & ~1023;
         int taps = 0;
         for (int v = 0; v < a.prog[0].nviews; v++) taps += a.prog[0].views[v].ntaps;
         a.npb = taps <= 2 ? 4 : 2;                       // 1x1 layers: a patch lasts one or two MMAs batches, the ring must be deeper
@@ -415,8 +482,23 @@ int launch2(Conv2Args& a, cudaStream_t stream) {
         a.sm_stg = a.sm_b + a.nbst * B;
     }
     const int sms = spi_num_sms();
-    const int grid = a.total < sms ? a.total : sms;
-    conv_tc2_kernel<<<grid, NT2, SM_TOTAL, stream>>>(a);
+    if (a.pair) {          // clusters of two CTAs (neighbouring SMs), one M = 256 tile per pair
+        const int pairs = a.total < sms / 2 ? a.total : sms / 2;
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(2 * pairs); cfg.blockDim = dim3(NT2); cfg.dynamicSmemBytes = SM_TOTAL; cfg.stream = stream;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, conv_tc2_kernel<true>, a) != cudaSuccess) {
+            spi_set_error("spi_conv_tc2: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return SPI_ERR_CUDA;
+        }
+    } else {
+        const int grid = a.total < sms ? a.total : sms;
+        conv_tc2_kernel<false><<<grid, NT2, SM_TOTAL, stream>>>(a);
+    }
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("spi_conv_tc2");
     return SPI_OK;
@@ -440,12 +522,16 @@ void common_args(Conv2Args& a, int n, int ci, int co, int per_sample, int wv_out
     a.tiles_o = cdiv(co, a.bn);
     a.dbg = flags;
     a.gain = 1.f; a.clamp = -1.f;
+    // CTA pairs (cta_group::2, M = 256): the two M tiles of a 16-pixel-wide tile go to the two CTAs of a cluster, each loads half of the
+    // weight tile -- an N = 128 layer then reads 96 B/clk of operands per SM instead of 128.  Large maps only (no split, full waves).
+    const long long pair_tiles = (long long)cdiv(wv_out, 16) * cdiv(hv_out, 16) * n * a.tiles_o;
+    if ((flags & 256) && a.bn == 128 && a.mt == 2 && pair_tiles >= spi_num_sms()) { a.pair = 1; a.mt = 1; }
 }
 
 bool map_weights(Conv2Args& a, const float* w, int taps, int g, int tf32_round) {
     cuuint64_t dims[3] = {(cuuint64_t)a.ci, (cuuint64_t)taps, (cuuint64_t)g * a.co};
     cuuint64_t str[2] = {(cuuint64_t)a.ci * 4, (cuuint64_t)taps * a.ci * 4};
-    cuuint32_t box[3] = {32, 1, (cuuint32_t)a.bn};
+    cuuint32_t box[3] = {32, 1, (cuuint32_t)(a.pair ? 64 : a.bn)};
     return make_map2(&a.wmap, w, 3, dims, str, box, tf32_round);
 }
 
@@ -473,7 +559,8 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
     a.px = a.mt * 8 + (halo ? ((flags & 64) ? 8 : 2 * halo) : 0);
     const int rows = 16 + 2 * halo;
     a.patch_bytes = rows * a.px * 128;
-    plan_tiles(a, cdiv(wd, a.mt * 8) * cdiv(h, 16) * n, !epi && !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
+    const int tile_w = a.pair ? 16 : a.mt * 8;
+    plan_tiles(a, cdiv(wd, tile_w) * cdiv(h, 16) * n, !epi && !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
     if (!map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) ||
         !map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0) ||
         !map_weights(a, w, k * k, per_sample ? n : 1, rnd)) {
@@ -483,7 +570,7 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
     for (int i = 1; i < MAXV; i++) a.amap[i] = a.amap[0];
     Program& P = a.prog[0];
     P.nviews = 1; P.omap = 0; P.tile_begin = 0; P.fuse_epilogue = 1;
-    P.tiles_x = cdiv(wd, a.mt * 8); P.tiles_y = cdiv(h, 16);
+    P.tiles_x = cdiv(wd, tile_w); P.tiles_y = cdiv(h, 16);
     View& V = P.views[0];
     V.amap = 0; V.oy = -halo; V.ox = -halo; V.ntaps = k * k;
     for (int ky = 0; ky < k; ky++)
@@ -505,7 +592,7 @@ extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float
     const int rnd = (flags & 1) ? 0 : 1;
     const int ho = 2 * h + 1, wo = 2 * wd + 1;
     Conv2Args a;
-    common_args(a, n, ci, co, per_sample, wd + 1, h + 1, flags);
+    common_args(a, n, ci, co, per_sample, wd + 1, h + 1, flags & ~256);
     a.px = a.mt * 8 + ((flags & 64) ? 8 : 1);
     const int rows = 17;
     a.patch_bytes = rows * a.px * 128;
@@ -548,7 +635,7 @@ extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n
     const int rnd = (flags & 1) ? 0 : 1;
     const int hi = 2 * h + 1, wi = 2 * wd + 1;
     Conv2Args a;
-    common_args(a, n, ci, co, per_sample, wd, h, flags);
+    common_args(a, n, ci, co, per_sample, wd, h, flags & ~256);
     a.px = a.mt * 8 + ((flags & 64) ? 8 : 1);
     const int rows = 17;
     a.patch_bytes = rows * a.px * 128;

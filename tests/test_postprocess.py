@@ -199,3 +199,46 @@ def test_coach_tail_writes_checkpoint_stills_clip_and_metrics():
         for k, v in saved.items():
             setattr(paths_config, k, v)
         hyperparameters.G_1_step, global_config.device = saved_step, saved_dev
+
+
+def test_inference_coach_reloads_checkpoints_and_writes_the_clips():
+    """`--G_1_type Inference` (inference_coach.py:18-46): for every dataset item the checkpoint {w, c, G} written by the coach named in
+    `load_embedding_coach_name` is reloaded into G and its 120-frame orbit clip goes to `video_output_dir/<name>.mp4|.avi`."""
+    cv2 = pytest.importorskip('cv2')
+    from spi_b200.configs import global_config, hyperparameters, paths_config
+    from spi_b200.training.coaches.base_coach import BaseCoach
+    from spi_b200.training.coaches.inference_coach import InferenceCoach
+    from spi_b200.utils.camera_utils import cal_canonical_c
+    keys = ('checkpoints_dir', 'embedding_base_dir', 'experiments_output_dir', 'images_output_dir', 'mirror_images_output_dir', 'video_output_dir')
+    saved = {k: getattr(paths_config, k) for k in keys}
+    saved_hp = (hyperparameters.load_embedding_coach_name, hyperparameters.max_images_to_invert, global_config.device)
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            for k in keys:
+                setattr(paths_config, k, os.path.join(d, k) + '/')
+                os.makedirs(os.path.join(d, k, 'Coach_src'))
+            global_config.device = 'cpu'
+            hyperparameters.load_embedding_coach_name, hyperparameters.max_images_to_invert = 'Coach_src', 10
+            writer = object.__new__(BaseCoach)
+            src = _FakeG()
+            with torch.no_grad():
+                src.p.fill_(3.5)
+            names = ['a0', 'b1']
+            for i, nm in enumerate(names):
+                writer.save(torch.full((1, 14, 512), float(i)), cal_canonical_c(0.3 + 0.1 * i, 0, 1, 'cpu'), src, os.path.join(d, 'checkpoints_dir', 'Coach_src', nm + '.pt'))
+            coach = object.__new__(InferenceCoach)
+            coach.G, coach.use_wandb, coach.coach_name, coach.image_counter = _FakeG(), False, 'InferenceCoach_x', 0
+            coach.data_loader = [{'name': [nm]} for nm in names]
+            clips = coach.train()
+            assert float(coach.G.p) == 3.5                                      # the checkpoint's generator state was loaded
+            assert coach.image_counter == 2 and len(clips) == 2
+            for nm, clip in zip(names, clips):
+                assert os.path.dirname(clip).rstrip('/') == os.path.join(d, 'video_output_dir') and os.path.basename(clip).startswith(nm + '.')
+                cap = cv2.VideoCapture(clip)
+                assert int(cap.get(cv2.CAP_PROP_FRAME_COUNT)) == 120
+                cap.release()
+                assert os.path.isdir(os.path.join(d, 'experiments_output_dir', 'InferenceCoach_x', nm))
+    finally:
+        for k, v in saved.items():
+            setattr(paths_config, k, v)
+        hyperparameters.load_embedding_coach_name, hyperparameters.max_images_to_invert, global_config.device = saved_hp

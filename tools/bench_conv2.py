@@ -234,7 +234,7 @@ def one():
     8: every tap reads the unshifted column -- wrong results, aligned descriptors --, 16: no output store)."""
     x, w, wl = make(1, 128, 128, 512, 512, 3, False)
     gf = 2 * 512 * 512 * 9 * 128 * 128 / 1e9
-    for flags in (0, 4, 64):
+    for flags in (0, 64, 64 | 8, 8, 4):
         t = time_ms(lambda: conv_s1(x, w, False, 3, flags))
         print(f'  flags {flags}: {t:.3f} ms {gf / t:.0f} TF/s err {L.spi_tc_error()}', flush=True)
     x, w, wl = make(1, 256, 256, 256, 256, 3, False)
@@ -302,6 +302,28 @@ def ncu_target():
     torch.cuda.synchronize()
 
 
+def pair_study():
+    """cta_group::2 path (flags 256) against the single-CTA kernel: correctness (bit-compare is not expected: same sums, same order -> should
+    in fact be identical) and timing on the 128-channel layers."""
+    for (n, ci, co, h) in ((1, 128, 128, 512), (4, 128, 128, 512), (1, 128, 128, 256), (2, 64, 128, 200)):
+        x, w, wl = make(n, ci, co, h, h, 3, False)
+        y0 = conv_s1(x, w, False, 3, 0)
+        y1 = conv_s1(x, w, False, 3, 256)
+        err = L.spi_tc_error()
+        ref = F.conv2d(x[:1].double(), wl[0].double(), padding=1)
+        print(f'  {n}x{ci}->{co} @{h}^2: pair vs single rel {rel(y1, y0):.2e} equal {bool(torch.equal(y0, y1))} | pair vs fp64 {rel(y1[:1], ref):.2e} | err {err}', flush=True)
+        if err:
+            return
+        b, nz, st = torch.randn(co, device='cuda'), torch.randn(h, h, device='cuda'), torch.tensor(0.7, device='cuda')
+        e0 = conv_s1(x, w, False, 3, 0, bias=b, noise=nz, strength=st, act=2, gain=1.41, clamp=256.0)
+        e1 = conv_s1(x, w, False, 3, 256, bias=b, noise=nz, strength=st, act=2, gain=1.41, clamp=256.0)
+        print(f'     fused epilogue: pair vs single rel {rel(e1, e0):.2e} err {L.spi_tc_error()}', flush=True)
+        gf = 2 * n * h * h * 9 * ci * co / 1e9
+        t0 = time_ms(lambda: conv_s1(x, w, False, 3, 0))
+        t1 = time_ms(lambda: conv_s1(x, w, False, 3, 256))
+        print(f'     single {t0:.3f} ms {gf / t0:.0f} TF/s | pair {t1:.3f} ms {gf / t1:.0f} TF/s', flush=True)
+
+
 def reps_study():
     torch.backends.cudnn.allow_tf32 = True
     torch.backends.cudnn.benchmark = True
@@ -332,6 +354,9 @@ def reps_study():
 if __name__ == '__main__':
     if '--ncu-target' in sys.argv:
         ncu_target()
+        sys.exit(0)
+    if '--pair' in sys.argv:
+        pair_study()
         sys.exit(0)
     if '--small' in sys.argv:
         small_study()
