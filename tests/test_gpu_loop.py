@@ -86,14 +86,21 @@ def make_coach(kind, gen_sd, lpips_mod, cx_mod):
     return coach
 
 
-@pytest.mark.parametrize('kind', ['pti', 'RotBbox'])
-def test_coach_step_golden(kind, golden, gen_sd, lpips_mod, cx_mod):
-    """One G-stage iteration (i = 0, all branches active) against the reference's recorded losses and gradients."""
+@pytest.mark.parametrize('kind,depth', [('pti', 48), ('RotBbox', 48), ('RotBbox', 32)])
+def test_coach_step_golden(kind, depth, golden, gen_sd, lpips_mod, cx_mod):
+    """One G-stage iteration (i = 0, all branches active) against the reference's recorded losses and gradients, at the pickle's 48+48
+    samples per ray and at the bench configuration's 32+32 (tests/golden/steps_32_full.npz, oracle/make_golden_32_steps.py)."""
     from spi_b200.training.coaches.rot_bbox_cx_coach import SPIState
-    from spi_b200.utils import rng
-    g = golden('steps')
-    rk = OG.RENDERING_DEFAULTS
-    coach = make_coach(kind, gen_sd, lpips_mod, cx_mod)
+    from spi_b200.utils import load_utils, rng
+    g = golden('steps' if depth == 48 else 'steps_32_full')
+    rk = dict(OG.RENDERING_DEFAULTS, depth_resolution=depth, depth_resolution_importance=depth)
+    old_depth = load_utils.DEPTH_OVERRIDE
+    load_utils.DEPTH_OVERRIDE = (depth, depth) if depth != 48 else None
+    try:
+        coach = make_coach(kind, gen_sd, lpips_mod, cx_mod)
+    finally:
+        load_utils.DEPTH_OVERRIDE = old_depth
+    assert coach.G.rendering_kwargs['depth_resolution'] == depth
     src = OL.NoiseSource(200)
     image, camera = weights.target_image().cuda(), weights.canonical_camera(0.3).cuda()
     w = weights.w_pivot(5).cuda().requires_grad_(True)
@@ -128,9 +135,11 @@ def test_coach_step_golden(kind, golden, gen_sd, lpips_mod, cx_mod):
         grad = params[k].grad.reshape(-1)
         sub = grad[::max(1, grad.numel() // 4096)]
         errs[k] = (rel_l2(sub, g[f'{kind}_grad_{k}']), abs(float(grad.double().norm()) / float(g[f'{kind}_gradnorm_{k}']) - 1))
-    print(kind, 'grad (rel-L2 of subsample, norm ratio - 1):', errs)
-    assert max(e[0] for e in errs.values()) < 5e-2 and max(e[1] for e in errs.values()) < 3e-2
-    assert rel_l2(w.grad, g[f'{kind}_wgrad']) < 5e-2
+    print(kind, depth, 'grad (rel-L2 of subsample, norm ratio - 1):', errs, 'dws', rel_l2(w.grad, g[f'{kind}_wgrad']))
+    # measured on B200 (TF32 contractions, 3xTF32 decoder): 0.8-1.3e-3 on every tensor except the 4x4 constant (1.3e-2), norms within 1e-3
+    assert max(e[0] for e in errs.values()) < 3e-2 and max(e[1] for e in errs.values()) < 5e-3
+    assert max(e[0] for k, e in errs.items() if k != 'backbone.synthesis.b4.const') < 5e-3
+    assert rel_l2(w.grad, g[f'{kind}_wgrad']) < 1e-2
 
 
 def test_pti_step_golden_at_the_bench_depth_resolution(golden, gen_sd, lpips_mod, cx_mod):
