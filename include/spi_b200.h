@@ -147,6 +147,19 @@ int spi_modulate_weights_backward(const float* weight, const float* styles, cons
                                   float* grad_weight, float* grad_styles, int n, int o, int i, int kk, int demodulate,
                                   int layout, cudaStream_t stream);
 
+/* ---- style bank: all affine layers of a synthesis network in one launch (FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+ *      inside every SynthesisLayer / ToRGBLayer, eg3d/training/networks_stylegan2.py:282,316,352,357-358) ----------------- */
+/* out[l][n,i] = ogain[l] * (wgain[l] * sum_k ws[n, widx[l], k] * W[l][i,k] + bgain[l] * b[l][i]).  ws has element strides
+ * (ws_sn, ws_sl, 1); the per-layer tables (W, b, out, I, widx, gains; layers <= 32) are HOST arrays read during the call. */
+int spi_style_bank_forward(const float* ws, long long ws_sn, long long ws_sl, int n, int k, int layers, const float* const* W,
+                           const float* const* b, float* const* out, const int* I, const int* widx, const float* wgain,
+                           const float* bgain, const float* ogain, cudaStream_t stream);
+/* ds[l] [n][I[l]] (NULL = zero); dW[l] [I[l]][k] / db[l] [I[l]] (NULL = not wanted) overwritten; dws (NULL = not wanted) contiguous
+ * [n][num_ws][k], overwritten. */
+int spi_style_bank_backward(const float* ws, long long ws_sn, long long ws_sl, int n, int k, int layers, const float* const* W,
+                            const float* const* ds, float* const* dW, float* const* db, const int* I, const int* widx,
+                            const float* wgain, const float* bgain, const float* ogain, float* dws, int num_ws, cudaStream_t stream);
+
 /* ---- depth-guided 3-D warp: replaces rotate() (spi/utils/rotate.py:92-116) --------------------------- */
 /* cameras [n, 25]; depths [n, 1, depth_res, depth_res]; image [n, 3, res, res]; mask [n, 1, res, res] or NULL;
  * *_bs = batch strides in elements of the source tensors (0 broadcasts one source over n views, replacing the

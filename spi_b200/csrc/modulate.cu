@@ -305,3 +305,164 @@ extern "C" int spi_modulate_weights_backward(const float* weight, const float* s
     SPI_LAUNCH_CHECK("modulate_weights_backward");
     return SPI_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Style bank: every affine layer of a synthesis network (FullyConnectedLayer(w_dim, in_channels, bias_init=1) of each
+// SynthesisLayer / ToRGBLayer, eg3d/training/networks_stylegan2.py:282,316 and :352,357-358) evaluated by ONE launch, and
+// their weight / bias / latent gradients by one more (two when the latents are being optimised).  Per layer the work is a
+// [I x 512] matrix-vector product -- a few microseconds of HBM time each, but 26 layers x (addmm, mul, and three backward
+// GEMV / outer-product launches) per iteration; grouped, the whole generator's affines cost one read of their 20 MB of weights.
+//   styles_l[n,i] = ogain_l * (wgain_l * sum_k ws[n, widx_l, k] * W_l[i,k] + bgain_l * b_l[i])
+namespace {
+
+constexpr int BANK_MAX = 32;
+struct BankLayer {
+    const float* W; const float* b; float* out;            // forward
+    const float* ds; float* dW; float* db;                 // backward (ds null: this layer's styles were not used)
+    int I, widx, row0;
+    float wgain, bgain, ogain;
+};
+struct BankArgs {
+    BankLayer layer[BANK_MAX];
+    int layers, n, k, rows;
+    long long ws_sn, ws_sl;                                // element strides of ws over samples / latent index (last dim contiguous)
+};
+
+__device__ __forceinline__ int bank_find(const BankArgs& a, int row) {
+    int l = 0;
+    while (l + 1 < a.layers && a.layer[l + 1].row0 <= row) l++;
+    return l;
+}
+
+// one warp per (layer, output row)
+__global__ void __launch_bounds__(256) style_bank_fwd_kernel(const __grid_constant__ BankArgs a, const float* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= a.rows) return;
+    const int l = bank_find(a, row);
+    const BankLayer& L = a.layer[l];
+    const int i = row - L.row0;
+    if (i >= L.I) return;                                  // padding rows between layers
+    const float4* wr = reinterpret_cast<const float4*>(L.W + (size_t)i * a.k);
+    const float bias = L.b ? L.b[i] * L.bgain : 0.f;
+    for (int n = 0; n < a.n; n++) {
+        const float4* x = reinterpret_cast<const float4*>(ws + n * a.ws_sn + L.widx * a.ws_sl);
+        float acc = 0.f;
+        for (int c = lane; c < a.k / 4; c += 32) {
+            const float4 w4 = __ldg(wr + c), x4 = __ldg(x + c);
+            acc = fmaf(w4.x, x4.x, acc); acc = fmaf(w4.y, x4.y, acc); acc = fmaf(w4.z, x4.z, acc); acc = fmaf(w4.w, x4.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) L.out[(size_t)n * L.I + i] = L.ogain * (L.wgain * acc + bias);
+    }
+}
+
+// one warp per (layer, row): dW_l[i,:] = ogain*wgain * sum_n ds[n,i] * ws[n,widx,:],  db_l[i] = ogain*bgain * sum_n ds[n,i]
+__global__ void __launch_bounds__(256) style_bank_bwd_kernel(const __grid_constant__ BankArgs a, const float* __restrict__ ws) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= a.rows) return;
+    const int l = bank_find(a, row);
+    const BankLayer& L = a.layer[l];
+    const int i = row - L.row0;
+    if (i >= L.I || (!L.dW && !L.db)) return;
+    float4* dw = L.dW ? reinterpret_cast<float4*>(L.dW + (size_t)i * a.k) : nullptr;
+    const float gw = L.ogain * L.wgain;
+    float dsum = 0.f;
+    for (int n = 0; n < a.n; n++) dsum += L.ds ? L.ds[(size_t)n * L.I + i] : 0.f;
+    if (L.db && lane == 0) L.db[i] = L.ogain * L.bgain * dsum;
+    if (!dw) return;
+    for (int c = lane; c < a.k / 4; c += 32) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (L.ds)
+            for (int n = 0; n < a.n; n++) {
+                const float d = L.ds[(size_t)n * L.I + i] * gw;
+                const float4 x4 = __ldg(reinterpret_cast<const float4*>(ws + n * a.ws_sn + L.widx * a.ws_sl) + c);
+                r.x = fmaf(d, x4.x, r.x); r.y = fmaf(d, x4.y, r.y); r.z = fmaf(d, x4.z, r.z); r.w = fmaf(d, x4.w, r.w);
+            }
+        dw[c] = r;
+    }
+}
+
+// latent gradient: dws[n, widx_l, :] += ogain*wgain * sum_i ds_l[n,i] * W_l[i,:]; grid (row chunks of 32 over all layers, n), a thread owns
+// 4 consecutive k; dws (contiguous [n][L][k]) zeroed by the caller
+__global__ void __launch_bounds__(128) style_bank_dws_kernel(const __grid_constant__ BankArgs a, float* __restrict__ dws, int num_ws) {
+    const int row_begin = blockIdx.x * 32, n = blockIdx.y;
+    const int l = bank_find(a, row_begin);
+    const BankLayer& L = a.layer[l];
+    if (!L.ds) return;
+    const int i0 = row_begin - L.row0, i1 = min(L.I, i0 + 32);          // row0 of every layer is a multiple of 32 (host pads)
+    const float g = L.ogain * L.wgain;
+    for (int c = threadIdx.x; c < a.k / 4; c += blockDim.x) {
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = i0; i < i1; i++) {
+            const float d = L.ds[(size_t)n * L.I + i] * g;
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(L.W + (size_t)i * a.k) + c);
+            r.x = fmaf(d, w4.x, r.x); r.y = fmaf(d, w4.y, r.y); r.z = fmaf(d, w4.z, r.z); r.w = fmaf(d, w4.w, r.w);
+        }
+        float* dst = dws + ((size_t)n * num_ws + L.widx) * a.k + c * 4;
+        atomicAdd(dst, r.x); atomicAdd(dst + 1, r.y); atomicAdd(dst + 2, r.z); atomicAdd(dst + 3, r.w);
+    }
+}
+
+int bank_args(BankArgs& a, int layers, int n, int k, const int* I, const int* widx, const float* wgain, const float* bgain, const float* ogain,
+              long long ws_sn, long long ws_sl) {
+    if (layers < 1 || layers > BANK_MAX || n < 1 || k < 4 || (k & 3)) return SPI_ERR_ARG;
+    int rows = 0;
+    for (int l = 0; l < layers; l++) {
+        if (I[l] < 1 || widx[l] < 0) return SPI_ERR_ARG;
+        BankLayer& L = a.layer[l];
+        L.I = I[l]; L.widx = widx[l]; L.row0 = rows; L.wgain = wgain[l]; L.bgain = bgain[l]; L.ogain = ogain[l];
+        rows += (I[l] + 31) / 32 * 32;                       // rows of a layer start on a multiple of 32 (the dws kernel's chunks)
+    }
+    a.layers = layers; a.n = n; a.k = k; a.rows = rows; a.ws_sn = ws_sn; a.ws_sl = ws_sl;
+    return SPI_OK;
+}
+
+}  // namespace
+
+// ws: latents, element strides (ws_sn, ws_sl, 1); per layer l < layers: W[l] [I[l]][k], b[l] [I[l]] (may be null), out[l] [n][I[l]].
+// The pointer / scalar tables are HOST arrays (read during the call only).
+extern "C" int spi_style_bank_forward(const float* ws, long long ws_sn, long long ws_sl, int n, int k, int layers, const float* const* W,
+                                      const float* const* b, float* const* out, const int* I, const int* widx, const float* wgain,
+                                      const float* bgain, const float* ogain, cudaStream_t stream) {
+    SPI_CHECK_ARG(ws && W && b && out && I && widx && wgain && bgain && ogain, "style_bank_forward: null table");
+    BankArgs a{};
+    SPI_CHECK_ARG(bank_args(a, layers, n, k, I, widx, wgain, bgain, ogain, ws_sn, ws_sl) == SPI_OK, "style_bank_forward: bad shape (layers=%d n=%d k=%d)", layers, n, k);
+    SPI_CHECK_ARG((((uintptr_t)ws | (uintptr_t)(ws_sn * 4) | (uintptr_t)(ws_sl * 4)) & 15) == 0, "style_bank_forward: latents must be 16-byte aligned");
+    for (int l = 0; l < layers; l++) {
+        SPI_CHECK_ARG(W[l] && out[l] && ((uintptr_t)W[l] & 15) == 0, "style_bank_forward: layer %d: null / misaligned weight", l);
+        a.layer[l].W = W[l]; a.layer[l].b = b[l]; a.layer[l].out = out[l];
+    }
+    style_bank_fwd_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a, ws);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("style_bank_forward");
+    return SPI_OK;
+}
+
+// ds[l] [n][I[l]] (null: zero); dW[l] / db[l] (null: not wanted) are overwritten; dws (null: not wanted) is contiguous [n][num_ws][k], overwritten.
+extern "C" int spi_style_bank_backward(const float* ws, long long ws_sn, long long ws_sl, int n, int k, int layers, const float* const* W,
+                                       const float* const* ds, float* const* dW, float* const* db, const int* I, const int* widx,
+                                       const float* wgain, const float* bgain, const float* ogain, float* dws, int num_ws, cudaStream_t stream) {
+    SPI_CHECK_ARG(ws && W && ds && dW && db && I && widx && wgain && bgain && ogain, "style_bank_backward: null table");
+    BankArgs a{};
+    SPI_CHECK_ARG(bank_args(a, layers, n, k, I, widx, wgain, bgain, ogain, ws_sn, ws_sl) == SPI_OK, "style_bank_backward: bad shape (layers=%d n=%d k=%d)", layers, n, k);
+    SPI_CHECK_ARG((((uintptr_t)ws | (uintptr_t)(ws_sn * 4) | (uintptr_t)(ws_sl * 4)) & 15) == 0, "style_bank_backward: latents must be 16-byte aligned");
+    bool any = false;
+    for (int l = 0; l < layers; l++) {
+        SPI_CHECK_ARG(W[l] && ((uintptr_t)W[l] & 15) == 0 && ((uintptr_t)dW[l] & 15) == 0, "style_bank_backward: layer %d: null / misaligned weight", l);
+        SPI_CHECK_ARG(!dws || widx[l] < num_ws, "style_bank_backward: layer %d: latent index %d outside num_ws=%d", l, widx[l], num_ws);
+        a.layer[l].W = W[l]; a.layer[l].ds = ds[l]; a.layer[l].dW = dW[l]; a.layer[l].db = db[l];
+        any = any || dW[l] || db[l];
+    }
+    int launches = 0;
+    if (any) { style_bank_bwd_kernel<<<(a.rows + 7) / 8, 256, 0, stream>>>(a, ws); launches++; }
+    if (dws) {
+        cudaMemsetAsync(dws, 0, sizeof(float) * (size_t)n * num_ws * k, stream);
+        style_bank_dws_kernel<<<dim3(a.rows / 32, n), 128, 0, stream>>>(a, dws, num_ws);
+        launches++;
+    }
+    SPI_COUNT_LAUNCH(launches);
+    SPI_LAUNCH_CHECK("style_bank_backward");
+    return SPI_OK;
+}

@@ -18,6 +18,7 @@ import torch
 
 from ..ops import conv as conv_engine
 from ..ops.modulate import modulate_weights
+from ..ops import style_bank
 from ..torch_utils import misc, persistence
 from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
 
@@ -202,13 +203,14 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, styles=None):
         assert noise_mode in ['random', 'const', 'none']
         in_resolution = self.resolution // self.up
         misc.assert_shape(x, [None, self.in_channels, in_resolution, in_resolution])
-        if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
-            w = w[:1]            # one latent broadcast over the batch: one weight set, one batched convolution
-        styles = self.affine(w)
+        if styles is None:       # (`styles`: this layer's affine output, already evaluated by the network's style bank)
+            if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
+                w = w[:1]        # one latent broadcast over the batch: one weight set, one batched convolution
+            styles = self.affine(w)
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.resolution, self.resolution], device=x.device) * self.noise_strength
@@ -253,10 +255,11 @@ class ToRGBLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
-    def forward(self, x, w, fused_modconv=True):
-        if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
-            w = w[:1]
-        styles = self.affine(w) * self.weight_gain
+    def forward(self, x, w, fused_modconv=True, styles=None):
+        if styles is None:       # (`styles`: affine output times weight_gain, from the network's style bank)
+            if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
+                w = w[:1]
+            styles = self.affine(w) * self.weight_gain
         if fused_modconv and x.dtype == torch.float32:
             epi = dict(b=self.bias.to(x.dtype), act='linear', clamp=self.conv_clamp)
             return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=True, conv_epilogue=epi)
@@ -265,6 +268,15 @@ class ToRGBLayer(torch.nn.Module):
 
     def extra_repr(self):
         return f'in_channels={self.in_channels:d}, out_channels={self.out_channels:d}, w_dim={self.w_dim:d}'
+
+
+def _fused(block, fused_modconv):
+    """The fused_modconv decision of _SynthesisBlockBase.forward (networks_stylegan2.py:425-428)."""
+    if fused_modconv is None:
+        fused_modconv = block.fused_modconv_default
+    if fused_modconv == 'inference_only':
+        fused_modconv = not block.training
+    return bool(fused_modconv)
 
 
 class _SynthesisBlockBase(torch.nn.Module):
@@ -299,9 +311,18 @@ class _SynthesisBlockBase(torch.nn.Module):
         if in_channels != 0 and architecture == 'resnet':
             raise NotImplementedError("architecture='resnet' is not used by EG3D generators (skip only)")
 
-    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, **layer_kwargs):
+    def style_entries(self, first_ws):
+        """(affine layer, latent index, output gain) of this block's layers in the order forward() consumes its latents."""
+        layers = ([self.conv0] if self.in_channels != 0 else []) + [self.conv1]
+        entries = [(layer.affine, first_ws + j, 1.0) for j, layer in enumerate(layers)]
+        if self.is_last or self.architecture == 'skip':
+            entries.append((self.torgb.affine, first_ws + len(layers), self.torgb.weight_gain))
+        return entries
+
+    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, styles=None, **layer_kwargs):
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
         w_iter = iter(ws.unbind(dim=1))
+        s_iter = iter(styles) if styles is not None else iter(lambda: None, 0)     # precomputed styles, same order as w_iter
         # Precision policy of this build: fp32 storage, TF32 tensor-core contraction (DESIGN.md); `use_fp16` only
         # selects the clamp, which the reference also applies in its fp32 fallback (networks_stylegan2.py:421-423).
         if fused_modconv is None:
@@ -315,15 +336,15 @@ class _SynthesisBlockBase(torch.nn.Module):
             misc.assert_shape(x, [None, self.in_channels, in_res, in_res])
             x = x.to(torch.float32)
         if self.in_channels == 0:
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), **layer_kwargs)
         else:
-            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), **layer_kwargs)
         if img is not None and self.block_up == 2:
             misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
             img = upfirdn2d.upsample2d(img, self.resample_filter)
         if self.is_last or self.architecture == 'skip':
-            y = self.torgb(x, next(w_iter), fused_modconv=fused_modconv).to(torch.float32)
+            y = self.torgb(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter)).to(torch.float32)
             img = img.add_(y) if img is not None else y
         return x, img
 
@@ -360,10 +381,20 @@ class SynthesisNetwork(torch.nn.Module):
         misc.assert_shape(ws, [None, self.num_ws, self.w_dim])
         ws = ws.to(torch.float32)
         x = img = None
+        blocks = [getattr(self, f'b{res}') for res in self.block_resolutions]
+        # all affine layers of the network in one launch (ops/style_bank.py) when every block takes the fused (eval-mode) branch
+        styles = None
+        if style_bank.usable(ws) and all(_fused(b, block_kwargs.get('fused_modconv')) for b in blocks):
+            entries, w_idx = [], 0
+            for block in blocks:
+                entries += block.style_entries(w_idx)
+                w_idx += block.num_conv
+            styles = iter(style_bank.style_bank(ws, entries))
         w_idx = 0
-        for res in self.block_resolutions:
-            block = getattr(self, f'b{res}')
-            x, img = block(x, img, ws.narrow(1, w_idx, block.num_conv + block.num_torgb), **block_kwargs)
+        for block in blocks:
+            count = block.num_conv + block.num_torgb
+            block_styles = [next(styles) for _ in range(count)] if styles is not None else None
+            x, img = block(x, img, ws.narrow(1, w_idx, count), styles=block_styles, **block_kwargs)
             w_idx += block.num_conv
         return img
 
