@@ -223,6 +223,11 @@ int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float* y, int n,
                                 cudaStream_t stream);
 int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
                       cudaStream_t stream);
+/* Number of Cin splits the call of form 0 (spi_conv2d_tc2) / 1 (spi_conv_transpose2d_s2_tc2) / 2 (spi_conv2d_s2_tc2) will use; > 1: the
+ * output is accumulated with reduce-adds and the entry point zero-fills it first -- unless flags bit 9 (512) says the caller hands in
+ * memory that is already zero (one fill per iteration for all such outputs instead of one per call).  The weight-gradient, RGB and
+ * modulate-backward entry points take the same promise as mode + 4, which + 4 and layout + 8.  No device work. */
+int spi_conv_tc2_splits(int form, int n, int h, int wd, int ci, int co, int k, int per_sample, int epilogue, int flags);
 /* Weight gradients of the same convolutions (spi_b200/csrc/conv_wgrad_tc2.cu; replaces cuDNN's wgrad behind the autograd of
  * `_conv2d_wrapper`, conv2d_resample.py:30-43).  mode 0: y = spi_conv2d_tc2(x, w), dy [n,h,w,co] -> dw [g][co][k*k][ci];
  * mode 1: y = spi_conv_transpose2d_s2_tc2(x, w), dy [n,2h+1,2w+1,co] -> dw TRANSPOSED [g][ci][9][co].  g = n when per_sample (one

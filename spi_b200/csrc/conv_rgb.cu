@@ -159,13 +159,16 @@ int dispatch(int which, const float* a, const float* b, float* c, long long pixe
 
 extern "C" int spi_conv1x1_rgb_supported(int ci, int co) { return (ci % 128 == 0 && ci >= 128 && ci <= 512 && co >= 1 && co <= MAXCO) ? 1 : 0; }
 
-// which: 0 forward (a = x, b = w, c = y), 1 data gradient (a = dy, b = w, c = dx), 2 weight gradient (a = x, b = dy, c = dw, overwritten)
+// which: 0 forward (a = x, b = w, c = y), 1 data gradient (a = dy, b = w, c = dx), 2 weight gradient (a = x, b = dy, c = dw, overwritten;
+// 2 + 4: dw is already zero on entry, the fill is skipped)
 extern "C" int spi_conv1x1_rgb(int which, const float* a, const float* b, float* c, long long pixels, int n, int ci, int co, int per_sample,
                                cudaStream_t stream) {
+    const bool prezeroed = (which & 4) != 0;
+    which &= 3;
     SPI_CHECK_ARG(a && b && c && which >= 0 && which <= 2, "spi_conv1x1_rgb: bad arguments");
     SPI_CHECK_ARG(spi_conv1x1_rgb_supported(ci, co), "spi_conv1x1_rgb: unsupported shape ci=%d co=%d", ci, co);
     SPI_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0 || co != 4, "spi_conv1x1_rgb: tensors must be 16-byte aligned");
-    if (which == 2) cudaMemsetAsync(c, 0, (size_t)(per_sample ? n : 1) * co * ci * 4, stream);
+    if (which == 2 && !prezeroed) cudaMemsetAsync(c, 0, (size_t)(per_sample ? n : 1) * co * ci * 4, stream);
     int rc;
     switch (co) {
         case 1: rc = dispatch<1>(which, a, b, c, pixels, n, ci, per_sample, stream); break;

@@ -438,7 +438,7 @@ int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 96 == 0 && co <= 96 ? 9
 // Small feature maps cannot fill 148 SMs with 256-pixel x 128-channel tiles: narrow the Cout tile to 64 and split the Cin chunks of
 // every tile over `splitk` CTAs.  Partial sums meet in the output through TMA reduce-adds, so the output is zeroed first and no fused
 // epilogue is possible (`allow_split` is false when the caller asked for one).  `tiles_pn` = pixel tiles x images.
-void plan_tiles(Conv2Args& a, int tiles_pn, bool allow_split, float* y, size_t y_bytes, cudaStream_t stream) {
+void plan_tiles(Conv2Args& a, int tiles_pn, bool allow_split) {
     const int cchunks = a.ci / 32, sms = spi_num_sms();
     if (a.bn == 128 && (long long)tiles_pn * a.tiles_o * (allow_split ? cchunks : 1) < sms) { a.bn = 64; a.tiles_o = cdiv(a.co, a.bn); }
     const int tiles = tiles_pn * a.tiles_o;
@@ -454,7 +454,11 @@ void plan_tiles(Conv2Args& a, int tiles_pn, bool allow_split, float* y, size_t y
         if (eff > best + 1e-9) { best = eff; a.splitk = s; a.cps = cps; }
         if (eff >= 0.8) break;
     }
-    if (a.splitk > 1) cudaMemsetAsync(y, 0, y_bytes, stream);
+}
+
+// flags bit 9 (512): the caller hands in an output that is already zero (a slice of its per-iteration zero arena), no fill needed
+void zero_split_output(const Conv2Args& a, float* y, size_t y_bytes, cudaStream_t stream) {
+    if (a.splitk > 1 && !(a.dbg & 512)) cudaMemsetAsync(y, 0, y_bytes, stream);
 }
 
 int launch2(Conv2Args& a, cudaStream_t stream) {
@@ -544,10 +548,10 @@ extern "C" int spi_conv_tc2_supported(int ci, int co) { return (ci % 32 == 0 && 
 // (Descriptor base offset stays 0 although tap-shifted operand rows start inside a 1024-byte swizzle atom: measured on B200, the
 // unit swizzles on absolute shared-memory address bits, so the pattern TMA wrote is the pattern the MMA reads; setting the field
 // from the shift gives wrong results -- profiles/r2_conv2_probe.txt.)
-extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int k, int per_sample,
-                              const float* bias, const float* noise, const float* noise_strength, int act, float slope, float gain, float clamp,
-                              int flags, cudaStream_t stream) {
-    SPI_CHECK_ARG(x && w && y, "spi_conv2d_tc2: null tensor");
+static int conv_s1(bool plan_only, const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int k, int per_sample,
+                   const float* bias, const float* noise, const float* noise_strength, int act, float slope, float gain, float clamp,
+                   int flags, cudaStream_t stream) {
+    SPI_CHECK_ARG(plan_only || (x && w && y), "spi_conv2d_tc2: null tensor");
     SPI_CHECK_ARG(spi_conv_tc2_supported(ci, co) && (k == 1 || k == 3), "spi_conv2d_tc2: unsupported shape ci=%d co=%d k=%d", ci, co, k);
     SPI_CHECK_ARG(act >= 0 && act <= 2, "spi_conv2d_tc2: act must be 0 (linear), 1 (relu) or 2 (lrelu)");
     SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "spi_conv2d_tc2: tensors must be 16-byte aligned");
@@ -560,7 +564,9 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
     const int rows = 16 + 2 * halo;
     a.patch_bytes = rows * a.px * 128;
     const int tile_w = a.pair ? 16 : a.mt * 8;
-    plan_tiles(a, cdiv(wd, tile_w) * cdiv(h, 16) * n, !epi && !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
+    plan_tiles(a, cdiv(wd, tile_w) * cdiv(h, 16) * n, !epi && !(flags & 32));
+    if (plan_only) return a.splitk;
+    zero_split_output(a, y, (size_t)n * h * wd * co * 4, stream);
     if (!map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) ||
         !map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0) ||
         !map_weights(a, w, k * k, per_sample ? n : 1, rnd)) {
@@ -584,9 +590,9 @@ extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, i
 
 // Stride-2 transposed 3x3 convolution, no padding: y[n, 2 iy + ky, 2 ix + kx, o] += x[n, iy, ix, i] * w[g, o, ky*3+kx, i].
 // x [N][H][W][Ci], w [G][Co][9][Ci], y [N][2H+1][2W+1][Co].  Four output-parity phases in one launch (heaviest first).
-extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample,
-                                           int flags, cudaStream_t stream) {
-    SPI_CHECK_ARG(x && w && y, "spi_conv_transpose2d_s2_tc2: null tensor");
+static int conv_t2(bool plan_only, const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample,
+                   int flags, cudaStream_t stream) {
+    SPI_CHECK_ARG(plan_only || (x && w && y), "spi_conv_transpose2d_s2_tc2: null tensor");
     SPI_CHECK_ARG(spi_conv_tc2_supported(ci, co), "spi_conv_transpose2d_s2_tc2: unsupported shape ci=%d co=%d", ci, co);
     SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "spi_conv_transpose2d_s2_tc2: tensors must be 16-byte aligned");
     const int rnd = (flags & 1) ? 0 : 1;
@@ -599,8 +605,10 @@ extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float
     {
         int tp = 0;
         for (int q = 0; q < 4; q++) tp += cdiv(wd + 1 - (q & 1), a.mt * 8) * cdiv(h + 1 - (q >> 1), 16) * n;
-        plan_tiles(a, tp, !(flags & 32), y, (size_t)n * ho * wo * co * 4, stream);
+        plan_tiles(a, tp, !(flags & 32));
     }
+    if (plan_only) return a.splitk;
+    zero_split_output(a, y, (size_t)n * ho * wo * co * 4, stream);
     bool ok = map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) &&
               map_weights(a, w, 9, per_sample ? n : 1, rnd);
     for (int i = 1; i < MAXV; i++) a.amap[i] = a.amap[0];
@@ -627,9 +635,9 @@ extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float
 
 // Stride-2 3x3 correlation, no padding: y[n, j, i, o] = sum x[n, 2j + ky, 2i + kx, c] * w[g, o, ky*3+kx, c].
 // x [N][2H+1][2W+1][Ci], w [G][Co][9][Ci], y [N][H][W][Co].  The four input-parity views are strided tensor maps.
-extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
-                                 cudaStream_t stream) {
-    SPI_CHECK_ARG(x && w && y, "spi_conv2d_s2_tc2: null tensor");
+static int conv_s2(bool plan_only, const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
+                   cudaStream_t stream) {
+    SPI_CHECK_ARG(plan_only || (x && w && y), "spi_conv2d_s2_tc2: null tensor");
     SPI_CHECK_ARG(spi_conv_tc2_supported(ci, co), "spi_conv2d_s2_tc2: unsupported shape ci=%d co=%d", ci, co);
     SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)w | (uintptr_t)y) & 15) == 0, "spi_conv2d_s2_tc2: tensors must be 16-byte aligned");
     const int rnd = (flags & 1) ? 0 : 1;
@@ -639,7 +647,9 @@ extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n
     a.px = a.mt * 8 + ((flags & 64) ? 8 : 1);
     const int rows = 17;
     a.patch_bytes = rows * a.px * 128;
-    plan_tiles(a, cdiv(wd, a.mt * 8) * cdiv(h, 16) * n, !(flags & 32), y, (size_t)n * h * wd * co * 4, stream);
+    plan_tiles(a, cdiv(wd, a.mt * 8) * cdiv(h, 16) * n, !(flags & 32));
+    if (plan_only) return a.splitk;
+    zero_split_output(a, y, (size_t)n * h * wd * co * 4, stream);
     bool ok = map_weights(a, w, 9, per_sample ? n : 1, rnd) &&
               map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0);
     Program& P = a.prog[0];
@@ -658,6 +668,32 @@ extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n
     a.nprog = 1;
     a.total = P.tiles_x * P.tiles_y * a.tiles_o * n * a.splitk;
     return launch2(a, stream);
+}
+
+extern "C" int spi_conv2d_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int k, int per_sample,
+                              const float* bias, const float* noise, const float* noise_strength, int act, float slope, float gain, float clamp,
+                              int flags, cudaStream_t stream) {
+    return conv_s1(false, x, w, y, n, h, wd, ci, co, k, per_sample, bias, noise, noise_strength, act, slope, gain, clamp, flags, stream);
+}
+extern "C" int spi_conv_transpose2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample,
+                                           int flags, cudaStream_t stream) {
+    return conv_t2(false, x, w, y, n, h, wd, ci, co, per_sample, flags, stream);
+}
+extern "C" int spi_conv2d_s2_tc2(const float* x, const float* w, float* y, int n, int h, int wd, int ci, int co, int per_sample, int flags,
+                                 cudaStream_t stream) {
+    return conv_s2(false, x, w, y, n, h, wd, ci, co, per_sample, flags, stream);
+}
+
+// How many Cin splits the call of the given form (0 stride-1 'same', 1 stride-2 transposed, 2 stride-2; same n/h/wd/ci/co/k/flags, epilogue
+// != 0 when a fused epilogue is requested) will use.  > 1 means the output is accumulated with reduce-adds and must be zero on entry: the
+// entry points fill it themselves unless flags bit 9 (512) says the caller already did.  Negative: invalid arguments.  No device work.
+extern "C" int spi_conv_tc2_splits(int form, int n, int h, int wd, int ci, int co, int k, int per_sample, int epilogue, int flags) {
+    int rc;
+    if (form == 0) rc = conv_s1(true, nullptr, nullptr, nullptr, n, h, wd, ci, co, k, per_sample, nullptr, nullptr, nullptr, epilogue ? 2 : 0, 0.2f, 1.f, -1.f, flags, nullptr);
+    else if (form == 1) rc = conv_t2(true, nullptr, nullptr, nullptr, n, h, wd, ci, co, per_sample, flags, nullptr);
+    else if (form == 2) rc = conv_s2(true, nullptr, nullptr, nullptr, n, h, wd, ci, co, per_sample, flags, nullptr);
+    else { spi_set_error("spi_conv_tc2_splits: form must be 0, 1 or 2"); return SPI_ERR_ARG; }
+    return rc;
 }
 
 extern "C" int spi_conv_weight_transpose(const float* w, float* wt, int g, int o, int taps, int i, int reverse, cudaStream_t stream) {

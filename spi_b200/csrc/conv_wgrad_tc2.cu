@@ -246,9 +246,12 @@ bool map_img(CUtensorMap* m, const float* ptr, int c, long long wv, long long hv
 //                           dw [G][Co][k*k][Ci]  (U = dy, V = x).
 //                   mode 1: y = stride-2 transposed 3x3 convolution of x [N][H][W][Ci] (spi_conv_transpose2d_s2_tc2); dy [N][2H+1][2W+1][Co];
 //                           dw is written TRANSPOSED as [G][Ci][9][Co]  (U = x, V = the four parity views of dy).
-// G = N when per_sample (one gradient per image), else 1 (summed over the batch).  dw is overwritten.
+// G = N when per_sample (one gradient per image), else 1 (summed over the batch).  dw is overwritten; mode + 4: dw is already zero on entry
+// (a slice of the caller's zero arena -- the partial sums meet in dw through reduce-adds), the fill is skipped.
 extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
                                   cudaStream_t stream) {
+    const bool prezeroed = (mode & 4) != 0;
+    mode &= 3;
     SPI_CHECK_ARG(x && dy && dw, "spi_conv_wgrad_tc2: null tensor");
     SPI_CHECK_ARG(ci % 32 == 0 && co % 32 == 0 && ci >= 32 && co >= 32, "spi_conv_wgrad_tc2: channel counts must be multiples of 32 (ci=%d co=%d)", ci, co);
     SPI_CHECK_ARG((mode == 0 && (k == 1 || k == 3)) || (mode == 1 && k == 3), "spi_conv_wgrad_tc2: unsupported mode %d / k %d", mode, k);
@@ -327,7 +330,7 @@ extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, in
         }
         configured = true;
     }
-    cudaMemsetAsync(dw, 0, (size_t)groups * cu * taps * cv * 4, stream);
+    if (!prezeroed) cudaMemsetAsync(dw, 0, (size_t)groups * cu * taps * cv * 4, stream);
     conv_wgrad_tc2_kernel<<<columns * a.splits, NTW, SMW_TOTAL, stream>>>(a);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("spi_conv_wgrad_tc2");

@@ -295,7 +295,9 @@ extern "C" int spi_modulate_weights_backward(const float* weight, const float* s
                                              int layout, cudaStream_t stream) {
     SPI_CHECK_ARG(weight && styles && grad_out, "modulate_weights_backward: null pointer");
     SPI_CHECK_ARG(!demodulate || dcoef, "modulate_weights_backward: dcoef required when demodulating");
-    if (grad_styles) cudaMemsetAsync(grad_styles, 0, sizeof(float) * (size_t)n * i, stream);
+    const bool prezeroed = (layout & 8) != 0;           // + 8: grad_styles is already zero on entry (a slice of the caller's zero arena)
+    layout &= 7;
+    if (grad_styles && !prezeroed) cudaMemsetAsync(grad_styles, 0, sizeof(float) * (size_t)n * i, stream);
     const size_t rows_bytes = 2 * sizeof(float) * (size_t)i * kk;
     if (rows_bytes <= 40 * 1024)
         modulate_bwd_rows_kernel<<<o, 256, rows_bytes, stream>>>(weight, styles, dcoef, grad_out, grad_weight, grad_styles, n, o, i, kk, demodulate, layout);

@@ -20,6 +20,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import _lib
+from . import zero_arena
 
 ALLOW_TF32 = True
 CUDNN_AUTOTUNE = True      # cudnn.benchmark for the cuDNN arm (every shape is first seen in an eager warm-up pass)
@@ -69,13 +70,27 @@ def _ohwi(w5):
     return w5.permute(0, 1, 3, 4, 2).contiguous()
 
 
+PREZEROED = 512      # conv flag: the output handed in is already zero (ops/zero_arena.py)
+
+
+def _tc2_output(form, n, co, ho, wo, h, wd, ci, k, per_sample, epilogue, flags, device):
+    """Output tensor of a tc2 convolution: when the call will split Cin (reduce-add partial sums into a zeroed output) and the iteration has
+    a zero arena, a slice of the arena plus the flag that tells the library not to fill it again; a plain uninitialised tensor otherwise."""
+    if zero_arena.recording():
+        splits = _lib.load().spi_conv_tc2_splits(form, n, h, wd, ci, co, k, int(per_sample), int(bool(epilogue)), flags)
+        if splits > 1:
+            y = zero_arena.take((n, co, ho, wo), channels_last=True)
+            if y is not None:
+                return y, flags | PREZEROED
+    return torch.empty(n, co, ho, wo, device=device, dtype=torch.float32, memory_format=CL), flags
+
+
 def tc2_s1(x, wk, k, per_sample, epilogue=None, allow_split=True):
     """Stride-1 'same' correlation.  x [N,I,H,W] channels-last, wk memory [G][O][k*k][I].  epilogue = dict(b, noise, strength, act, slope, gain, clamp)."""
     n, ci, h, wd = x.shape
     co = wk.shape[1]
-    y = torch.empty(n, co, h, wd, device=x.device, dtype=torch.float32, memory_format=CL)
     e = epilogue or {}
-    flags = (0 if allow_split else 32) | TC2_FLAGS
+    y, flags = _tc2_output(0, n, co, h, wd, h, wd, ci, k, per_sample, epilogue, (0 if allow_split else 32) | TC2_FLAGS, x.device)
     with _lib.timed('conv', 2 * n * h * wd * k * k * ci * co, detail=f's1 k{k} {n}x{ci}->{co} @{h}x{wd}' + (' +epilogue' if epilogue else '')):
         _lib.check(_lib.load().spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, k, int(per_sample), _lib.ptr(e.get('b')),
                                               _lib.ptr(e.get('noise')), _lib.ptr(e.get('strength')), int(e.get('act', 0)), float(e.get('slope', 0.2)),
@@ -87,9 +102,9 @@ def tc2_t2(x, wk, per_sample):
     """Stride-2 transposed 3x3 convolution, no padding: [N,I,H,W] -> [N,O,2H+1,2W+1]; wk memory [G][O][9][I]."""
     n, ci, h, wd = x.shape
     co = wk.shape[1]
-    y = torch.empty(n, co, 2 * h + 1, 2 * wd + 1, device=x.device, dtype=torch.float32, memory_format=CL)
+    y, flags = _tc2_output(1, n, co, 2 * h + 1, 2 * wd + 1, h, wd, ci, 3, per_sample, None, 0, x.device)
     with _lib.timed('conv', 2 * n * h * wd * 9 * ci * co, detail=f't2 {n}x{ci}->{co} @{h}x{wd}'):
-        _lib.check(_lib.load().spi_conv_transpose2d_s2_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), 0, _lib.stream()))
+        _lib.check(_lib.load().spi_conv_transpose2d_s2_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), flags, _lib.stream()))
     return y
 
 
@@ -98,9 +113,9 @@ def tc2_s2(x, wk, per_sample):
     n, ci, hi, wi = x.shape
     h, wd = (hi - 1) // 2, (wi - 1) // 2
     co = wk.shape[1]
-    y = torch.empty(n, co, h, wd, device=x.device, dtype=torch.float32, memory_format=CL)
+    y, flags = _tc2_output(2, n, co, h, wd, h, wd, ci, 3, per_sample, None, 0, x.device)
     with _lib.timed('conv', 2 * n * h * wd * 9 * ci * co, detail=f's2 {n}x{ci}->{co} ->{h}x{wd}'):
-        _lib.check(_lib.load().spi_conv2d_s2_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), 0, _lib.stream()))
+        _lib.check(_lib.load().spi_conv2d_s2_tc2(_lib.ptr(x), _lib.ptr(wk), _lib.ptr(y), n, h, wd, ci, co, int(per_sample), flags, _lib.stream()))
     return y
 
 
@@ -171,15 +186,22 @@ def _weight_grad(form, gy, x, w5, stride, padding, transpose):
     n = x.shape[0]
     o, i, kh, kw = w5.shape[1:]
     if form == 'rgb':
-        gw = torch.empty(g, o, i, device=x.device, dtype=torch.float32)
-        return rgb_conv(2, x, gy, n, x.shape[2] * x.shape[3], i, o, g > 1, gw).view(g, o, i, 1, 1)
+        gw = zero_arena.take((g, o, i))
+        which = 2 if gw is None else 2 | 4                     # + 4: gw is already zero
+        if gw is None:
+            gw = torch.empty(g, o, i, device=x.device, dtype=torch.float32)
+        return rgb_conv(which, x, gy, n, x.shape[2] * x.shape[3], i, o, g > 1, gw).view(g, o, i, 1, 1)
     if WGRAD_ENGINE == 'tc2' and form is not None:
         h, wd = x.shape[2], x.shape[3]
         mode = 0 if form == 's1' else 1
         # mode 0 writes [G][O][taps][I]; mode 1 (transposed convolution: the roles of x and dy swap) writes [G][I][taps][O]
-        gw = torch.empty((g, o, kh, kw, i) if mode == 0 else (g, i, kh, kw, o), device=x.device, dtype=torch.float32)
+        shape = (g, o, kh, kw, i) if mode == 0 else (g, i, kh, kw, o)
+        gw = zero_arena.take(shape)                            # the kernel reduce-adds its partial sums into gw
+        zeroed = 0 if gw is None else 4
+        if gw is None:
+            gw = torch.empty(shape, device=x.device, dtype=torch.float32)
         with _lib.timed('conv', 2 * n * h * wd * kh * kw * i * o, detail=f'wgrad{mode} k{kh} {n}x{i}->{o} @{h}x{wd}'):
-            _lib.check(_lib.load().spi_conv_wgrad_tc2(_lib.ptr(x), _lib.ptr(gy), _lib.ptr(gw), n, h, wd, i, o, kh, int(g > 1), mode, _lib.stream()))
+            _lib.check(_lib.load().spi_conv_wgrad_tc2(_lib.ptr(x), _lib.ptr(gy), _lib.ptr(gw), n, h, wd, i, o, kh, int(g > 1), mode | zeroed, _lib.stream()))
         return gw.permute(0, 1, 4, 2, 3) if mode == 0 else gw.permute(0, 4, 1, 2, 3)
     _cudnn_flags()
     gw = torch.empty_like(w5) if g > 1 else None          # preserves w5's (conv-native) strides

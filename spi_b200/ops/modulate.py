@@ -6,9 +6,11 @@ for the stride-2 transposed convolution), so no layout-conversion copy sits betw
 import torch
 
 from .. import _lib
+from . import zero_arena
 
 LAYOUTS = {'oihw': 0, 'ohwi': 1, 'ihwo': 2}
 FLIP = 4          # + FLIP: the taps are written reversed (the result equals w.flip([3, 4])), see modulate.cu
+PREZEROED = 8     # backward only: grad_styles handed in is already zero (ops/zero_arena.py)
 
 
 def _alloc(n, o, i, kh, kw, layout, device):
@@ -46,10 +48,14 @@ class _Modulate(torch.autograd.Function):
             ref.copy_(g)
             g = ref
         gw = torch.empty_like(weight) if ctx.needs_input_grad[0] else None
-        gs = torch.empty_like(styles) if ctx.needs_input_grad[1] else None
+        gs = zeroed = None
+        if ctx.needs_input_grad[1]:           # accumulated with atomics over the output channels: zero on entry
+            gs = zeroed = zero_arena.take(styles.shape)
+            if gs is None:
+                gs = torch.empty_like(styles)
         _lib.check(_lib.load().spi_modulate_weights_backward(_lib.ptr(weight), _lib.ptr(styles), _lib.ptr(dcoef), _lib.ptr(g),
-                                                             _lib.ptr(gw), _lib.ptr(gs), n, o, i, kh * kw, int(ctx.demodulate), ctx.layout,
-                                                             _lib.stream()))
+                                                             _lib.ptr(gw), _lib.ptr(gs), n, o, i, kh * kw, int(ctx.demodulate),
+                                                             ctx.layout | (PREZEROED if zeroed is not None else 0), _lib.stream()))
         return gw, gs, None, None
 
 

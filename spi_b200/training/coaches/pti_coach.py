@@ -5,6 +5,7 @@ import torch
 
 from ...configs import global_config, hyperparameters, paths_config
 from ...graphs import GraphedStep
+from ...ops import zero_arena
 from ...utils import rng
 from ...criteria.l2_loss import l2_loss
 from .base_coach import BaseCoach
@@ -28,6 +29,11 @@ class SingleIDCoach(BaseCoach):
         return loss, loss_lpips
 
     def _body(self, w_pivot, camera, image):
+        # one zero-filled buffer per iteration for every accumulate-into output (ops/zero_arena.py)
+        with zero_arena.iteration(('pti', tuple(w_pivot.shape), tuple(image.shape)), w_pivot.device):
+            return self._iteration(w_pivot, camera, image)
+
+    def _iteration(self, w_pivot, camera, image):
         """pti_coach.py:62-74 without host synchronisation; the early exit is applied on the device (conditional Adam)."""
         generated_images = self.G.synthesis(w_pivot, camera, noise_mode='const')['image']
         loss, loss_lpips = self.calc_loss(generated_images, image)

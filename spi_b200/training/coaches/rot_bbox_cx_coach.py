@@ -8,6 +8,7 @@ import torch
 
 from ...configs import global_config, hyperparameters, paths_config
 from ...graphs import GraphedStep
+from ...ops import zero_arena
 from ...utils import rng
 from ...criteria.bbox_cx_loss import BoxCXLoss
 from ...criteria.l2_loss import l2_loss
@@ -42,6 +43,11 @@ class RotBboxCoach(BaseCoach):
         self.box_cx_loss = box_cx_loss if box_cx_loss is not None else BoxCXLoss().to(global_config.device).eval()
 
     def _body(self, heavy, st, w_pivot, rot_bs=4):
+        # one zero-filled buffer per iteration for every accumulate-into output (ops/zero_arena.py); light and heavy iterations differ in size
+        with zero_arena.iteration(('rot', bool(heavy), rot_bs, tuple(w_pivot.shape)), w_pivot.device):
+            return self._iteration(heavy, st, w_pivot, rot_bs)
+
+    def _iteration(self, heavy, st, w_pivot, rot_bs=4):
         """One iteration of rot_bbox_cx_coach.py:68-157 without host synchronisation (capturable as a CUDA graph).
         The early exit (`if loss_lpips <= threshold: break` BEFORE `optimizer.step()`, :148-151) is applied on the device:
         the Adam kernel is a no-op when the LPIPS scalar is below the threshold; the host reads the scalar afterwards."""

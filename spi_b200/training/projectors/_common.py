@@ -14,6 +14,7 @@ import torch.nn.functional as F
 
 from ...configs import global_config
 from ...graphs import GraphedStep
+from ...ops import zero_arena
 from ...optim import FlatAdam
 from ...ops import noise_reg
 from ...ops.resize import downsample2x
@@ -91,6 +92,11 @@ class LatentProjector:
         return hp['lr0'] * lr_ramp, w_noise_scale
 
     def _body(self):
+        # one zero-filled buffer per iteration for every accumulate-into output (ops/zero_arena.py)
+        with zero_arena.iteration(('projector', self.kind, tuple(self.w_opt.shape)), self.w_opt.device):
+            return self._iteration()
+
+    def _iteration(self):
         """One iteration, free of host synchronisation (capturable): mirror_projector.py:93-131."""
         ws = self.w_opt + rng.randn_like(self.w_opt) * self.w_noise_scale
         G = self.G

@@ -197,3 +197,56 @@ def test_rgb_head_1x1_conv(lib, n, ci, h, per_sample):
     yr = torch.cat([F.conv2d(xr[i:i + 1], wr[i if per_sample else 0]) for i in range(n)])
     yr.backward(gy.double())
     assert rel_l2(y, yr) < 1e-5 and rel_l2(xg.grad, xr.grad) < 1e-5 and rel_l2(wg.grad, wr.grad) < 1e-4
+
+
+def test_zero_arena_outputs_equal_self_zeroed_outputs(lib):
+    """Accumulate-into outputs (Cin-split convolutions, weight gradients, RGB weight gradient, style gradients of the modulation backward)
+    carved from the per-iteration zero arena give the results of the calls that zero-fill their own output; the second iteration of a
+    kind gets the arena (sized by the first) and the library's fill is skipped (flag), a third, larger request falls back."""
+    from spi_b200.ops import conv as E
+    from spi_b200.ops import zero_arena as Z
+    from spi_b200.ops.modulate import modulate_weights
+
+    def work(scale=1):
+        gen = torch.Generator().manual_seed(11)
+        outs = []
+        for (n, ci, co, h, k, ps) in [(1, 512, 512, 8 * scale, 3, False), (2, 256, 512, 16, 3, True), (1, 128, 128, 64, 3, False)]:
+            x = torch.randn(n, ci, h, h, generator=gen).cuda().contiguous(memory_format=CL).requires_grad_(True)
+            w = (torch.randn(n if ps else 1, co, ci, k, k, generator=gen) / (ci * k * k) ** 0.5).cuda().requires_grad_(True)
+            y = E.conv2d_per_sample(x, w, padding=k // 2)
+            gy = torch.randn(y.shape, generator=gen).cuda().contiguous(memory_format=CL)
+            gx, gw = torch.autograd.grad(y, [x, w], gy)
+            outs += [y.detach(), gx, gw]
+        # stride-2 transposed layer on a small map + modulation backward (style gradients) + RGB head
+        x = torch.randn(1, 256, 16, 16, generator=gen).cuda().contiguous(memory_format=CL).requires_grad_(True)
+        wt = torch.randn(128, 256, 3, 3, generator=gen).cuda().requires_grad_(True)
+        s = (1 + 0.1 * torch.randn(1, 256, generator=gen)).cuda().requires_grad_(True)
+        w5 = modulate_weights(wt, s, True, layout='ohwi', flip=True)
+        y = E.conv2d_per_sample(x, w5, stride=2, padding=0, transpose=True)
+        outs += [y.detach()] + list(torch.autograd.grad(y.square().sum(), [x, wt, s]))
+        x = torch.randn(2, 128, 32, 32, generator=gen).cuda().contiguous(memory_format=CL).requires_grad_(True)
+        w = torch.randn(2, 3, 128, 1, 1, generator=gen).cuda().requires_grad_(True)
+        y = E.conv2d_per_sample(x, w, padding=0)
+        outs += [y.detach()] + list(torch.autograd.grad(y.square().sum(), [x, w]))
+        return outs
+
+    Z.reset()
+    plain = work()
+    with Z.iteration('test', torch.device('cuda')):
+        first = work()                     # no hint yet: every take() falls back
+        assert not Z.active()
+    assert Z._hint['test'] > 0
+    with Z.iteration('test', torch.device('cuda')):
+        assert Z.active()
+        second = work()
+        used = Z._state[2]
+    assert used == Z._hint['test'] and used > 0
+    with Z.iteration('test', torch.device('cuda')):
+        third = work(scale=2)              # asks for more than the arena holds: the tail of the requests falls back
+    assert lib.spi_tc_error() == 0
+    for a, b, c in zip(plain, first, second):
+        assert rel_l2(b, a) < 1e-6 and rel_l2(c, a) < 1e-6
+    ref3 = work(scale=2)
+    for a, b in zip(ref3, third):
+        assert rel_l2(b, a) < 1e-6
+    Z.reset()

@@ -221,3 +221,27 @@ def test_bench_schedule_accepts_any_step_count():
             hm, hh, hl = bench.mix_of(half)
             assert abs(hm - n_mir / 2) <= 1 and abs(hh - heavy / 2) <= 1
     assert bench.mix_of(bench.schedule(24)) == (8, 4, 12) and bench.mix_of(bench.schedule(20)) == (7, 3, 10)
+
+
+def test_zero_arena_sizing_and_fallback():
+    """ops/zero_arena.py host logic on CPU tensors: the first iteration of a kind only records its requests, the second gets one zeroed
+    buffer of exactly that size, slices are 1 KiB-aligned, disjoint and shaped as asked, an over-ask returns None."""
+    from spi_b200.ops import zero_arena as Z
+    Z.reset()
+    cpu = torch.device('cpu')
+    assert Z.take((4, 4)) is None                       # outside an iteration
+    with Z.iteration('k', cpu):
+        assert not Z.active() and Z.take((3, 5)) is None and Z.take((2, 8, 4, 4), channels_last=True) is None
+    assert Z._hint['k'] == 1024 + 1024
+    with Z.iteration('k', cpu):
+        assert Z.active()
+        a = Z.take((3, 5))
+        b = Z.take((2, 8, 4, 4), channels_last=True)
+        c = Z.take((1,))
+        assert a.shape == (3, 5) and a.dtype == torch.float32 and float(a.abs().sum()) == 0
+        assert b.shape == (2, 8, 4, 4) and b.is_contiguous(memory_format=torch.channels_last)
+        assert b.data_ptr() - a.data_ptr() == 1024 and c is None
+    assert Z._hint['k'] == 3 * 1024                      # the over-ask is remembered: the next iteration's buffer has room for it
+    with Z.iteration('other', cpu):
+        assert not Z.active()
+    Z.reset()
