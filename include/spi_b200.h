@@ -147,6 +147,19 @@ int spi_modulate_weights_backward(const float* weight, const float* styles, cons
                                   float* grad_weight, float* grad_styles, int n, int o, int i, int kk, int demodulate,
                                   int layout, cudaStream_t stream);
 
+/* The same for every modulated convolution of a network at once (one launch each; per-layer HOST tables of `layers` <= 32 entries):
+ * forward (layouts 0 / 1 only), backward (grad_styles[l] must be ZERO on entry: the caller packs them into one zero-filled buffer), and
+ * the [g][o][taps][i] -> [g][i][taps'][o] re-layouts the data-gradient convolutions read (spi_conv_weight_transpose for many tensors). */
+int spi_modulate_weights_many(int layers, const float* const* weight, const float* const* styles, float* const* out, float* const* dcoef,
+                              const int* n, const int* o, const int* i, const int* kk, const int* demodulate, const int* layout,
+                              cudaStream_t stream);
+int spi_modulate_weights_backward_many(int layers, const float* const* weight, const float* const* styles, const float* const* dcoef,
+                                       const float* const* grad_out, float* const* grad_weight, float* const* grad_styles, const int* n,
+                                       const int* o, const int* i, const int* kk, const int* demodulate, const int* layout,
+                                       cudaStream_t stream);
+int spi_conv_weight_transpose_many(int layers, const float* const* w, float* const* wt, const int* g, const int* o, const int* taps,
+                                   const int* i, const int* reverse, cudaStream_t stream);
+
 /* ---- style bank: all affine layers of a synthesis network in one launch (FullyConnectedLayer(w_dim, in_channels, bias_init=1)
  *      inside every SynthesisLayer / ToRGBLayer, eg3d/training/networks_stylegan2.py:282,316,352,357-358) ----------------- */
 /* out[l][n,i] = ogain[l] * (wgain[l] * sum_k ws[n, widx[l], k] * W[l][i,k] + bgain[l] * b[l][i]).  ws has element strides

@@ -41,6 +41,9 @@ _SIGS = {
     'spi_epilogue_grad_reduce': [c_void_p, c_ll, c_int, c_int] + [c_void_p] * 4 + [c_void_p],
     'spi_modulate_weights': [c_void_p] * 4 + [c_int] * 6 + [c_void_p],
     'spi_modulate_weights_backward': [c_void_p] * 6 + [c_int] * 6 + [c_void_p],
+    'spi_modulate_weights_many': [c_int] + [c_void_p] * 10 + [c_void_p],
+    'spi_modulate_weights_backward_many': [c_int] + [c_void_p] * 12 + [c_void_p],
+    'spi_conv_weight_transpose_many': [c_int] + [c_void_p] * 7 + [c_void_p],
     'spi_style_bank_forward': [c_void_p, c_ll, c_ll, c_int, c_int, c_int] + [c_void_p] * 8 + [c_void_p],
     'spi_style_bank_backward': [c_void_p, c_ll, c_ll, c_int, c_int, c_int] + [c_void_p] * 9 + [c_void_p, c_int, c_void_p],
     'spi_downsample2x': [c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_void_p],

@@ -115,13 +115,12 @@ __global__ void __launch_bounds__(256) modulate_bwd_kernel(const float* __restri
 
 // Forward, layouts 0 (OIK) and 1 (OKI): grid (O, N), one CTA per output row; the modulated row W*s is staged in shared
 // memory, reduced for the demodulation coefficient, and written out in the destination order with coalesced stores.
-__global__ void __launch_bounds__(256) modulate_row_kernel(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ dcoef,
-                                                           float* __restrict__ out, int O, int I, int KK, int layout_flags, int demod) {
-    extern __shared__ float row[];
-    __shared__ float sh[32];
+__device__ __forceinline__ void modulate_row_body(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ dcoef,
+                                                  float* __restrict__ out, int O, int I, int KK, int layout_flags, int demod, int o, int n,
+                                                  float* row, float* sh) {
     const int layout = layout_flags & 3;
     const bool flip = (layout_flags & 4) != 0;
-    const int o = blockIdx.x, n = blockIdx.y, len = I * KK;
+    const int len = I * KK;
     const float* w = W + (size_t)o * len;
     const float* sn = s + (size_t)n * I;
     float acc = 0.f;
@@ -150,6 +149,13 @@ __global__ void __launch_bounds__(256) modulate_row_kernel(const float* __restri
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) modulate_row_kernel(const float* __restrict__ W, const float* __restrict__ s, float* __restrict__ dcoef,
+                                                           float* __restrict__ out, int O, int I, int KK, int layout_flags, int demod) {
+    extern __shared__ float row[];
+    __shared__ float sh[32];
+    modulate_row_body(W, s, dcoef, out, O, I, KK, layout_flags, demod, blockIdx.x, blockIdx.y, row, sh);
 }
 
 // Forward, layout 2 (IKO, the transposed-convolution weights): 32 x 32 (o, e) tiles transposed through shared memory so that
@@ -189,15 +195,12 @@ __global__ void __launch_bounds__(256) modulate_apply_iko_kernel(const float* __
 // Backward, every layout: grid (O); the W row and the incoming gradient row are staged in shared memory in W's own (i, k)
 // order (coalesced loads for layouts 0 and 1), then each thread owns whole channels i: A, t, dW and ds come from shared memory,
 // dW leaves through a coalesced store.  Shared memory: 2 * I * KK floats.
-__global__ void __launch_bounds__(256) modulate_bwd_rows_kernel(const float* __restrict__ W, const float* __restrict__ s,
-                                                                const float* __restrict__ dcoef, const float* __restrict__ g,
-                                                                float* __restrict__ dW, float* __restrict__ ds, int N, int O, int I, int KK,
-                                                                int demod, int layout_flags) {
-    extern __shared__ float sm[];
-    __shared__ float sh[32];
+__device__ __forceinline__ void modulate_bwd_rows_body(const float* __restrict__ W, const float* __restrict__ s, const float* __restrict__ dcoef,
+                                                       const float* __restrict__ g, float* __restrict__ dW, float* __restrict__ ds, int N, int O,
+                                                       int I, int KK, int demod, int layout_flags, int o, float* sm, float* sh) {
     const int layout = layout_flags & 3;
     const bool flip = (layout_flags & 4) != 0;
-    const int o = blockIdx.x, len = I * KK;
+    const int len = I * KK;
     float* wrow = sm;
     float* grow = sm + len;
     const float* w = W + (size_t)o * len;
@@ -259,6 +262,47 @@ __global__ void __launch_bounds__(256) modulate_bwd_rows_kernel(const float* __r
             else { for (int e = threadIdx.x; e < len; e += blockDim.x) dw[e] += grow[e]; }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) modulate_bwd_rows_kernel(const float* __restrict__ W, const float* __restrict__ s,
+                                                                const float* __restrict__ dcoef, const float* __restrict__ g,
+                                                                float* __restrict__ dW, float* __restrict__ ds, int N, int O, int I, int KK,
+                                                                int demod, int layout_flags) {
+    extern __shared__ float sm[];
+    __shared__ float sh[32];
+    modulate_bwd_rows_body(W, s, dcoef, g, dW, ds, N, O, I, KK, demod, layout_flags, blockIdx.x, sm, sh);
+}
+
+// ---- the same two kernels over EVERY modulated convolution of a synthesis network in one launch each (the per-layer launches are small
+// -- 20 MB of traffic, 8 / 12 us -- and latency-bound; grouped, the 26 layers of the generator stream their 120 MB of weights once).
+constexpr int MOD_MAX = 32;
+struct ModLayer {
+    const float* W; const float* s; float* dcoef; float* out;      // forward
+    const float* g; float* dW; float* ds;                          // backward
+    int O, I, KK, n, layout_flags, demod, row0;
+};
+struct ModArgs {
+    ModLayer layer[MOD_MAX];
+    int layers, rows;
+};
+
+__global__ void __launch_bounds__(256) modulate_rows_many_kernel(const __grid_constant__ ModArgs a) {
+    extern __shared__ float row[];
+    __shared__ float sh[32];
+    int l = 0;
+    while (l + 1 < a.layers && a.layer[l + 1].row0 <= (int)blockIdx.x) l++;
+    const ModLayer& L = a.layer[l];
+    const int r = blockIdx.x - L.row0;
+    modulate_row_body(L.W, L.s, L.dcoef, L.out, L.O, L.I, L.KK, L.layout_flags, L.demod, r % L.O, r / L.O, row, sh);
+}
+
+__global__ void __launch_bounds__(256) modulate_bwd_rows_many_kernel(const __grid_constant__ ModArgs a) {
+    extern __shared__ float sm[];
+    __shared__ float sh[32];
+    int l = 0;
+    while (l + 1 < a.layers && a.layer[l + 1].row0 <= (int)blockIdx.x) l++;
+    const ModLayer& L = a.layer[l];
+    modulate_bwd_rows_body(L.W, L.s, L.dcoef, L.g, L.dW, L.ds, L.n, L.O, L.I, L.KK, L.demod, L.layout_flags, blockIdx.x - L.row0, sm, sh);
 }
 
 }  // namespace
@@ -466,5 +510,128 @@ extern "C" int spi_style_bank_backward(const float* ws, long long ws_sn, long lo
     }
     SPI_COUNT_LAUNCH(launches);
     SPI_LAUNCH_CHECK("style_bank_backward");
+    return SPI_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Grouped entry points: every modulated convolution of a network per launch.  All tables are HOST arrays of `layers` entries (<= 32).
+namespace {
+
+// w [G][O][T][I] -> wt [G][I][T'][O] for many tensors in one launch (T' = T-1-t when reverse): 32 x 32 tiles through shared memory
+struct TrLayer { const float* w; float* wt; int g, o, taps, i, reverse, tiles_i, tiles_o, tile0; };
+struct TrArgs { TrLayer layer[MOD_MAX]; int layers; };
+
+__global__ void __launch_bounds__(256) weight_transpose_many_kernel(const __grid_constant__ TrArgs a) {
+    __shared__ float tile[32][33];
+    int l = 0;
+    while (l + 1 < a.layers && a.layer[l + 1].tile0 <= (int)blockIdx.x) l++;
+    const TrLayer& L = a.layer[l];
+    int r = blockIdx.x - L.tile0;
+    const int ti = r % L.tiles_i; r /= L.tiles_i;
+    const int to = r % L.tiles_o; r /= L.tiles_o;
+    const int t = r % L.taps, g = r / L.taps;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int o0 = to * 32, i0 = ti * 32;
+    const float* src = L.w + ((size_t)g * L.o * L.taps + t) * L.i;
+    float* dst = L.wt + ((size_t)g * L.i * L.taps + (L.reverse ? L.taps - 1 - t : t)) * L.o;
+    for (int q = ty; q < 32; q += 8) {
+        const int oo = o0 + q, ii = i0 + tx;
+        tile[q][tx] = (oo < L.o && ii < L.i) ? src[(size_t)oo * L.taps * L.i + ii] : 0.f;
+    }
+    __syncthreads();
+    for (int q = ty; q < 32; q += 8) {
+        const int ii = i0 + q, oo = o0 + tx;
+        if (ii < L.i && oo < L.o) dst[(size_t)ii * L.taps * L.o + oo] = tile[tx][q];
+    }
+}
+
+}  // namespace
+
+extern "C" int spi_conv_weight_transpose_many(int layers, const float* const* w, float* const* wt, const int* g, const int* o, const int* taps,
+                                              const int* i, const int* reverse, cudaStream_t stream) {
+    SPI_CHECK_ARG(layers >= 1 && layers <= MOD_MAX && w && wt && g && o && taps && i && reverse, "conv_weight_transpose_many: bad tables (layers=%d)", layers);
+    TrArgs a{};
+    long long tiles = 0;
+    for (int l = 0; l < layers; l++) {
+        SPI_CHECK_ARG(w[l] && wt[l] && g[l] > 0 && o[l] > 0 && taps[l] > 0 && i[l] > 0, "conv_weight_transpose_many: layer %d: bad arguments", l);
+        TrLayer& L = a.layer[l];
+        L.w = w[l]; L.wt = wt[l]; L.g = g[l]; L.o = o[l]; L.taps = taps[l]; L.i = i[l]; L.reverse = reverse[l] ? 1 : 0;
+        L.tiles_i = (i[l] + 31) / 32; L.tiles_o = (o[l] + 31) / 32; L.tile0 = (int)tiles;
+        tiles += (long long)L.tiles_i * L.tiles_o * taps[l] * g[l];
+        SPI_CHECK_ARG(tiles < (1LL << 30), "conv_weight_transpose_many: too many tiles");
+    }
+    a.layers = layers;
+    weight_transpose_many_kernel<<<(unsigned)tiles, 256, 0, stream>>>(a);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("conv_weight_transpose_many");
+    return SPI_OK;
+}
+
+// Forward of spi_modulate_weights for `layers` convolutions at once; layout[l] in {0, 1} (+4: taps reversed), rows of at most 40 KB.
+extern "C" int spi_modulate_weights_many(int layers, const float* const* weight, const float* const* styles, float* const* out, float* const* dcoef,
+                                         const int* n, const int* o, const int* i, const int* kk, const int* demodulate, const int* layout,
+                                         cudaStream_t stream) {
+    SPI_CHECK_ARG(layers >= 1 && layers <= MOD_MAX && weight && styles && out && dcoef && n && o && i && kk && demodulate && layout,
+                  "modulate_weights_many: bad tables (layers=%d)", layers);
+    ModArgs a{};
+    long long rows = 0;
+    size_t smem = 0;
+    for (int l = 0; l < layers; l++) {
+        SPI_CHECK_ARG(weight[l] && styles[l] && out[l] && n[l] >= 1 && o[l] >= 1 && i[l] >= 1 && kk[l] >= 1, "modulate_weights_many: layer %d: bad arguments", l);
+        SPI_CHECK_ARG(layout[l] >= 0 && layout[l] < 8 && (layout[l] & 3) <= 1, "modulate_weights_many: layer %d: layout must be 0 (OIK) or 1 (OKI), +4 to reverse the taps", l);
+        SPI_CHECK_ARG(!demodulate[l] || dcoef[l], "modulate_weights_many: layer %d: dcoef buffer required when demodulating", l);
+        const size_t row_bytes = sizeof(float) * (size_t)i[l] * kk[l];
+        SPI_CHECK_ARG(row_bytes <= 40 * 1024, "modulate_weights_many: layer %d: row of %zu bytes does not fit (use spi_modulate_weights)", l, row_bytes);
+        smem = row_bytes > smem ? row_bytes : smem;
+        ModLayer& L = a.layer[l];
+        L.W = weight[l]; L.s = styles[l]; L.dcoef = dcoef[l]; L.out = out[l];
+        L.O = o[l]; L.I = i[l]; L.KK = kk[l]; L.n = n[l]; L.layout_flags = layout[l]; L.demod = demodulate[l] ? 1 : 0; L.row0 = (int)rows;
+        rows += (long long)o[l] * n[l];
+        SPI_CHECK_ARG(rows < (1LL << 30), "modulate_weights_many: too many rows");
+    }
+    a.layers = layers; a.rows = (int)rows;
+    modulate_rows_many_kernel<<<(unsigned)rows, 256, smem, stream>>>(a);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("modulate_weights_many");
+    return SPI_OK;
+}
+
+// Backward of the same: grad_out[l] in layout[l]; grad_weight[l] (null: not wanted) overwritten; grad_styles[l] (null: not wanted) must be ZERO
+// on entry (the caller packs them into one zero-filled buffer: they are accumulated with atomics over the output channels).
+extern "C" int spi_modulate_weights_backward_many(int layers, const float* const* weight, const float* const* styles, const float* const* dcoef,
+                                                  const float* const* grad_out, float* const* grad_weight, float* const* grad_styles, const int* n,
+                                                  const int* o, const int* i, const int* kk, const int* demodulate, const int* layout,
+                                                  cudaStream_t stream) {
+    SPI_CHECK_ARG(layers >= 1 && layers <= MOD_MAX && weight && styles && dcoef && grad_out && grad_weight && grad_styles && n && o && i && kk && demodulate && layout,
+                  "modulate_weights_backward_many: bad tables (layers=%d)", layers);
+    ModArgs a{};
+    long long rows = 0;
+    size_t smem = 0;
+    for (int l = 0; l < layers; l++) {
+        SPI_CHECK_ARG(weight[l] && styles[l] && grad_out[l] && n[l] >= 1 && o[l] >= 1 && i[l] >= 1 && kk[l] >= 1, "modulate_weights_backward_many: layer %d: bad arguments", l);
+        SPI_CHECK_ARG(layout[l] >= 0 && layout[l] < 8 && (layout[l] & 3) <= 2, "modulate_weights_backward_many: layer %d: bad layout", l);
+        SPI_CHECK_ARG(!demodulate[l] || dcoef[l], "modulate_weights_backward_many: layer %d: dcoef required when demodulating", l);
+        const size_t rows_bytes = 2 * sizeof(float) * (size_t)i[l] * kk[l];
+        SPI_CHECK_ARG(rows_bytes <= 80 * 1024, "modulate_weights_backward_many: layer %d: rows of %zu bytes do not fit (use spi_modulate_weights_backward)", l, rows_bytes);
+        smem = rows_bytes > smem ? rows_bytes : smem;
+        ModLayer& L = a.layer[l];
+        L.W = weight[l]; L.s = styles[l]; L.dcoef = const_cast<float*>(dcoef[l]); L.g = grad_out[l]; L.dW = grad_weight[l]; L.ds = grad_styles[l];
+        L.O = o[l]; L.I = i[l]; L.KK = kk[l]; L.n = n[l]; L.layout_flags = layout[l]; L.demod = demodulate[l] ? 1 : 0; L.row0 = (int)rows;
+        rows += o[l];
+    }
+    a.layers = layers; a.rows = (int)rows;
+    if (smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            if (cudaFuncSetAttribute(modulate_bwd_rows_many_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024) != cudaSuccess) {
+                spi_set_error("modulate_weights_backward_many: cannot reserve 80 KB of shared memory");
+                return SPI_ERR_CUDA;
+            }
+            configured = true;
+        }
+    }
+    modulate_bwd_rows_many_kernel<<<(unsigned)rows, 256, smem, stream>>>(a);
+    SPI_COUNT_LAUNCH(1);
+    SPI_LAUNCH_CHECK("modulate_weights_backward_many");
     return SPI_OK;
 }

@@ -167,7 +167,8 @@ def _wT(wk, reverse, frozen):
     return hit[0]
 
 
-def _tc2_input_grad(form, gy, wk, frozen=False):
+def _tc2_input_grad(form, gy, wk, frozen=False, wT=None):
+    """dL/dx.  `wT`: the transposed weights [G][I][taps'][O] when the caller already has them (ops/modulate.py `modulate_bank`)."""
     per_sample = wk.shape[0] > 1
     if form == 'rgb':
         n, co, h, wd = gy.shape
@@ -176,8 +177,8 @@ def _tc2_input_grad(form, gy, wk, frozen=False):
         return rgb_conv(1, gy, wk, n, h * wd, ci, co, per_sample, gx)
     if form == 's1':
         k = int(round(wk.shape[2] ** 0.5))
-        return tc2_s1(gy, _wT(wk, True, frozen), k, per_sample)
-    return tc2_s2(gy, _wT(wk, False, frozen), per_sample)
+        return tc2_s1(gy, wT if wT is not None else _wT(wk, True, frozen), k, per_sample)
+    return tc2_s2(gy, wT if wT is not None else _wT(wk, False, frozen), per_sample)
 
 
 def _weight_grad(form, gy, x, w5, stride, padding, transpose):
@@ -224,7 +225,7 @@ class _PerSampleConv(torch.autograd.Function):
     """y[n] = conv(x[n], w[n]) (or conv_transpose) for n in range(N); x [N,C,H,W] channels-last, w [G,O,I,kh,kw] logical, G in {1, N}."""
 
     @staticmethod
-    def forward(ctx, x, w, stride, padding, transpose):
+    def forward(ctx, x, w, stride, padding, transpose, wT=None):
         n, _, h, wd = x.shape
         o, kh, kw = w.shape[1], w.shape[3], w.shape[4]
         st, pd = _pair(stride), _pair(padding)
@@ -233,7 +234,7 @@ class _PerSampleConv(torch.autograd.Function):
         ctx.cfg = (stride, padding, transpose, form)
         if form is not None:
             y, wk = _tc2_forward(form, x, w)
-            ctx.save_for_backward(x, w, wk)
+            ctx.save_for_backward(x, w, wk, wT)
             return y
         _cudnn_flags()
         if transpose:
@@ -241,7 +242,7 @@ class _PerSampleConv(torch.autograd.Function):
         else:
             oh, ow = (h + 2 * pd[0] - kh) // st[0] + 1, (wd + 2 * pd[1] - kw) // st[1] + 1
         shared = (w.shape[0] == 1 and n > 1)       # one weight set for the whole batch: a single batched call
-        ctx.save_for_backward(x, w, None)
+        ctx.save_for_backward(x, w, None, None)
         if shared or n == 1:
             wk = (w[0].transpose(0, 1) if transpose else w[0]).contiguous(memory_format=CL)
             if transpose:
@@ -258,14 +259,14 @@ class _PerSampleConv(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gy):
-        x, w, wk = ctx.saved_tensors
+        x, w, wk, wT = ctx.saved_tensors
         stride, padding, transpose, form = ctx.cfg
         need_x, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         gy = _cl(gy)
         if form is not None:
-            gx = _tc2_input_grad(form, gy, wk, frozen=not need_w) if need_x else None
+            gx = _tc2_input_grad(form, gy, wk, frozen=not need_w, wT=wT) if need_x else None
             gw = _weight_grad(form, gy, x, w, stride, padding, transpose) if need_w else None
-            return gx, gw, None, None, None
+            return gx, gw, None, None, None, None
         _cudnn_flags()
         n = x.shape[0]
         shared = (w.shape[0] == 1 and n > 1)
@@ -274,7 +275,7 @@ class _PerSampleConv(torch.autograd.Function):
             gx, gwk, _ = torch.ops.aten.convolution_backward(gy, x, wc, None, _pair(stride), _pair(padding), [1, 1], transpose, [0, 0], 1,
                                                              [need_x, need_w, False])
             gw = (gwk.transpose(0, 1) if transpose else gwk).unsqueeze(0) if need_w else None
-            return gx, gw, None, None, None
+            return gx, gw, None, None, None, None
         gx = torch.empty_like(x) if need_x else None
         gw = torch.empty_like(w) if need_w else None          # preserves w's (conv-native) strides
         for k in [slice(i, i + 1) for i in range(n)]:
@@ -285,7 +286,7 @@ class _PerSampleConv(torch.autograd.Function):
                 gx[k].copy_(gxk)
             if need_w:
                 gw[k.start].copy_(gwk.transpose(0, 1) if transpose else gwk)
-        return gx, gw, None, None, None
+        return gx, gw, None, None, None, None
 
 
 class _ConvBiasActNoise(torch.autograd.Function):
@@ -295,21 +296,21 @@ class _ConvBiasActNoise(torch.autograd.Function):
     noise reductions, then the data- and weight-gradient convolutions."""
 
     @staticmethod
-    def forward(ctx, x, w, b, noise_const, noise_strength, cfg):
+    def forward(ctx, x, w, b, noise_const, noise_strength, cfg, wT=None):
         dim, spec, alpha, gain, clamp = cfg
         x = _cl(x)
         nc = noise_const.contiguous() if noise_const is not None else None
         epi = dict(b=b.contiguous() if b is not None else None, noise=nc, strength=noise_strength, act={'linear': 0, 'relu': 1, 'lrelu': 2}[spec.name],
                    slope=alpha, gain=gain, clamp=clamp)
         y, wk = _tc2_forward('s1', x, w, epi)
-        ctx.save_for_backward(x, w, wk, b, y, nc, noise_strength)
+        ctx.save_for_backward(x, w, wk, b, y, nc, noise_strength, wT)
         ctx.cfg = cfg
         return y
 
     @staticmethod
     def backward(ctx, dy):
         from ..torch_utils.ops import bias_act as BA
-        x, w, wk, b, y, nc, strength = ctx.saved_tensors
+        x, w, wk, b, y, nc, strength, wT = ctx.saved_tensors
         dy = _cl(dy)
         if dy.stride() != y.stride():            # size-1 dimensions: "channels-last contiguous" does not pin their strides
             dy = torch.empty_like(y).copy_(dy)
@@ -328,10 +329,10 @@ class _ConvBiasActNoise(torch.autograd.Function):
                     pix = dpre.sum([0, 1])
                     dn = pix * strength if need_n else None
                     ds = (pix * nc).sum() if need_s else None
-        gx = _tc2_input_grad('s1', dpre, wk, frozen=not ctx.needs_input_grad[1]) if ctx.needs_input_grad[0] else None
+        gx = _tc2_input_grad('s1', dpre, wk, frozen=not ctx.needs_input_grad[1], wT=wT) if ctx.needs_input_grad[0] else None
         k = w.shape[-1]
         gw = _weight_grad('s1', dpre, x, w, 1, k // 2, False) if ctx.needs_input_grad[1] else None
-        return gx, gw, db, dn, ds, None
+        return gx, gw, db, dn, ds, None, None
 
 
 def conv_bias_act_fusable(x, w5, act):
@@ -342,9 +343,9 @@ def conv_bias_act_fusable(x, w5, act):
             and x.shape[0] * x.shape[2] * x.shape[3] * ((w5.shape[1] + 127) // 128) >= 128 * 256)
 
 
-def conv2d_bias_act(x, w5, b=None, noise_const=None, noise_strength=None, act='lrelu', alpha=None, gain=None, clamp=None):
+def conv2d_bias_act(x, w5, b=None, noise_const=None, noise_strength=None, act='lrelu', alpha=None, gain=None, clamp=None, wT=None):
     """`bias_act(conv(x, w5[g]) + noise_const * noise_strength, b, act, gain, clamp)` for a stride-1 'same' convolution; one kernel when
-    `conv_bias_act_fusable`, the separate ops otherwise."""
+    `conv_bias_act_fusable`, the separate ops otherwise.  `wT`: the tap-reversed transposed weights, when the caller has them."""
     from ..torch_utils.ops import bias_act as BA
     _check(x)
     k = w5.shape[-1]
@@ -353,8 +354,8 @@ def conv2d_bias_act(x, w5, b=None, noise_const=None, noise_strength=None, act='l
         spec.name = act
         cfg = (1, spec, float(alpha if alpha is not None else spec.def_alpha), float(gain if gain is not None else spec.def_gain),
                float(clamp if clamp is not None else -1))
-        return _ConvBiasActNoise.apply(x, w5, b, noise_const, noise_strength, cfg)
-    y = _PerSampleConv.apply(x, w5, 1, k // 2, False)
+        return _ConvBiasActNoise.apply(x, w5, b, noise_const, noise_strength, cfg, wT)
+    y = _PerSampleConv.apply(x, w5, 1, k // 2, False, wT)
     if noise_const is not None:
         return BA.bias_act_noise(y, b, noise_const, noise_strength, act=act, alpha=alpha, gain=gain, clamp=clamp)
     return BA.bias_act(y, b, act=act, alpha=alpha, gain=gain, clamp=clamp)
@@ -393,13 +394,14 @@ def conv2d(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=Tru
     return op(x.contiguous(memory_format=CL), w.contiguous(memory_format=CL), stride=stride, padding=padding, groups=groups)
 
 
-def conv2d_per_sample(x, w, stride=1, padding=0, transpose=False, flip_weight=True):
+def conv2d_per_sample(x, w, stride=1, padding=0, transpose=False, flip_weight=True, wT=None):
     """x [N,Cin,H,W], w [N,Cout,Cin,kh,kw] (per-sample weights, any strides) -> [N,Cout,H',W'].
-    For `transpose=True` the per-sample weight is used as conv_transpose2d's [Cin,Cout,kh,kw] (= w[n].transpose(0,1))."""
+    For `transpose=True` the per-sample weight is used as conv_transpose2d's [Cin,Cout,kh,kw] (= w[n].transpose(0,1)).
+    `wT` (optional): w as memory [N][Cin][taps][Cout], taps reversed for the stride-1 form -- the data-gradient convolution's weights."""
     _check(x)
     if not flip_weight and (w.shape[-1] > 1 or w.shape[-2] > 1):
-        w = w.flip([3, 4])
-    return _PerSampleConv.apply(x, w, stride, padding, transpose)
+        w, wT = w.flip([3, 4]), None
+    return _PerSampleConv.apply(x, w, stride, padding, transpose, wT)
 
 
 # ---------------------------------------------------------------------------------------------------------------------

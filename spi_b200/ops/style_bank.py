@@ -28,6 +28,7 @@ class _StyleBank(torch.autograd.Function):
     def forward(ctx, ws, meta, *params):
         """ws [N, L, K] (last dim contiguous); meta = tuple of (in_features, ws index, weight gain, bias gain, output gain); params = W_0, b_0,
         W_1, b_1, ... (b_l may be None)."""
+        ctx.set_materialize_grads(False)            # unused styles hand back None, not zeros
         n, num_ws, k = ws.shape
         weights = [p.contiguous() for p in params[0::2]]
         biases = [None if p is None else p.contiguous() for p in params[1::2]]

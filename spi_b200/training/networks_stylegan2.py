@@ -17,7 +17,7 @@ import numpy as np
 import torch
 
 from ..ops import conv as conv_engine
-from ..ops.modulate import modulate_weights
+from ..ops.modulate import bank_usable, modulate_bank, modulate_weights
 from ..ops import style_bank
 from ..torch_utils import misc, persistence
 from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
@@ -31,31 +31,45 @@ def normalize_2nd_moment(x, dim=1, eps=1e-8):
     return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
 
 
-def _batched_resample_conv(x, w, f, up, padding, flip_weight, epilogue=None):
+def _batched_resample_conv(x, w, f, up, padding, flip_weight, epilogue=None, wT=None):
     """conv2d_resample (conv2d_resample.py:48-143) for per-sample weights w [N, O, I, kh, kw]: the two branches a
     generator layer takes (up = 1: plain conv; up = 2: stride-2 transposed conv then 4x4 FIR with gain 4).  `epilogue` (keyword
     arguments of `bias_act.blur_bias_act_noise`) folds the layer's noise / bias / activation pass into the FIR kernel."""
     o, i, kh, kw = w.shape[1:]
     if up == 1:
-        return conv_engine.conv2d_per_sample(x, w, padding=[padding, padding], flip_weight=flip_weight)
+        return conv_engine.conv2d_per_sample(x, w, padding=[padding, padding], flip_weight=flip_weight, wT=wT)
     fw, fh = upfirdn2d._get_filter_size(f)
     px0 = padding + (fw + up - 1) // 2 - (kw - 1)
     px1 = padding + (fw - up) // 2 - (kw - up)
     py0 = padding + (fh + up - 1) // 2 - (kh - 1)
     py1 = padding + (fh - up) // 2 - (kh - up)
     pxt, pyt = max(min(-px0, -px1), 0), max(min(-py0, -py1), 0)
-    y = conv_engine.conv2d_per_sample(x, w, stride=up, padding=[pyt, pxt], transpose=True, flip_weight=(not flip_weight))
+    y = conv_engine.conv2d_per_sample(x, w, stride=up, padding=[pyt, pxt], transpose=True, flip_weight=(not flip_weight), wT=wT)
     if epilogue is not None:
         return bias_act.blur_bias_act_noise(y, f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], fir_gain=up ** 2, **epilogue)
     return upfirdn2d.upfirdn2d(x=y, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2)
 
 
+def modulation_plan(weight, up, flip_weight):
+    """How the fused branch of `modulated_conv2d` lays out the per-sample weights of a layer: (memory layout, taps written reversed, which
+    transposed copy the layer's data-gradient convolution reads -- 'rev' / 'keep' on the tc2 engine, else None)."""
+    o, i, kh, kw = weight.shape
+    tc2 = conv_engine.ENGINE == 'tc2' and i % 32 == 0 and o % 32 == 0 and kh == kw
+    if up == 2:
+        # the stride-2 transposed convolution consumes [I,O,kh,kw] channels-last weights with the taps reversed when
+        # flip_weight is set (conv2d_resample.py:38-40,117): modulate_weights writes them like that directly
+        # (cuDNN's transposed convolution wants [I][kh][kw][O]; this library's engine reads [O][kh][kw][I] for every form)
+        return ('ohwi' if tc2 else 'ihwo'), bool(flip_weight) and (kh > 1 or kw > 1), ('keep' if tc2 and kh == 3 else None)
+    return 'ohwi', (not flip_weight) and (kh > 1 or kw > 1), ('rev' if tc2 and kh in (1, 3) else None)
+
+
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True, blur_epilogue=None, conv_epilogue=None):
+                     flip_weight=True, fused_modconv=True, blur_epilogue=None, conv_epilogue=None, modw=None):
     """networks_stylegan2.py:34-91.  x [N,I,H,W], weight [O,I,kh,kw], styles [N,I].  `blur_epilogue` (up = 2, fused branch only):
     the caller's noise / bias / activation pass, applied inside the FIR kernel that ends the up-sampling convolution.  `conv_epilogue`
     (up = 1, fused branch only; keyword arguments of `conv_engine.conv2d_bias_act`): the same pass applied inside the convolution's
-    accumulator read-out."""
+    accumulator read-out.  `modw` (fused branch only): the layer's per-sample weights and their transposed copy, already built by the
+    network's modulation bank (`modulate_bank`, one launch for all layers) according to `modulation_plan`."""
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
     misc.assert_shape(weight, [out_channels, in_channels, kh, kw])
@@ -65,23 +79,18 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
         # one launch: w[n,o,i,k] = W*s (*rsqrt(sum (W s)^2 + 1e-8))  (spi_modulate_weights)
         assert down == 1
         kh, kw = weight.shape[2:]
+        layout, pre, _ = modulation_plan(weight, up, flip_weight)
+        w, wT = modw if modw is not None else (modulate_weights(weight, styles, demodulate, layout=layout, flip=pre), None)
         if up == 2:
-            # the stride-2 transposed convolution consumes [I,O,kh,kw] channels-last weights with the taps reversed when
-            # flip_weight is set (conv2d_resample.py:38-40,117): modulate_weights writes them like that directly
-            pre = bool(flip_weight) and (kh > 1 or kw > 1)
-            # cuDNN's transposed convolution wants [I][kh][kw][O]; this library's engine reads [O][kh][kw][I] for every form
-            up_layout = 'ohwi' if (conv_engine.ENGINE == 'tc2' and in_channels % 32 == 0 and out_channels % 32 == 0) else 'ihwo'
-            w = modulate_weights(weight, styles, demodulate, layout=up_layout, flip=pre)
-            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight and not pre, epilogue=blur_epilogue)
+            x = _batched_resample_conv(x, w, resample_filter, up, padding, flip_weight and not pre, epilogue=blur_epilogue, wT=wT)
             if blur_epilogue is not None:
                 assert noise is None
                 return x
         else:
-            w = modulate_weights(weight, styles, demodulate, layout='ohwi', flip=not flip_weight and (kh > 1 or kw > 1))
             if conv_epilogue is not None:
                 assert noise is None
-                return conv_engine.conv2d_bias_act(x, w, **conv_epilogue)
-            x = _batched_resample_conv(x, w, resample_filter, up, padding, True)
+                return conv_engine.conv2d_bias_act(x, w, wT=wT, **conv_epilogue)
+            x = _batched_resample_conv(x, w, resample_filter, up, padding, True, wT=wT)
         if noise is not None:
             x = x + noise
         return x
@@ -203,7 +212,11 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, styles=None):
+    def modulation_entry(self, styles):
+        """This layer's entry for `modulate_bank`, matching what forward() asks of modulated_conv2d."""
+        return (self.weight, styles, True) + modulation_plan(self.weight, self.up, self.up == 1)
+
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, styles=None, modw=None):
         assert noise_mode in ['random', 'const', 'none']
         in_resolution = self.resolution // self.up
         misc.assert_shape(x, [None, self.in_channels, in_resolution, in_resolution])
@@ -225,16 +238,17 @@ class SynthesisLayer(torch.nn.Module):
             if fuse_noise:
                 epi.update(noise_const=self.noise_const, noise_strength=self.noise_strength)
             return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=None, up=self.up, padding=self.padding,
-                                    resample_filter=self.resample_filter, flip_weight=False, fused_modconv=True, blur_epilogue=epi)
+                                    resample_filter=self.resample_filter, flip_weight=False, fused_modconv=True, blur_epilogue=epi, modw=modw)
         if self.up == 1 and fused_modconv and noise is None and x.dtype == torch.float32 and self.padding == self.weight.shape[-1] // 2:
             # non-resampling layer: conv -> (constant noise) + bias + lrelu*gain + clamp in the convolution's own epilogue
             epi = dict(b=self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
             if fuse_noise:
                 epi.update(noise_const=self.noise_const, noise_strength=self.noise_strength)
             return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=None, up=1, padding=self.padding,
-                                    resample_filter=self.resample_filter, flip_weight=True, fused_modconv=True, conv_epilogue=epi)
+                                    resample_filter=self.resample_filter, flip_weight=True, fused_modconv=True, conv_epilogue=epi, modw=modw)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
+                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
+                             modw=modw if fused_modconv else None)
         if fuse_noise:      # + noise_const*noise_strength + bias -> lrelu*gain -> clamp in one pass
             return bias_act.bias_act_noise(x, self.bias.to(x.dtype), self.noise_const, self.noise_strength, act=self.activation,
                                            gain=act_gain, clamp=act_clamp)
@@ -255,14 +269,17 @@ class ToRGBLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
-    def forward(self, x, w, fused_modconv=True, styles=None):
+    def modulation_entry(self, styles):
+        return (self.weight, styles, False) + modulation_plan(self.weight, 1, True)
+
+    def forward(self, x, w, fused_modconv=True, styles=None, modw=None):
         if styles is None:       # (`styles`: affine output times weight_gain, from the network's style bank)
             if w.shape[0] > 1 and w.stride(0) == 0 and fused_modconv:
                 w = w[:1]
             styles = self.affine(w) * self.weight_gain
         if fused_modconv and x.dtype == torch.float32:
             epi = dict(b=self.bias.to(x.dtype), act='linear', clamp=self.conv_clamp)
-            return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=True, conv_epilogue=epi)
+            return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=True, conv_epilogue=epi, modw=modw)
         x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
         return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
 
@@ -277,6 +294,25 @@ def _fused(block, fused_modconv):
     if fused_modconv == 'inference_only':
         fused_modconv = not block.training
     return bool(fused_modconv)
+
+
+def plan_blocks(blocks, styles):
+    """Per block: (its slice of the precomputed `styles`, its layers' per-sample weights from ONE grouped modulation launch), or (None, None)
+    per block when the styles were not precomputed."""
+    if styles is None:
+        return [(None, None)] * len(blocks)
+    per_block, first = [], 0
+    for block in blocks:
+        count = block.num_conv + block.num_torgb
+        per_block.append(styles[first:first + count])
+        first += count
+    entries = [e for block, s in zip(blocks, per_block) for e in block.modulation_entries(s)]
+    modws = modulate_bank(entries) if bank_usable(entries) else None
+    plan, first = [], 0
+    for s in per_block:
+        plan.append((s, modws[first:first + len(s)] if modws is not None else None))
+        first += len(s)
+    return plan
 
 
 class _SynthesisBlockBase(torch.nn.Module):
@@ -319,10 +355,18 @@ class _SynthesisBlockBase(torch.nn.Module):
             entries.append((self.torgb.affine, first_ws + len(layers), self.torgb.weight_gain))
         return entries
 
-    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, styles=None, **layer_kwargs):
+    def modulation_entries(self, styles):
+        """`modulate_bank` entries of this block's layers for their (precomputed) styles, in the order of `style_entries`."""
+        layers = ([self.conv0] if self.in_channels != 0 else []) + [self.conv1]
+        if self.is_last or self.architecture == 'skip':
+            layers.append(self.torgb)
+        return [layer.modulation_entry(s) for layer, s in zip(layers, styles)]
+
+    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, update_emas=False, styles=None, modws=None, **layer_kwargs):
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
         w_iter = iter(ws.unbind(dim=1))
         s_iter = iter(styles) if styles is not None else iter(lambda: None, 0)     # precomputed styles, same order as w_iter
+        m_iter = iter(modws) if modws is not None else iter(lambda: None, 0)       # precomputed per-sample weights, likewise
         # Precision policy of this build: fp32 storage, TF32 tensor-core contraction (DESIGN.md); `use_fp16` only
         # selects the clamp, which the reference also applies in its fp32 fallback (networks_stylegan2.py:421-423).
         if fused_modconv is None:
@@ -336,15 +380,15 @@ class _SynthesisBlockBase(torch.nn.Module):
             misc.assert_shape(x, [None, self.in_channels, in_res, in_res])
             x = x.to(torch.float32)
         if self.in_channels == 0:
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), modw=next(m_iter), **layer_kwargs)
         else:
-            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), **layer_kwargs)
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), modw=next(m_iter), **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), modw=next(m_iter), **layer_kwargs)
         if img is not None and self.block_up == 2:
             misc.assert_shape(img, [None, self.img_channels, self.resolution // 2, self.resolution // 2])
             img = upfirdn2d.upsample2d(img, self.resample_filter)
         if self.is_last or self.architecture == 'skip':
-            y = self.torgb(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter)).to(torch.float32)
+            y = self.torgb(x, next(w_iter), fused_modconv=fused_modconv, styles=next(s_iter), modw=next(m_iter)).to(torch.float32)
             img = img.add_(y) if img is not None else y
         return x, img
 
@@ -389,12 +433,11 @@ class SynthesisNetwork(torch.nn.Module):
             for block in blocks:
                 entries += block.style_entries(w_idx)
                 w_idx += block.num_conv
-            styles = iter(style_bank.style_bank(ws, entries))
+            styles = style_bank.style_bank(ws, entries)
+        plan = plan_blocks(blocks, styles)
         w_idx = 0
-        for block in blocks:
-            count = block.num_conv + block.num_torgb
-            block_styles = [next(styles) for _ in range(count)] if styles is not None else None
-            x, img = block(x, img, ws.narrow(1, w_idx, count), styles=block_styles, **block_kwargs)
+        for block, (block_styles, block_modws) in zip(blocks, plan):
+            x, img = block(x, img, ws.narrow(1, w_idx, block.num_conv + block.num_torgb), styles=block_styles, modws=block_modws, **block_kwargs)
             w_idx += block.num_conv
         return img
 

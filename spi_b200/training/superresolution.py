@@ -5,7 +5,7 @@ import torch
 
 from ..torch_utils import persistence
 from ..ops import style_bank
-from .networks_stylegan2 import SynthesisBlock, _SynthesisBlockBase, _fused
+from .networks_stylegan2 import SynthesisBlock, _SynthesisBlockBase, _fused, plan_blocks
 
 
 @persistence.persistent_class
@@ -34,11 +34,12 @@ class SuperresolutionHybrid8XDC(torch.nn.Module):
             size = (self.input_resolution, self.input_resolution)
             x = torch.nn.functional.interpolate(x, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)
             rgb = torch.nn.functional.interpolate(rgb, size=size, mode='bilinear', align_corners=False, antialias=self.sr_antialias)
-        styles0 = styles1 = None
+        styles = None
         if style_bank.usable(ws) and all(_fused(b, block_kwargs.get('fused_modconv')) for b in (self.block0, self.block1)):
-            # the six affine layers of the two blocks in one launch; both blocks read the same three (identical) latents
+            # the six affine layers of the two blocks in one launch (both blocks read the same three identical latents), then their six
+            # weight modulations in one more
             styles = style_bank.style_bank(ws, self.block0.style_entries(0) + self.block1.style_entries(0))
-            styles0, styles1 = styles[:3], styles[3:]
-        x, rgb = self.block0(x, rgb, ws, styles=styles0, **block_kwargs)
-        x, rgb = self.block1(x, rgb, ws, styles=styles1, **block_kwargs)
+        (styles0, modws0), (styles1, modws1) = plan_blocks([self.block0, self.block1], styles)
+        x, rgb = self.block0(x, rgb, ws, styles=styles0, modws=modws0, **block_kwargs)
+        x, rgb = self.block1(x, rgb, ws, styles=styles1, modws=modws1, **block_kwargs)
         return rgb

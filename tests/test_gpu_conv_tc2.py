@@ -244,9 +244,10 @@ def test_zero_arena_outputs_equal_self_zeroed_outputs(lib):
     with Z.iteration('test', torch.device('cuda')):
         third = work(scale=2)              # asks for more than the arena holds: the tail of the requests falls back
     assert lib.spi_tc_error() == 0
-    for a, b, c in zip(plain, first, second):
-        assert rel_l2(b, a) < 1e-6 and rel_l2(c, a) < 1e-6
+    # (reduce-adds and atomics arrive in a different order from run to run: fp32 rounding of sums of ~1e3 terms, not bit equality)
+    for j, (a, b, c) in enumerate(zip(plain, first, second)):
+        assert rel_l2(b, a) < 1e-5 and rel_l2(c, a) < 1e-5, (j, rel_l2(b, a), rel_l2(c, a))
     ref3 = work(scale=2)
-    for a, b in zip(ref3, third):
-        assert rel_l2(b, a) < 1e-6
+    for j, (a, b) in enumerate(zip(ref3, third)):
+        assert rel_l2(b, a) < 1e-5, (j, rel_l2(b, a))
     Z.reset()
