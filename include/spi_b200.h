@@ -247,6 +247,11 @@ int spi_conv_tc2_splits(int form, int n, int h, int wd, int ci, int co, int k, i
  * gradient per image) else 1 (summed over the batch); dw is overwritten; partial sums are combined with fp32 reduce-adds. */
 int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
                        cudaStream_t stream);
+/* Tall-skinny reduction over `rows` rows (a multiple of 8) on the same kernel: out[m][c] = sum_r u[r][m] * v[r][c] and, when usum is not
+ * NULL, usum[m] = sum_r u[r][m].  u [rows][cu], v [rows][cv] row-major fp32, cu / cv multiples of 4 and >= 32; TF32 operands, fp32
+ * accumulation; out [cu][cv] and usum [cu] are overwritten.  Replaces the two GEMMs + column sums behind the decoder gradients of the
+ * renderer (OSGDecoder, eg3d/training/triplane.py:112-135, as autograd differentiates it). */
+int spi_rows_outer_sum(const float* u, const float* v, long long rows, int cu, int cv, float* out, float* usum, cudaStream_t stream);
 /* 1x1 convolution onto at most 4 output channels (the RGB heads of the super-resolution ToRGB layers, networks_stylegan2.py:503-518):
  * a streaming op (1.5 FLOP/byte), plain coalesced kernels (spi_b200/csrc/conv_rgb.cu).  x [n][pixels][ci] (ci a multiple of 128, <= 512),
  * y / dy [n][pixels][co], w / dw [g][co][ci], g = n when per_sample else 1.

@@ -61,6 +61,7 @@ _SIGS = {
     'spi_conv_weight_flip_transpose': [c_void_p, c_void_p] + [c_int] * 4 + [c_void_p],
     'spi_conv_tc2_supported': [c_int] * 2,
     'spi_conv_tc2_splits': [c_int] * 10,
+    'spi_rows_outer_sum': [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'spi_conv2d_tc2': [c_void_p] * 3 + [c_int] * 7 + [c_void_p] * 3 + [c_int] + [c_float] * 3 + [c_int, c_void_p],
     'spi_conv_transpose2d_s2_tc2': [c_void_p] * 3 + [c_int] * 7 + [c_void_p],
     'spi_conv2d_s2_tc2': [c_void_p] * 3 + [c_int] * 7 + [c_void_p],

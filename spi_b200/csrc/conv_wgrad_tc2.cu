@@ -51,6 +51,8 @@ struct WgradArgs {
     int n, groups, imgs_per_group, tiles_x, tiles_y, tiles_per_group, tiles_per_item, splits;
     int mblocks, cchunks, uchunks_total;      // 128-blocks of U channels, 32-chunks of V channels, 32-chunks of U channels
     int px, patch_bytes, nps, patch_stride;
+    float* usum;                      // optional: column sums of U over all pixels ([groups][U channels], accumulated with atomics)
+    int cu;
     int* err;
 };
 
@@ -91,8 +93,11 @@ __global__ void __launch_bounds__(NTW, 1) conv_wgrad_tc2_kernel(const __grid_con
     const int t1 = min(a.tiles_per_group, t0 + a.tiles_per_item);
     const int uchunks = min(4, a.uchunks_total - mb * 4);          // valid 32-channel chunks of this 128-block
 
+    // column sums of U (the bias gradient that goes with a tall-skinny weight gradient): the epilogue warps, idle during the main loop, read
+    // every U tile out of shared memory; one CTA per (group, M block) does it (cc == 0), and its U stages wait for that reader as well
+    const bool do_sum = a.usum != nullptr && cc == 0;
     if (tid == 0) {
-        for (int s = 0; s < UST; s++) { mbar_init(&full_u[s], 1); mbar_init(&empty_u[s], 1); }
+        for (int s = 0; s < UST; s++) { mbar_init(&full_u[s], 1); mbar_init(&empty_u[s], do_sum ? 2 : 1); }
         for (int s = 0; s < MAXPS; s++) { mbar_init(&full_p[s], 1); mbar_init(&empty_p[s], 1); }
         mbar_init(done, 1);
         fence_mbar_init();
@@ -178,6 +183,26 @@ __global__ void __launch_bounds__(NTW, 1) conv_wgrad_tc2_kernel(const __grid_con
         const int q = warp & 3;
         const int row = q * 32 + lane;                 // channel of U inside the 128-block = TMEM lane
         const bool leader = (warp == 4 && lane == 0);
+        if (do_sum) {
+            // thread `row` owns channel `row` of the 128-block: its values sit at one 4-byte column of the 128 rows of box `row / 32`
+            // (SWIZZLE_128B_ATOM_32B: 32-byte chunk index XOR-ed with the row) -- a warp reads 128 contiguous bytes per row, conflict-free
+            const int c = row & 31;
+            const bool have = (row >> 5) < uchunks;
+            float acc = 0.f;
+            int us = 0; uint32_t uph = 0;
+            for (int t = t0; t < t1; t++) {
+                if (!mbar_wait_bounded(&full_u[us], uph)) { atomicExch(a.err, 26); break; }
+                if (have) {
+                    const uint8_t* reg = sm + SMW_U + us * U_BYTES + (row >> 5) * 16384 + (c & 7) * 4;
+#pragma unroll 8
+                    for (int r = 0; r < 128; r++) acc += *reinterpret_cast<const float*>(reg + r * 128 + ((((c >> 3) ^ r) & 3) << 5));
+                }
+                named_bar_sync(2, 128);
+                if (leader) mbar_arrive(&empty_u[us]);
+                if (++us == UST) { us = 0; uph ^= 1; }
+            }
+            if (have && mb * 128 + row < a.cu) atomicAdd(a.usum + (size_t)g * a.cu + mb * 128 + row, acc);
+        }
         if (t1 > t0) {
             if (!mbar_wait_bounded(done, 0)) { atomicExch(a.err, 25); }
             fence_after();
@@ -248,12 +273,17 @@ bool map_img(CUtensorMap* m, const float* ptr, int c, long long wv, long long hv
 //                           dw is written TRANSPOSED as [G][Ci][9][Co]  (U = x, V = the four parity views of dy).
 // G = N when per_sample (one gradient per image), else 1 (summed over the batch).  dw is overwritten; mode + 4: dw is already zero on entry
 // (a slice of the caller's zero arena -- the partial sums meet in dw through reduce-adds), the fill is skipped.
-extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
-                                  cudaStream_t stream) {
+static int wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
+                      float* usum, cudaStream_t stream) {
     const bool prezeroed = (mode & 4) != 0;
     mode &= 3;
     SPI_CHECK_ARG(x && dy && dw, "spi_conv_wgrad_tc2: null tensor");
-    SPI_CHECK_ARG(ci % 32 == 0 && co % 32 == 0 && ci >= 32 && co >= 32, "spi_conv_wgrad_tc2: channel counts must be multiples of 32 (ci=%d co=%d)", ci, co);
+    // (k = 1, mode 0: ci may be any multiple of 4 >= 32 -- the last 32-channel chunk of x is zero-filled and its dw columns clipped by TMA;
+    //  that is the tall-skinny reduction dw[co][ci] = sum_rows dy[row][co] * x[row][ci] of the renderer's decoder gradients)
+    const bool ragged_ok = (k == 1 && mode == 0);
+    SPI_CHECK_ARG(ci >= 32 && co >= 32 && (ci % 32 == 0 || (ci % 4 == 0 && ragged_ok)) && (co % 32 == 0 || (co % 4 == 0 && ragged_ok)),
+                  "spi_conv_wgrad_tc2: channel counts must be multiples of 32 (ci=%d co=%d)", ci, co);
+    SPI_CHECK_ARG(!usum || mode == 0, "spi_conv_wgrad_tc2: column sums are taken of dy (mode 0 only)");
     SPI_CHECK_ARG((mode == 0 && (k == 1 || k == 3)) || (mode == 1 && k == 3), "spi_conv_wgrad_tc2: unsupported mode %d / k %d", mode, k);
     SPI_CHECK_ARG((((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dw) & 15) == 0, "spi_conv_wgrad_tc2: tensors must be 16-byte aligned");
     WgradArgs a;
@@ -267,7 +297,8 @@ extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, in
     a.n = n; a.groups = groups; a.imgs_per_group = n / groups;
     a.tiles_x = cdiv(wd, 8); a.tiles_y = cdiv(h, 16);
     a.tiles_per_group = a.tiles_x * a.tiles_y * a.imgs_per_group;
-    a.mblocks = cdiv(cu, 128); a.cchunks = cv / 32; a.uchunks_total = cu / 32;
+    a.mblocks = cdiv(cu, 128); a.cchunks = cdiv(cv, 32); a.uchunks_total = cdiv(cu, 32);
+    a.usum = usum; a.cu = cu;
     bool ok = map_img(&a.umap, U, cu, wd, h, n, (long long)cu * 4, (long long)wd * cu * 4, (long long)h * wd * cu * 4, 8, 16);
     {
         cuuint64_t dims[4] = {(cuuint64_t)cv, (cuuint64_t)taps, (cuuint64_t)cu, (cuuint64_t)groups};
@@ -331,8 +362,23 @@ extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, in
         configured = true;
     }
     if (!prezeroed) cudaMemsetAsync(dw, 0, (size_t)groups * cu * taps * cv * 4, stream);
+    if (usum) cudaMemsetAsync(usum, 0, (size_t)groups * cu * 4, stream);
     conv_wgrad_tc2_kernel<<<columns * a.splits, NTW, SMW_TOTAL, stream>>>(a);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("spi_conv_wgrad_tc2");
     return SPI_OK;
+}
+
+extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
+                                  cudaStream_t stream) {
+    return wgrad_impl(x, dy, dw, n, h, wd, ci, co, k, per_sample, mode, nullptr, stream);
+}
+
+// Tall-skinny reduction over `rows` rows (a multiple of 8): out[m][c] = sum_r u[r][m] * v[r][c] and, when usum is given, usum[m] = sum_r u[r][m].
+// u [rows][cu], v [rows][cv] row-major, cu / cv multiples of 4 and >= 32; TF32 operands, fp32 accumulation; out [cu][cv] and usum [cu] are
+// overwritten.  This is the 1x1 weight gradient above with the rows as pixels: every byte of u and v is read once per 32-column chunk of v.
+// Used for the decoder gradients of the renderer (dW = d_pre^T f, db = sum d_pre; OSGDecoder, eg3d/training/triplane.py:112-135).
+extern "C" int spi_rows_outer_sum(const float* u, const float* v, long long rows, int cu, int cv, float* out, float* usum, cudaStream_t stream) {
+    SPI_CHECK_ARG(rows >= 8 && rows % 8 == 0 && rows / 8 <= 2147483647LL, "spi_rows_outer_sum: rows must be a positive multiple of 8");
+    return wgrad_impl(v, u, out, 1, (int)(rows / 8), 8, cv, cu, 1, 0, 0, usum, stream);
 }

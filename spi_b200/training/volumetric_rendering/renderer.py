@@ -45,29 +45,30 @@ def _decoder_grads(sc, n_rows, lr_mul):
     f, hid, dpre, dout = sc
     g1 = lr_mul / (32 ** 0.5)
     g2 = lr_mul / (64 ** 0.5)
-    # K = millions of samples: TF32 tensor-core GEMMs (rounding errors average out over K); bias grads ride along as a
-    # ones-column would, here as plain column sums
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        # K = n_rows is in the millions while the outputs are 64x32 / 36x64: split K into independent batched products (many
-        # CTAs) and add the partial results, instead of one tall-skinny GEMM that leaves most SMs idle (measured 1.40 -> 1.27
-        # ms/img for the whole backward; a hand-written mma.sync reduction kernel was slower than this and was dropped)
-        chunks = 1
-        for c in (512, 256, 128, 64, 32, 16, 8, 4, 2):
-            if n_rows % c == 0 and n_rows // c >= 1024:
-                chunks = c
-                break
-        k = n_rows // chunks
-        dw1 = torch.bmm(dpre[:n_rows].view(chunks, k, -1).transpose(1, 2), f[:n_rows].view(chunks, k, -1)).sum(0) * g1
-        dw2 = torch.bmm(dout[:n_rows].view(chunks, k, -1).transpose(1, 2), hid[:n_rows].view(chunks, k, -1)).sum(0)[:33] * g2
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
-    # column sums of the tall scratch matrices at HBM speed (`spi_column_sums`; ATen's strided column reduction ran at 1.3 TB/s)
+    # K = millions of samples, outputs 64x32 / 36x64: the convolution weight-gradient kernel with a 1x1 "tap" is exactly this reduction
+    # (out[m][c] = sum_rows u[row][m] v[row][c]: TF32 operands through TMA, fp32 accumulation in tensor memory, the row range split over the
+    # SMs, reduce-add stores), and its idle epilogue warps add up the columns of u on the way: weight and bias gradients of a layer come
+    # out of ONE pass that reads every scratch byte once (spi_rows_outer_sum; before: two batched GEMMs over 512 row chunks, two sums over
+    # the chunks and two column-sum passes that re-read d_pre / d_out)
     lib = _lib.load()
-    s1, s2 = torch.empty(64, device=f.device), torch.empty(36, device=f.device)
-    _lib.check(lib.spi_column_sums(_lib.ptr(dpre), n_rows, 64, _lib.ptr(s1), _lib.stream()))
-    _lib.check(lib.spi_column_sums(_lib.ptr(dout), n_rows, 36, _lib.ptr(s2), _lib.stream()))
+    dev = f.device
+    dw1, s1 = torch.empty(64, 32, device=dev), torch.empty(64, device=dev)
+    dw2, s2 = torch.empty(36, 64, device=dev), torch.empty(36, device=dev)
+    if n_rows % 8 == 0 and n_rows >= 8:
+        _lib.check(lib.spi_rows_outer_sum(_lib.ptr(dpre), _lib.ptr(f), n_rows, 64, 32, _lib.ptr(dw1), _lib.ptr(s1), _lib.stream()))
+        _lib.check(lib.spi_rows_outer_sum(_lib.ptr(dout), _lib.ptr(hid), n_rows, 36, 64, _lib.ptr(dw2), _lib.ptr(s2), _lib.stream()))
+    else:           # ragged row counts (stand-alone point queries): library GEMMs + the streaming column sums
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            dw1 = dpre[:n_rows].t() @ f[:n_rows]
+            dw2 = dout[:n_rows].t() @ hid[:n_rows]
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        _lib.check(lib.spi_column_sums(_lib.ptr(dpre), n_rows, 64, _lib.ptr(s1), _lib.stream()))
+        _lib.check(lib.spi_column_sums(_lib.ptr(dout), n_rows, 36, _lib.ptr(s2), _lib.stream()))
+    dw1 = dw1 * g1
+    dw2 = dw2[:33] * g2
     db1 = s1 * lr_mul
     db2 = s2[:33] * lr_mul
     return dw1, db1, dw2, db2

@@ -251,3 +251,26 @@ def test_zero_arena_outputs_equal_self_zeroed_outputs(lib):
     for j, (a, b) in enumerate(zip(ref3, third)):
         assert rel_l2(b, a) < 1e-5, (j, rel_l2(b, a))
     Z.reset()
+
+
+@pytest.mark.parametrize('rows,cu,cv', [(1 << 16, 64, 32), (1 << 16, 36, 64), (8 * 1237, 64, 32), (4096 * 64 * 4, 36, 64), (1 << 14, 128, 96)])
+def test_rows_outer_sum(lib, rows, cu, cv):
+    """spi_rows_outer_sum (the decoder-gradient reduction of the renderer: out = u^T v over millions of rows, column sums of u from the same
+    pass) against fp64; ragged channel counts (36) and a row count that is not a multiple of the 128-row tile included."""
+    from spi_b200 import _lib
+    gen = torch.Generator().manual_seed(rows % 1000 + cu)
+    u = torch.randn(rows, cu, generator=gen).cuda()
+    v = (torch.randn(rows, cv, generator=gen) + 0.3).cuda()
+    u[:, 0] += 0.5                                         # a column with a non-zero mean: its sum does not cancel
+    out = torch.full((cu, cv), float('nan'), device='cuda')
+    usum = torch.full((cu,), float('nan'), device='cuda')
+    _lib.check(lib.spi_rows_outer_sum(_lib.ptr(u), _lib.ptr(v), rows, cu, cv, _lib.ptr(out), _lib.ptr(usum), _lib.stream()))
+    torch.cuda.synchronize()
+    assert lib.spi_tc_error() == 0
+    ref = u.double().t() @ v.double()
+    assert rel_l2(out, ref) < TOL
+    rs = u.double().sum(0)
+    assert (usum.double() - rs).abs().max().item() < 1e-3 * u.double().abs().sum(0).max().item()
+    out2 = torch.empty_like(out)
+    _lib.check(lib.spi_rows_outer_sum(_lib.ptr(u), _lib.ptr(v), rows, cu, cv, _lib.ptr(out2), None, _lib.stream()))
+    assert rel_l2(out2, out) < 1e-5
