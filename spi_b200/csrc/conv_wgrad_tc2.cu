@@ -39,8 +39,8 @@ constexpr int SMW_TOTAL = SMW_BAR + 1024 + 1024;
 constexpr int MAXWV = 4, MAXWM = 3, MAXWO = 9, MAXPS = 5;
 
 struct WMma { int dy, dx, n, dcol; };                     // patch row / pixel shift, N (32 x taps in the instruction), accumulator column
-struct WView { int vmap, oy, ox, nmma; WMma mma[MAXWM]; };
-struct WOut { int dcol, tap; };
+struct WView { int vmap, oy, ox, nmma; WMma mma[MAXWM]; int coff; };       // coff: channel offset of this view inside V (folded 32-channel chunks)
+struct WOut { int dcol, tap, coff; };
 struct WgradArgs {
     CUtensorMap umap;                 // U: {channels, W, H, N}, box {32, 8, 16, 1}
     CUtensorMap vmap[MAXWV];          // V views: box {32, px, rows, 1}
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NTW, 1) conv_wgrad_tc2_kernel(const __grid_con
                 for (int v = 0; v < a.nviews; v++) {
                     if (!mbar_wait_bounded(&empty_p[s], ph ^ 1)) { atomicExch(a.err, 22); return; }
                     mbar_expect_tx(&full_p[s], (uint32_t)a.patch_bytes);
-                    tma_load_4d(sm + SMW_P + s * a.patch_stride, &a.vmap[a.views[v].vmap], cc * 32, x0 + a.views[v].ox, y0 + a.views[v].oy, img, &full_p[s]);
+                    tma_load_4d(sm + SMW_P + s * a.patch_stride, &a.vmap[a.views[v].vmap], cc * 32 + a.views[v].coff, x0 + a.views[v].ox, y0 + a.views[v].oy, img, &full_p[s]);
                     if (++s == a.nps) { s = 0; ph ^= 1; }
                 }
             }
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NTW, 1) conv_wgrad_tc2_kernel(const __grid_con
                 fence_async_smem();
                 named_bar_sync(1, 128);
                 if (leader) {
-                    tma_reduce_add_4d_w(&a.omap, stg, cc * 32, a.outs[k].tap, mb * 128, g);
+                    tma_reduce_add_4d_w(&a.omap, stg, cc * 32 + a.outs[k].coff, a.outs[k].tap, mb * 128, g);
                     tma_commit_group();
                 }
             }
@@ -274,7 +274,7 @@ bool map_img(CUtensorMap* m, const float* ptr, int c, long long wv, long long hv
 // G = N when per_sample (one gradient per image), else 1 (summed over the batch).  dw is overwritten; mode + 4: dw is already zero on entry
 // (a slice of the caller's zero arena -- the partial sums meet in dw through reduce-adds), the fill is skipped.
 static int wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
-                      float* usum, cudaStream_t stream) {
+                      float* usum, bool fold_v, cudaStream_t stream) {
     const bool prezeroed = (mode & 4) != 0;
     mode &= 3;
     SPI_CHECK_ARG(x && dy && dw, "spi_conv_wgrad_tc2: null tensor");
@@ -306,7 +306,22 @@ static int wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, 
         cuuint32_t box[4] = {32, 1, 128, 1};
         ok = ok && map4(&a.omap, dw, dims, str, box, 0);
     }
-    if (mode == 0) {
+    if (mode == 0 && fold_v) {
+        // tall-skinny form (k = 1): ONE CTA column takes all 32-channel chunks of V (a view per chunk, 32 accumulator columns each), so U is
+        // read once however wide V is
+        SPI_CHECK_ARG(k == 1 && cv <= 32 * MAXWV, "spi_conv_wgrad_tc2: folded form needs k = 1 and at most %d V channels", 32 * MAXWV);
+        a.px = 8;
+        a.patch_bytes = 16 * a.px * 128;
+        ok = ok && map_img(&a.vmap[0], V, cv, wd, h, n, (long long)cv * 4, (long long)wd * cv * 4, (long long)h * wd * cv * 4, a.px, 16);
+        a.nviews = a.cchunks;
+        for (int q = 0; q < a.nviews; q++) {
+            WView& v = a.views[q];
+            v.vmap = 0; v.oy = 0; v.ox = 0; v.nmma = 1; v.coff = 32 * q;
+            v.mma[0] = WMma{0, 0, 32, 32 * q};
+            a.outs[a.nouts++] = WOut{32 * q, 0, 32 * q};
+        }
+        a.cchunks = 1;
+    } else if (mode == 0) {
         const int halo = k / 2;
         a.px = 8 + 2 * halo;
         const int rows = 16 + 2 * halo;
@@ -317,7 +332,7 @@ static int wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, 
         v.vmap = 0; v.oy = -halo; v.ox = -halo; v.nmma = 0;
         for (int ky = 0; ky < k; ky++) {
             v.mma[v.nmma++] = WMma{ky, 0, 32 * k, ky * 32 * k};          // the k taps of this row in one instruction (N = 32 k)
-            for (int kx = 0; kx < k; kx++) a.outs[a.nouts++] = WOut{ky * 32 * k + kx * 32, ky * k + kx};
+            for (int kx = 0; kx < k; kx++) a.outs[a.nouts++] = WOut{ky * 32 * k + kx * 32, ky * k + kx, 0};
         }
     } else {
         const int hi = 2 * h + 1, wi = 2 * wd + 1;
@@ -334,7 +349,7 @@ static int wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, 
             const int nkx = px ? 1 : 2;                   // taps of this parity in x: kx = px, px + 2
             for (int ky = py; ky < 3; ky += 2) {
                 v.mma[v.nmma++] = WMma{ky >> 1, 0, 32 * nkx, dcol};
-                for (int j = 0; j < nkx; j++) a.outs[a.nouts++] = WOut{dcol + 32 * j, ky * 3 + px + 2 * j};
+                for (int j = 0; j < nkx; j++) a.outs[a.nouts++] = WOut{dcol + 32 * j, ky * 3 + px + 2 * j, 0};
                 dcol += 32 * nkx;
             }
         }
@@ -371,14 +386,14 @@ static int wgrad_impl(const float* x, const float* dy, float* dw, int n, int h, 
 
 extern "C" int spi_conv_wgrad_tc2(const float* x, const float* dy, float* dw, int n, int h, int wd, int ci, int co, int k, int per_sample, int mode,
                                   cudaStream_t stream) {
-    return wgrad_impl(x, dy, dw, n, h, wd, ci, co, k, per_sample, mode, nullptr, stream);
+    return wgrad_impl(x, dy, dw, n, h, wd, ci, co, k, per_sample, mode, nullptr, false, stream);
 }
 
 // Tall-skinny reduction over `rows` rows (a multiple of 8): out[m][c] = sum_r u[r][m] * v[r][c] and, when usum is given, usum[m] = sum_r u[r][m].
 // u [rows][cu], v [rows][cv] row-major, cu / cv multiples of 4 and >= 32; TF32 operands, fp32 accumulation; out [cu][cv] and usum [cu] are
-// overwritten.  This is the 1x1 weight gradient above with the rows as pixels: every byte of u and v is read once per 32-column chunk of v.
+// overwritten.  This is the 1x1 weight gradient above with the rows as pixels; for cv <= 128 one CTA column takes all of v, so u and v are read once.
 // Used for the decoder gradients of the renderer (dW = d_pre^T f, db = sum d_pre; OSGDecoder, eg3d/training/triplane.py:112-135).
 extern "C" int spi_rows_outer_sum(const float* u, const float* v, long long rows, int cu, int cv, float* out, float* usum, cudaStream_t stream) {
     SPI_CHECK_ARG(rows >= 8 && rows % 8 == 0 && rows / 8 <= 2147483647LL, "spi_rows_outer_sum: rows must be a positive multiple of 8");
-    return wgrad_impl(v, u, out, 1, (int)(rows / 8), 8, cv, cu, 1, 0, 0, usum, stream);
+    return wgrad_impl(v, u, out, 1, (int)(rows / 8), 8, cv, cu, 1, 0, 0, usum, cv <= 32 * MAXWV, stream);
 }
