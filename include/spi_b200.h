@@ -50,6 +50,12 @@ int spi_blur4_bias_act_noise(const float* x, const float* f, float* y, const flo
                              const long long* y_strides, int padx0, int padx1, int pady0, int pady1, int flip, float fir_gain,
                              int act, float alpha, float gain, float clamp, cudaStream_t stream);
 
+/* Activation gradient and its reductions in one pass (what `bias_act(grad=1)` followed by the sums of `SynthesisLayer`'s bias /
+ * noise_strength gradients computes, eg3d/torch_utils/ops/bias_act.py:150-187 + autograd's sums): dx = act'(yref) * dy, db[c] = sum over pixels
+ * of dx (NULL: not wanted), dstrength = sum dx * noise[pixel % hw] (NULL: not wanted).  act 1 linear / 2 relu / 3 lrelu; channels-last rows
+ * of c floats (c % 4 == 0, c <= 1024), 16-byte aligned.  db / dstrength are overwritten. */
+int spi_bias_act_grad_reduce(const float* dy, const float* yref, float* dx, long long numel, int c, int hw, int act, float alpha, float gain,
+                             float clamp, const float* noise, float* db, float* dstrength, cudaStream_t stream);
 /* Gradient reductions of that epilogue in one pass over dx (channels-last fp32 [pixels, C]): db[c] = sum dx (bias_act.py:166),
  * dpix[h,w] = sum_{n,c} dx (gradient of the noise term), dstrength = sum dpix*noise.  Any output may be NULL; pixels = n * hw. */
 int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,

@@ -38,6 +38,7 @@ _SIGS = {
     'spi_adam_step': [c_void_p] * 4 + [c_ll] + [c_float] * 4 + [c_int, c_void_p, c_int, c_void_p, c_float, c_void_p],
     'spi_adam_step_multi': [c_void_p, c_int, c_int] + [c_float] * 4 + [c_int, c_void_p, c_void_p, c_float, c_void_p],
     'spi_bias_act_noise': [c_void_p] * 5 + [c_ll] + [c_int] * 6 + [c_float] * 3 + [c_void_p],
+    'spi_bias_act_grad_reduce': [c_void_p] * 3 + [c_ll, c_int, c_int, c_int] + [c_float] * 3 + [c_void_p] * 3 + [c_void_p],
     'spi_epilogue_grad_reduce': [c_void_p, c_ll, c_int, c_int] + [c_void_p] * 4 + [c_void_p],
     'spi_modulate_weights': [c_void_p] * 4 + [c_int] * 6 + [c_void_p],
     'spi_modulate_weights_backward': [c_void_p] * 6 + [c_int] * 6 + [c_void_p],

@@ -209,6 +209,84 @@ __global__ void __launch_bounds__(256) bias_act_rows_kernel(BiasActParams p, uns
     }
 }
 
+// Gradient of the activation AND its reductions in one pass (grad = 1 of linear / relu / lrelu; channels-last rows of C floats):
+// dx = act'(yref) * dy is written, while every thread -- which keeps one column of 4 channels for its whole life -- adds what it wrote to
+// four private sums (the bias gradient db[c] = sum over pixels of dx) and, when a noise map is given, to sum dx * noise[pixel] (the
+// gradient of the layer's noise_strength).  Private sums meet in shared memory, then one atomic per channel and CTA.  Replaces the
+// epilogue_grad_reduce pass over dx that used to follow bias_act(grad = 1) (one read of dx saved per layer).
+template <int A>
+__global__ void __launch_bounds__(256) bias_act_grad_reduce_rows_kernel(BiasActParams p, unsigned c4, unsigned rows, float* __restrict__ db,
+                                                                        float* __restrict__ dstrength) {
+    extern __shared__ float sred[];                       // 4 * c4 channel sums + 1
+    const float* __restrict__ x = (const float*)p.x;
+    const float* __restrict__ yr = (const float*)p.yref;
+    float* __restrict__ y = (float*)p.y;
+    const unsigned T = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned col = t % c4, rstep = T / c4;
+    unsigned row = t / c4;
+    const bool nz = dstrength != nullptr;
+    const unsigned hw = (unsigned)p.hw;
+    unsigned rhw = row % hw;
+    const unsigned hstep = rstep % hw;
+    constexpr int U = 4;
+    const unsigned hstep_u = (U * hstep) % hw;
+    for (unsigned i = threadIdx.x; i < 4 * c4 + 1; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+    float4 sb = make_float4(0.f, 0.f, 0.f, 0.f);
+    float ss = 0.f;
+    while (row < rows) {
+        float4 vx[U], vy[U];
+        float nv[U];
+        unsigned rr[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            rr[u] = row + u * rstep;
+            const bool ok = rr[u] < rows;
+            const size_t off = ((size_t)rr[u] * c4 + col) * 4;
+            vx[u] = ok ? ldg_stream((const float4*)(x + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            vy[u] = ok ? ldg_stream((const float4*)(yr + off)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            nv[u] = 0.f;
+            if (nz) {
+                unsigned h = rhw + u * hstep;            // < 4*hw: at most three conditional subtractions, no division
+                if (h >= 2 * hw) h -= 2 * hw;
+                if (h >= hw) h -= hw;
+                if (h >= hw) h -= hw;
+                nv[u] = ok ? __ldg(p.noise + h) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (rr[u] < rows) {
+                float4 o;
+                o.x = act_eval<float, A>(vx[u].x, 0.f, 0.f, vy[u].x, 1.f, 1, p.alpha, p.gain, p.clamp);
+                o.y = act_eval<float, A>(vx[u].y, 0.f, 0.f, vy[u].y, 1.f, 1, p.alpha, p.gain, p.clamp);
+                o.z = act_eval<float, A>(vx[u].z, 0.f, 0.f, vy[u].z, 1.f, 1, p.alpha, p.gain, p.clamp);
+                o.w = act_eval<float, A>(vx[u].w, 0.f, 0.f, vy[u].w, 1.f, 1, p.alpha, p.gain, p.clamp);
+                stg_stream((float4*)(y + ((size_t)rr[u] * c4 + col) * 4), o);
+                sb.x += o.x; sb.y += o.y; sb.z += o.z; sb.w += o.w;
+                ss = fmaf((o.x + o.y) + (o.z + o.w), nv[u], ss);
+            }
+        }
+        row += U * rstep;
+        if (nz) {
+            unsigned h = rhw + hstep_u;
+            rhw = h >= hw ? h - hw : h;
+        }
+    }
+    if (db) {
+        atomicAdd(&sred[4 * col + 0], sb.x); atomicAdd(&sred[4 * col + 1], sb.y);
+        atomicAdd(&sred[4 * col + 2], sb.z); atomicAdd(&sred[4 * col + 3], sb.w);
+    }
+    if (nz) {
+        ss = warp_sum(ss);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sred[4 * c4], ss);
+    }
+    __syncthreads();
+    if (db)
+        for (unsigned i = threadIdx.x; i < 4 * c4; i += blockDim.x) atomicAdd(db + i, sred[i]);
+    if (nz && threadIdx.x == 0) atomicAdd(dstrength, sred[4 * c4]);
+}
+
 template <int G>
 void* pick_rows_kernel(int act) {
     switch (act) {
@@ -418,6 +496,38 @@ __global__ void __launch_bounds__(256) bias_grad_smallc_kernel(const float* __re
 }
 
 }  // namespace
+
+// dx = d act(x + b)/dx * dy from the saved output yref (grad = 1 of act 1 linear / 2 relu / 3 lrelu, with gain and clamp as spi_bias_act),
+// db[c] = sum over pixels of dx (NULL: not wanted), dstrength = sum dx * noise[pixel % hw] (NULL: not wanted; noise [hw]) -- one pass.
+// dy / yref / dx: channels-last rows of c floats (c % 4 == 0, c <= 1024), numel = pixels * c, 16-byte aligned.  db / dstrength overwritten.
+extern "C" int spi_bias_act_grad_reduce(const float* dy, const float* yref, float* dx, long long numel, int c, int hw, int act, float alpha,
+                                        float gain, float clamp, const float* noise, float* db, float* dstrength, cudaStream_t stream) {
+    SPI_CHECK_ARG(dy && yref && dx && (db || dstrength), "bias_act_grad_reduce: null pointer");
+    SPI_CHECK_ARG(act >= 1 && act <= 3, "bias_act_grad_reduce: act must be 1 (linear), 2 (relu) or 3 (lrelu)");
+    SPI_CHECK_ARG(c >= 4 && c % 4 == 0 && c <= 1024 && numel > 0 && numel % c == 0 && numel / c <= 4294967295LL, "bias_act_grad_reduce: bad shape (numel=%lld c=%d)", numel, c);
+    SPI_CHECK_ARG(!dstrength || noise, "bias_act_grad_reduce: noise map required for dstrength");
+    SPI_CHECK_ARG((((uintptr_t)dy | (uintptr_t)yref | (uintptr_t)dx) & 15) == 0, "bias_act_grad_reduce: tensors must be 16-byte aligned");
+    if (db && dstrength == db + c) cudaMemsetAsync(db, 0, sizeof(float) * (c + 1), stream);      // one fill when the caller packed them
+    else {
+        if (db) cudaMemsetAsync(db, 0, sizeof(float) * c, stream);
+        if (dstrength) cudaMemsetAsync(dstrength, 0, sizeof(float), stream);
+    }
+    BiasActParams p{dy, nullptr, nullptr, yref, nullptr, dx, 1, act, alpha, gain, clamp, numel, 1, 1, 0, noise, nullptr, hw > 0 ? hw : 1, c};
+    const unsigned c4 = (unsigned)(c / 4), rows = (unsigned)(numel / c);
+    unsigned need = c4, r256 = 256;                      // grid * 256 must be a multiple of c4
+    while (need % 2 == 0 && r256 % 2 == 0) { need /= 2; r256 /= 2; }
+    long long want = (numel / 4 + 256 * 4 - 1) / (256 * 4);
+    long long capb = (long long)spi_num_sms() * 8;
+    long long grid = want < capb ? want : capb;
+    grid = (grid + need - 1) / need * need;
+    const size_t smem = sizeof(float) * (4 * c4 + 1);
+    void* k = act == 1 ? (void*)bias_act_grad_reduce_rows_kernel<1> : (act == 2 ? (void*)bias_act_grad_reduce_rows_kernel<2> : (void*)bias_act_grad_reduce_rows_kernel<3>);
+    void* args[] = {&p, (void*)&c4, (void*)&rows, (void*)&db, (void*)&dstrength};
+    cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)grid), dim3(256), args, smem, stream);
+    SPI_COUNT_LAUNCH(1);
+    if (e != cudaSuccess) { spi_set_error("bias_act_grad_reduce: %s", cudaGetErrorString(e)); return SPI_ERR_CUDA; }
+    return SPI_OK;
+}
 
 extern "C" int spi_epilogue_grad_reduce(const float* dx, long long pixels, int c, int hw, const float* noise, float* db, float* dpix,
                                         float* dstrength, cudaStream_t stream) {

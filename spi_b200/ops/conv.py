@@ -314,21 +314,10 @@ class _ConvBiasActNoise(torch.autograd.Function):
         dy = _cl(dy)
         if dy.stride() != y.stride():            # size-1 dimensions: "channels-last contiguous" does not pin their strides
             dy = torch.empty_like(y).copy_(dy)
-        dpre = BA._BiasActGrad.apply(dy, None, b, y, ctx.cfg)
-        db = dn = ds = None
         need_b = b is not None and ctx.needs_input_grad[2]
         need_n, need_s = nc is not None and ctx.needs_input_grad[3], nc is not None and ctx.needs_input_grad[4]
-        if need_b or need_n or need_s:
-            red = BA._fused_reductions(dpre, need_b, noise=nc, want_dpix=need_n, want_ds=need_s)
-            if red is not None:
-                db, pix, ds = red
-                dn = pix * strength if need_n else None
-            else:
-                db = dpre.sum([0, 2, 3]) if need_b else None
-                if need_n or need_s:
-                    pix = dpre.sum([0, 1])
-                    dn = pix * strength if need_n else None
-                    ds = (pix * nc).sum() if need_s else None
+        dpre, db, pix, ds = BA._grad_and_reductions(dy, b, y, ctx.cfg, noise=nc, want_db=need_b, want_dpix=need_n, want_ds=need_s)
+        dn = pix * strength if need_n else None
         gx = _tc2_input_grad('s1', dpre, wk, frozen=not ctx.needs_input_grad[1], wT=wT) if ctx.needs_input_grad[0] else None
         k = w.shape[-1]
         gw = _weight_grad('s1', dpre, x, w, 1, k // 2, False) if ctx.needs_input_grad[1] else None

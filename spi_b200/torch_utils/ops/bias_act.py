@@ -57,6 +57,45 @@ def _fused_reductions(dx, want_db, noise=None, want_dpix=False, want_ds=False):
     return db, dpix, ds
 
 
+def _grad_and_reductions(dy, b, y, cfg, noise=None, want_db=False, want_dpix=False, want_ds=False):
+    """(dx, db, dpix, ds) of an activation epilogue given its saved output y: dx = bias_act(grad=1), db = sum of dx over pixels, dpix = sum of
+    dx over channels ([H,W]), ds = sum dx * noise.  One kernel (`spi_bias_act_grad_reduce`) when only db / ds are wanted -- always the case
+    while the generator is tuned: noise_const is a buffer then -- on channels-last fp32 with linear / relu / lrelu; otherwise the gradient
+    kernel followed by the reduction kernel (`_fused_reductions`) or ATen sums."""
+    dim, spec, alpha, gain, clamp = cfg
+    fast = ((want_db or want_ds) and not want_dpix and not torch.is_grad_enabled() and dim == 1 and spec.cuda_idx in (1, 2, 3) and dy.ndim == 4
+            and dy.dtype == torch.float32 and y is not None and y.dtype == torch.float32 and dy.is_contiguous(memory_format=torch.channels_last)
+            and dy.stride() == y.stride() and dy.shape == y.shape and dy.shape[1] % 4 == 0 and 4 <= dy.shape[1] <= 1024
+            and dy.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0 and dy.numel() >= 4096 and (not want_ds or noise is not None))
+    if fast:
+        n, c, h, w = dy.shape
+        dx = torch.empty_like(dy)
+        if want_db and want_ds:                      # packed so the library zero-fills both with one memset
+            buf = torch.empty(c + 1, device=dy.device)
+            db, ds = buf[:c], buf[c]
+        else:
+            db = torch.empty(c, device=dy.device) if want_db else None
+            ds = torch.empty((), device=dy.device) if want_ds else None
+        with _lib.timed('bias_act', dy.numel() * 4 * 3, detail=f'grad1+reduce act{spec.cuda_idx} {tuple(dy.shape)}'):
+            _lib.check(_lib.load().spi_bias_act_grad_reduce(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), dy.numel(), c, h * w, spec.cuda_idx, alpha, gain, clamp,
+                                                            _lib.ptr(noise) if want_ds else None, _lib.ptr(db), ds.data_ptr() if ds is not None else None,
+                                                            _lib.stream()))
+        return dx, db, None, ds
+    dx = _BiasActGrad.apply(dy, None, b, y, cfg)
+    db = dpix = ds = None
+    if want_db or want_dpix or want_ds:
+        red = _fused_reductions(dx, want_db, noise=noise, want_dpix=want_dpix, want_ds=want_ds) if dim == 1 else None
+        if red is not None:
+            db, dpix, ds = red
+        else:
+            if want_db:
+                db = dx.sum([i for i in range(dx.ndim) if i != dim])
+            if want_dpix or want_ds:
+                dpix = dx.sum([0, 1])
+                ds = (dpix * noise).sum() if want_ds else None
+    return dx, db, dpix, ds
+
+
 def _plugin_bias_act(x, b, xref, yref, dy, grad, dim, act_idx, alpha, gain, clamp):
     """The plugin entry point `bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)` (bias_act.cpp:36)."""
     if not x.is_cuda:
@@ -137,6 +176,9 @@ class _BiasAct(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             dx = dy
             if spec.cuda_idx != 1 or gain != 1 or clamp >= 0:
+                if x is None and y is not None and ctx.needs_input_grad[1] and dim == 1:
+                    dx, db, _, _ = _grad_and_reductions(dy, b, y, ctx.cfg, want_db=True)     # gradient and bias gradient in one pass
+                    return dx, db, None
                 dx = _BiasActGrad.apply(dy, x, b, y, ctx.cfg)
         if ctx.needs_input_grad[1]:
             red = _fused_reductions(dx, True) if dim == 1 else None
@@ -181,23 +223,9 @@ class _BiasActNoise(torch.autograd.Function):
         dim, spec, alpha, gain, clamp = ctx.cfg
         b, y, nc, strength = ctx.saved_tensors
         dy = dy.contiguous(memory_format=ctx.fmt)
-        dx = _BiasActGrad.apply(dy, None, b, y, ctx.cfg)
-        db = dn = ds = None
         need_b, need_n, need_s = ctx.needs_input_grad[1], ctx.needs_input_grad[2], ctx.needs_input_grad[3]
-        red = _fused_reductions(dx, need_b, noise=nc, want_dpix=need_n, want_ds=need_s) if (need_b or need_n or need_s) else None
-        if red is not None:
-            db, pix, ds = red
-            if need_n:
-                dn = pix * strength
-            return dx, db, dn, ds, None
-        if need_b:
-            db = dx.sum([0, 2, 3])
-        if need_n or need_s:
-            pix = dx.sum([0, 1])                      # [H, W]: d/d(noise term)
-            if need_n:
-                dn = pix * strength
-            if need_s:
-                ds = (pix * nc).sum()
+        dx, db, pix, ds = _grad_and_reductions(dy, b, y, ctx.cfg, noise=nc, want_db=need_b, want_dpix=need_n, want_ds=need_s)
+        dn = pix * strength if need_n else None
         return dx, db, dn, ds, None
 
 
@@ -244,21 +272,9 @@ class _BlurBiasActNoise(torch.autograd.Function):
         f, b, y, nc, strength = ctx.saved_tensors
         padx0, padx1, pady0, pady1, flip, fir_gain = ctx.fir_cfg
         dy = dy.contiguous(memory_format=torch.channels_last)
-        dpre = _BiasActGrad.apply(dy, None, b, y, ctx.cfg)
-        db = dn = ds = None
         need_b, need_n, need_s = ctx.needs_input_grad[2], nc is not None and ctx.needs_input_grad[3], nc is not None and ctx.needs_input_grad[4]
-        red = _fused_reductions(dpre, need_b, noise=nc, want_dpix=need_n, want_ds=need_s) if (need_b or need_n or need_s) else None
-        if red is not None:
-            db, pix, ds = red
-            if need_n:
-                dn = pix * strength
-        else:
-            if need_b:
-                db = dpre.sum([0, 2, 3])
-            if need_n or need_s:
-                pix = dpre.sum([0, 1])
-                dn = pix * strength if need_n else None
-                ds = (pix * nc).sum() if need_s else None
+        dpre, db, pix, ds = _grad_and_reductions(dy, b, y, ctx.cfg, noise=nc, want_db=need_b, want_dpix=need_n, want_ds=need_s)
+        dn = pix * strength if need_n else None
         dx = None
         if ctx.needs_input_grad[0]:
             _, _, ih, iw = ctx.x_shape

@@ -312,3 +312,38 @@ def test_bias_gradient_small_channel_counts_channels_last(P, shape):
     bg = b.cuda().requires_grad_(True)
     P.bias_act.bias_act(xg, bg, act='linear', clamp=1.0).backward(dy.cuda().contiguous(memory_format=torch.channels_last))
     assert rel_l2(xg.grad, xo.grad) < TOL and rel_l2(bg.grad, bo.grad) < 1e-5
+
+
+@pytest.mark.parametrize('shape,act,clamp,with_noise', [
+    ((1, 128, 64, 64), 'lrelu', 256.0, True),      # generator layer: bias + noise_strength gradients
+    ((2, 96, 33, 31), 'linear', 0.9, False),       # 24 vectors per row (not a power of two), clamp masks part of the gradient
+    ((1, 512, 8, 8), 'lrelu', None, True),         # small map, many channels
+    ((4, 64, 40, 40), 'relu', None, False),        # relu (VGG layers with a trainable bias)
+    ((1, 1024, 4, 4), 'lrelu', 1.0, True),         # widest row the kernel takes
+])
+def test_activation_gradient_and_its_reductions_in_one_pass(P, shape, act, clamp, with_noise):
+    """While the generator is tuned noise_const is a buffer: the backward pass of a layer epilogue wants dx, db and d noise_strength only, which
+    `spi_bias_act_grad_reduce` produces in ONE pass over (dy, y) -- checked against the oracle's autograd (eg3d bias_act.py:54-88 semantics)."""
+    n, c, h, w = shape
+    gen = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=gen)
+    b = torch.randn(c, generator=gen)
+    nc = torch.randn(h, w, generator=gen) if with_noise else None
+    st = torch.tensor(0.41)
+    dy = torch.randn(*shape, generator=gen)
+    xo, bo, so = x.clone().requires_grad_(True), b.clone().requires_grad_(True), st.clone().requires_grad_(True)
+    O.bias_act(xo + (nc * so if with_noise else 0), bo, act=act, gain=1.3, clamp=clamp).backward(dy)
+    xg = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    bg, sg = b.cuda().requires_grad_(True), st.cuda().requires_grad_(True)
+    from spi_b200 import _lib
+    before = _lib.launch_count()
+    if with_noise:
+        yg = P.bias_act.bias_act_noise(xg, bg, nc.cuda(), sg, act=act, gain=1.3, clamp=clamp)       # noise_const: no gradient wanted
+    else:
+        yg = P.bias_act.bias_act(xg, bg, act=act, gain=1.3, clamp=clamp)
+    fwd = _lib.launch_count() - before
+    yg.backward(dy.cuda().contiguous(memory_format=torch.channels_last))
+    assert _lib.launch_count() - before - fwd == 1         # the whole epilogue backward is one kernel of this library
+    assert rel_l2(xg.grad, xo.grad) < 1e-6 and rel_l2(bg.grad, bo.grad) < 1e-5
+    if with_noise:
+        assert abs(float(sg.grad) - float(so.grad)) < 1e-4 * float((dy * nc).abs().sum())
