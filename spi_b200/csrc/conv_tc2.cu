@@ -52,6 +52,7 @@ struct Conv2Args {
     Program prog[MAXP];
     int nprog, total;
     int n, ci, co, bn, tiles_o, mt, px, patch_bytes, per_sample, dbg, splitk, cps, npb, patch_stride, nbst, b_stride, sm_b, sm_stg, pair;
+    int swap, trows;                  // swap: output channels on M, 256 pixels (32 rows x 8) on N; trows = image rows per tile (16 or 32)
     const float* bias; const float* noise; const float* noise_strength;
     int noise_w, out_h, out_w;
     int act; float slope, gain, clamp;
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                 const TileCoord c = decode_tile(a, t);
                 const int4* st = steps + c.q * MAXV * MAXT;
                 const int ns = nsteps[c.q];
-                const int x0 = c.tx * xmul + rank * 8, y0 = c.ty * 16;
+                const int x0 = c.tx * xmul + rank * 8, y0 = c.ty * a.trows;
                 const int c1 = min(cchunks, (c.ks + 1) * a.cps);
                 for (int cc = c.ks * a.cps; cc < c1; cc++)
                     for (int j = 0; j < ns; j++) {
@@ -244,7 +245,8 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
         }
     } else if (warp == 2) {
         if (lane == 0 && rank == 0) {
-            const uint32_t idesc = idesc_tf32(PAIR ? 256 : 128, a.bn);
+            const uint32_t idesc = idesc_tf32(PAIR ? 256 : 128, a.swap ? 256 : a.bn);
+            const bool swp = !PAIR && a.swap;
             // descriptor words: hi = SBO | version 1 | SWIZZLE_128B, lo = (address >> 4) | LBO 1; advancing an operand only adds to lo
             const uint32_t a_hi = (((uint32_t)a.px * 128u) >> 4) | (1u << 14) | (2u << 29);
             const uint32_t b_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
@@ -279,6 +281,13 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
                             mma_lohi_2sm(dcol, alo + 2, a_hi, blo + 2, b_hi, idesc, 1u);
                             mma_lohi_2sm(dcol, alo + 4, a_hi, blo + 4, b_hi, idesc, 1u);
                             mma_lohi_2sm(dcol, alo + 6, a_hi, blo + 6, b_hi, idesc, 1u);
+                        } else if (swp) {
+                            // swapped roles: A = the [128 co x 32 ci] weight tile, B = 256 pixels of the patch (32 rows x 8 px, 8-pixel groups at
+                            // a stride of PX * 128 bytes): D[co lane][pixel column], one N = 256 instruction per K step
+                            mma_lohi(dcol, blo, b_hi, alo, a_hi, idesc, acc);
+                            mma_lohi(dcol, blo + 2, b_hi, alo + 2, a_hi, idesc, 1u);
+                            mma_lohi(dcol, blo + 4, b_hi, alo + 4, a_hi, idesc, 1u);
+                            mma_lohi(dcol, blo + 6, b_hi, alo + 6, a_hi, idesc, 1u);
                         } else {
                         mma_lohi(dcol, alo, a_hi, blo, b_hi, idesc, acc);
                         mma_lohi(dcol, alo + 2, a_hi, blo + 2, b_hi, idesc, 1u);
@@ -322,6 +331,52 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             if (!mbar_wait_bounded(&tfull[buf], (local >> 1) & 1)) { atomicExch(a.err, 16); break; }
             fence_after();
             const bool fuse = P.fuse_epilogue != 0;
+            if (!PAIR && a.swap) {
+                // D[co lane][pixel column]: this thread owns output channel og of 32 pixels per chunk (4 image rows x 8 px).  Each warp
+                // stages its own [32 px][32 ch] tile (a lane writes one float per pixel row: 32 lanes = one 128-byte row, conflict-free)
+                // and stores it with its own TMA box {32 ch, 8 px, 4 rows}: no barrier between the four warps inside a tile.
+                const int og = c.ot * 128 + row;
+                const float bv = (fuse && a.bias && og < a.co) ? __ldg(a.bias + og) : 0.f;
+                const int xo = c.tx * 8, yo = c.ty * 32;
+                const uint32_t tbase = tm + ((uint32_t)(q * 32) << 16) + buf * 256;
+                const uint32_t so = (uint32_t)((lane & 3) * 4);
+                const int kc = lane >> 2;
+#pragma unroll 1
+                for (int cb = 0; cb < 8; cb++, cidx++) {
+                    if (yo + 4 * cb >= a.out_h) break;
+                    float v[32];
+                    tmem_ld32(tbase + cb * 32, v);
+                    tmem_wait_ld();
+                    if (lane == 0) tma_wait_group_read<1>();       // this warp's staging buffer of two chunks ago has been read
+                    __syncwarp();
+                    uint8_t* stg = sC + q * 8192 + (cidx & 1) * 4096;
+                    if (fuse) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) {
+                            float nzv = 0.f;
+                            if (a.noise) {
+                                const int py = yo + 4 * cb + (j >> 3), px = xo + (j & 7);
+                                if (py < a.out_h && px < a.out_w) nzv = __ldg(a.noise + py * a.noise_w + px) * strength;      // same address for the whole warp
+                            }
+                            const float e = v[j] + (nzv + bv);
+                            *reinterpret_cast<float*>(stg + swz(j, kc) + so) = fminf(fmaxf(fmaxf(e, e * neg) * gain, -cl), cl);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) *reinterpret_cast<float*>(stg + swz(j, kc) + so) = v[j];
+                    }
+                    fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0 && !(a.dbg & 16)) {
+                        tma_store_4d(&a.omap[1], stg, c.ot * 128 + q * 32, xo, yo + 4 * cb, c.n);
+                        tma_commit_group();
+                    }
+                }
+                fence_before();
+                named_bar_sync(1, 128);
+                if (leader) mbar_arrive(&tempty[buf]);
+                continue;
+            }
             if (fuse) {          // read by everybody after the first barrier of the chunk loop; the previous tile's readers are past their last barrier
                 for (int o = row; o < a.bn; o += 128) {
                     const int og = c.ot * a.bn + o;
@@ -374,7 +429,7 @@ __global__ void __launch_bounds__(NT2, 1) conv_tc2_kernel(const __grid_constant_
             named_bar_sync(1, 128);
             if (leader) { if (PAIR) mbar_arrive_leader(&tempty[buf]); else mbar_arrive(&tempty[buf]); }
         }
-        if (leader) tma_wait_group_read<0>();      // the staging tiles have been read; the stores themselves complete with the grid (as CUTLASS' tma_store_wait<0>)
+        if (leader || (a.swap && lane == 0)) tma_wait_group_read<0>();      // the staging tiles have been read; the stores themselves complete with the grid (as CUTLASS' tma_store_wait<0>)
     }
     fence_before();
     __syncthreads();
@@ -440,7 +495,7 @@ int pick_bn(int co) { return co % 128 == 0 ? 128 : (co % 96 == 0 && co <= 96 ? 9
 // epilogue is possible (`allow_split` is false when the caller asked for one).  `tiles_pn` = pixel tiles x images.
 void plan_tiles(Conv2Args& a, int tiles_pn, bool allow_split) {
     const int cchunks = a.ci / 32, sms = spi_num_sms();
-    if (a.bn == 128 && (long long)tiles_pn * a.tiles_o * (allow_split ? cchunks : 1) < sms) { a.bn = 64; a.tiles_o = cdiv(a.co, a.bn); }
+    if (!a.swap && a.bn == 128 && (long long)tiles_pn * a.tiles_o * (allow_split ? cchunks : 1) < sms) { a.bn = 64; a.tiles_o = cdiv(a.co, a.bn); }
     const int tiles = tiles_pn * a.tiles_o;
     a.splitk = 1; a.cps = cchunks;
     if (!allow_split || tiles >= sms * 3 / 4 || cchunks < 2) return;
@@ -524,6 +579,7 @@ void common_args(Conv2Args& a, int n, int ci, int co, int per_sample, int wv_out
         a.mt = (wv_out > 8 && !(flags & 4)) ? 2 : 1;
     }
     a.tiles_o = cdiv(co, a.bn);
+    a.trows = 16;
     a.dbg = flags;
     a.gain = 1.f; a.clamp = -1.f;
     // CTA pairs (cta_group::2, M = 256): the two M tiles of a 16-pixel-wide tile go to the two CTAs of a cluster, each loads half of the
@@ -560,15 +616,23 @@ static int conv_s1(bool plan_only, const float* x, const float* w, float* y, int
     const bool epi = bias || noise || act != 0 || gain != 1.f || clamp >= 0.f;
     common_args(a, n, ci, co, per_sample, wd, h, flags, !epi);
     const int halo = k / 2;
+    // Cout = 128 tiles on a map that fills the chip: swap the operand roles -- the [128 co x 32 ci] weight tile becomes A and 256 pixels
+    // (32 rows x 8 px of the halo patch) become B, so that every instruction is M128 x N256 (96 B/clk of shared-memory operand reads
+    // instead of the 128 B/clk that bound the N = 128 form at 57 % tensor pipe).  flags bit 10 (1024) keeps the unswapped form.
+    if (!(flags & 1024) && a.bn == 128 && !a.pair && co % 128 == 0 &&
+        (long long)cdiv(wd, 8) * cdiv(h, 32) * n * (co / 128) >= spi_num_sms() * 3 / 4) {
+        a.swap = 1; a.mt = 1; a.trows = 32;
+    }
     a.px = a.mt * 8 + (halo ? ((flags & 64) ? 8 : 2 * halo) : 0);
-    const int rows = 16 + 2 * halo;
+    const int rows = a.trows + 2 * halo;
     a.patch_bytes = rows * a.px * 128;
     const int tile_w = a.pair ? 16 : a.mt * 8;
-    plan_tiles(a, cdiv(wd, tile_w) * cdiv(h, 16) * n, !epi && !(flags & 32));
+    plan_tiles(a, cdiv(wd, tile_w) * cdiv(h, a.trows) * n, !epi && !(flags & 32) && !a.swap);
     if (plan_only) return a.splitk;
     zero_split_output(a, y, (size_t)n * h * wd * co * 4, stream);
     if (!map_image(&a.amap[0], x, ci, wd, h, n, (long long)ci * 4, (long long)wd * ci * 4, (long long)h * wd * ci * 4, a.px, rows, rnd) ||
         !map_image(&a.omap[0], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 16, 0) ||
+        (a.swap && !map_image(&a.omap[1], y, co, wd, h, n, (long long)co * 4, (long long)wd * co * 4, (long long)h * wd * co * 4, 8, 4, 0)) ||
         !map_weights(a, w, k * k, per_sample ? n : 1, rnd)) {
         spi_set_error("spi_conv2d_tc2: cuTensorMapEncodeTiled failed");
         return SPI_ERR_CUDA;
@@ -576,7 +640,7 @@ static int conv_s1(bool plan_only, const float* x, const float* w, float* y, int
     for (int i = 1; i < MAXV; i++) a.amap[i] = a.amap[0];
     Program& P = a.prog[0];
     P.nviews = 1; P.omap = 0; P.tile_begin = 0; P.fuse_epilogue = 1;
-    P.tiles_x = cdiv(wd, tile_w); P.tiles_y = cdiv(h, 16);
+    P.tiles_x = cdiv(wd, tile_w); P.tiles_y = cdiv(h, a.trows);
     View& V = P.views[0];
     V.amap = 0; V.oy = -halo; V.ox = -halo; V.ntaps = k * k;
     for (int ky = 0; ky < k; ky++)

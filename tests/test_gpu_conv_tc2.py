@@ -274,3 +274,30 @@ def test_rows_outer_sum(lib, rows, cu, cv):
     out2 = torch.empty_like(out)
     _lib.check(lib.spi_rows_outer_sum(_lib.ptr(u), _lib.ptr(v), rows, cu, cv, _lib.ptr(out2), None, _lib.stream()))
     assert rel_l2(out2, out) < 1e-5
+
+
+@pytest.mark.parametrize('n,ci,co,h,wd,k,epi', [
+    (1, 128, 128, 256, 256, 3, False), (1, 128, 128, 256, 256, 3, True), (2, 96, 128, 130, 204, 3, True), (1, 64, 128, 256, 256, 1, False),
+    (4, 32, 128, 96, 96, 3, True),
+])
+def test_swapped_operand_form_for_128_channel_tiles(lib, n, ci, co, h, wd, k, epi, monkeypatch):
+    """Cout = 128 layers on large maps run with the operand roles swapped (weights on M, 256 pixels on N: M128 x N256 instructions, per-warp
+    TMA stores of [32 px][32 ch] boxes).  Same results as the unswapped form (flag 1024) and as fp64, ragged right / bottom edges included."""
+    from spi_b200.ops import conv as E
+    gen, x, w = _mk(n, ci, co, h, wd, k, False, 17 + ci + h)
+    wk = E._ohwi(w).view(1, co, k * k, ci)
+    e = None
+    if epi:
+        e = dict(b=torch.randn(co, generator=gen).cuda(), noise=torch.randn(h, wd, generator=gen).cuda(), strength=torch.tensor(0.7).cuda(), act=2, slope=0.2,
+                 gain=1.4, clamp=2.5)
+    y_swapped = E.tc2_s1(x, wk, k, False, e, allow_split=e is None)
+    monkeypatch.setattr(E, 'TC2_FLAGS', E.TC2_FLAGS | 1024)
+    y_plain = E.tc2_s1(x, wk, k, False, e, allow_split=e is None)
+    assert lib.spi_tc_error() == 0
+    ref = F.conv2d(x.double(), w[0].double(), padding=k // 2)
+    if epi:
+        ref = ref + e['noise'].double() * 0.7 + e['b'].double().view(1, -1, 1, 1)
+        ref = (torch.where(ref > 0, ref, ref * 0.2) * 1.4).clamp(-2.5, 2.5)
+    assert y_swapped.shape == ref.shape and y_swapped.is_contiguous(memory_format=CL)
+    assert rel_l2(y_plain, ref) < TOL and rel_l2(y_swapped, ref) < TOL
+    assert rel_l2(y_swapped, y_plain) < 1e-6          # same operands, same accumulation order over (chunk, tap, k): rounding-identical
