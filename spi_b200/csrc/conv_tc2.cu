@@ -16,6 +16,9 @@
 // is not a multiple of the 1024-byte atom disturbs the pattern TMA wrote: PX is just the tile width plus the halo (18 for 3x3).  The nine taps are nine descriptors into the same
 // patch; A traffic drops from 9 x 16 KB to 27 KB per M tile and chunk, and each B (weight) tile is used by MT M tiles.
 // 3x3, Cout tile 128, MT = 2: (55 + 147) KB per 4608 MMA cycles = 44 B/clk/SM.
+// Tile forms: Cout % 256 == 0 on a chip-filling map: one M tile x N = 256 channels; Cout = 128 tiles on a chip-filling map: operand roles
+// swapped (A = weight tile, B = 256 pixels of a [34 rows][10 px] patch: M128 x N256 again, accumulator = channels x pixels, per-warp
+// epilogue stores); otherwise MT = 2 M tiles x N <= 128; maps too small for 148 tiles split Cin over CTAs (reduce-add stores).
 //
 // Warp roles (256 threads, persistent CTAs, static round-robin over tiles):
 //   warp 0  patch producer (one lane): empty_a -> TMA box load of the next (view, chunk) patch -> full_a          (2 buffers)
