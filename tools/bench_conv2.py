@@ -293,8 +293,16 @@ def ncu_target():
     y = torch.empty(1, 128, 512, 512, device='cuda', memory_format=CL)
     for _ in range(3):
         _lib.check(L.spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), 1, 512, 512, 128, 128, 3, 0, None, None, None, 0, 0.2, 1.0, -1.0, 0, _lib.stream()))
+    for _ in range(3):      # the same layer in the unswapped form (two M tiles x N = 128) for comparison
+        _lib.check(L.spi_conv2d_tc2(_lib.ptr(x), _lib.ptr(w), _lib.ptr(y), 1, 512, 512, 128, 128, 3, 0, None, None, None, 0, 0.2, 1.0, -1.0, 1024, _lib.stream()))
     for _ in range(3):
         wgrad(x, dy, 128, 128, 3, False, 0)
+    # layer-epilogue backward in one pass (activation gradient + bias / noise-strength gradients) on the same tensor
+    db, nz = torch.empty(129, device='cuda'), torch.randn(512, 512, device='cuda')
+    dx = torch.empty_like(y)
+    for _ in range(3):
+        _lib.check(L.spi_bias_act_grad_reduce(_lib.ptr(dy), _lib.ptr(y), _lib.ptr(dx), dy.numel(), 128, 512 * 512, 3, 0.2, 1.4, 256.0, _lib.ptr(nz), _lib.ptr(db),
+                                              db.data_ptr() + 128 * 4, _lib.stream()))
     x2, w2, _ = make(4, 256, 256, 256, 256, 3, False)
     y2 = torch.empty(4, 256, 256, 256, device='cuda', memory_format=CL)
     for _ in range(3):
