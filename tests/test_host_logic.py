@@ -245,3 +245,27 @@ def test_zero_arena_sizing_and_fallback():
     with Z.iteration('other', cpu):
         assert not Z.active()
     Z.reset()
+
+
+def test_modulation_plan_and_bank_rules(monkeypatch):
+    """Host-side decisions of the grouped modulation (no kernels): layout / tap reversal / transposed copy per layer kind and engine,
+    and which layer sets the grouped kernels accept."""
+    from spi_b200.ops import conv as E
+    from spi_b200.ops.modulate import bank_usable
+    from spi_b200.training.networks_stylegan2 import modulation_plan
+    w33 = torch.empty(128, 256, 3, 3)
+    w11 = torch.empty(96, 512, 1, 1)
+    wrgb = torch.empty(3, 128, 1, 1)
+    monkeypatch.setattr(E, 'ENGINE', 'tc2')
+    assert modulation_plan(w33, 1, True) == ('ohwi', False, 'rev')            # non-resampling layer: taps as stored, reversed copy for the data gradient
+    assert modulation_plan(w33, 1, False) == ('ohwi', True, 'rev')            # flip_weight=False: modulate writes the taps reversed
+    assert modulation_plan(w33, 2, False) == ('ohwi', False, 'keep')          # up-sampling layer on the engine: [O][taps][I], plain transposed copy
+    assert modulation_plan(w11, 1, True) == ('ohwi', False, 'rev')
+    assert modulation_plan(wrgb, 1, True) == ('ohwi', False, None)            # RGB head (3 channels): streaming kernels, no transposed copy
+    monkeypatch.setattr(E, 'ENGINE', 'cudnn')
+    assert modulation_plan(w33, 2, False) == ('ihwo', False, None)            # the library's transposed convolution wants [I][taps][O]
+    assert modulation_plan(w33, 1, True) == ('ohwi', False, None)
+    # bank_usable: CUDA fp32 only (a CPU tensor is refused without touching the library), layouts OIHW / OHWI, rows that fit in shared memory
+    s = torch.empty(1, 256)
+    assert not bank_usable([(w33, s, True, 'ohwi', False, 'rev')])
+    assert not bank_usable([])
