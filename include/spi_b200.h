@@ -298,10 +298,13 @@ int spi_noise_renorm(const void* table, int count, cudaStream_t stream);
 /* ---- one LPIPS feature tap: spi/criteria/lpips/lpips.py:50-71 + utils.normalize_activation, fused.
  * x: raw VGG features of the generated image, channels-last fp32 [n, hw, c]; yn: unit-normalised target features [ny, hw, c]
  * (ny = n or 1, constant); lin: 1x1 lin-layer weights [c].  forward ACCUMULATES out[0] += sum_n mean_hw sum_c lin_c (xn_c - yn_c)^2
- * with xn = x / (sqrt(sum_c x^2) + 1e-10); backward writes dx = gout[0] * d(tap)/dx. */
-int spi_lpips_tap_forward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, float* out, cudaStream_t stream);
+ * with xn = x / (sqrt(sum_c x^2) + 1e-10); backward writes dx = gout[0] * d(tap)/dx.  sample_weight [n] (NULL = ones) weights the sum
+ * over n: the two views of the mirror projector (`mirror_projector.py:100-104`: lpips(img, target) + w_m * lpips(img_m, target_m)) share
+ * one pass of the VGG trunk that way. */
+int spi_lpips_tap_forward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, float* out,
+                          const float* sample_weight, cudaStream_t stream);
 int spi_lpips_tap_backward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, const float* gout, float* dx,
-                           cudaStream_t stream);
+                           const float* sample_weight, cudaStream_t stream);
 
 /* out[c] = sum over rows of x[row, c]; x row-major [rows, cols] fp32, cols a multiple of 4 (<= 128).  Used for the decoder bias
  * gradients db1 = sum dpre, db2 = sum dout over the per-sample rows of spi_render_backward (triplane.py:123-135). */

@@ -51,8 +51,8 @@ _SIGS = {
     'spi_noise_reg_forward': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p],
     'spi_noise_reg_backward': [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'spi_noise_renorm': [c_void_p, c_int, c_void_p],
-    'spi_lpips_tap_forward': [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p],
-    'spi_lpips_tap_backward': [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p],
+    'spi_lpips_tap_forward': [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p],
+    'spi_lpips_tap_backward': [c_void_p] * 3 + [c_int] * 4 + [c_void_p, c_void_p, c_void_p, c_void_p],
     'spi_column_sums': [c_void_p, c_ll, c_int, c_void_p, c_void_p],
     'spi_maxpool2x2': [c_void_p] * 3 + [c_int] * 5 + [c_void_p],
     'spi_conv2d_tc_supported': [c_int] * 6,

@@ -29,6 +29,7 @@ class LPIPS(nn.Module):
         self.num_scales = num_scales
         self._cache = {}                 # id(y) -> (y, version, resize, feats); holds y alive so its id/ptr cannot be recycled
         self._retired = []
+        self._pairs = {}                 # ids of cached target taps -> their concatenation over the batch (weighted_pairs)
 
     def load_weights(self, vgg_features_state_dict, lin_weights):
         """vgg_features_state_dict: torchvision `vgg16().features` names ('0.weight', ...); lin_weights: 5 x [1,C,1,1]."""
@@ -56,6 +57,7 @@ class LPIPS(nn.Module):
         reads them will be replayed again -- the coaches do so when they start a new image and drop that image's graphs."""
         self._cache.clear()
         self._retired.clear()
+        self._pairs.clear()
 
     def _target_feats(self, y, resize):
         if y.requires_grad:
@@ -72,6 +74,29 @@ class LPIPS(nn.Module):
             self._cache[id(y)] = (y, y._version, resize, feats)
             return feats
         return hit[3]
+
+    def weighted_pairs(self, x, targets, weights):
+        """sum_n weights[n] * LPIPS(x[n:n+1], targets[n]) for constant targets (one per sample of x) and a device vector `weights` [N]:
+        the expression of the mirror projector (mirror_projector.py:100-104: lpips(img, target) + w_m * lpips(img_m, target_m)) with ONE pass
+        of the VGG trunk over the batch instead of one per pair -- the trunk's small layers cost the same for 1 and 2 images."""
+        assert len(targets) == x.shape[0] and weights.shape == (x.shape[0],) and self.num_scales == 1
+        resize = x.shape[-1] > 256
+        per_target = [self._target_feats(t, resize) for t in targets]
+        if not all(_fusable(f, t) for f, t in zip(per_target, targets)):
+            return sum(self.forward(x[i:i + 1], t) * weights[i] for i, t in enumerate(targets))
+        registered = all(self._cache.get(id(t), (None,))[0] is t for t in targets)
+        key = tuple(id(f[0]) for f in per_target)
+        hit = self._pairs.get(key) if registered else None
+        if hit is None:               # concatenated taps of this set of targets (registered targets: kept, captured graphs read them)
+            hit = ([torch.cat([f[k] for f in per_target], 0) for k in range(len(per_target[0]))], per_target)
+            if registered:
+                if len(self._pairs) > 8:
+                    self._retired.extend(self._pairs.values())
+                    self._pairs.clear()
+                self._pairs[key] = hit
+        feat_x = self.net(self._resize(x) if resize else x, normalize=False)
+        lins = [l[1].weight.reshape(-1) for l in self.lin]
+        return _LpipsTail.apply(len(feat_x), *feat_x, *hit[0], *lins, weights.float().contiguous())
 
     def forward(self, x, y, conf_sigma=None, mask=None):
         assert conf_sigma is None and mask is None, 'conf_sigma / mask variants are not used by SPI and not built'
@@ -92,7 +117,8 @@ class LPIPS(nn.Module):
 
 
 def _fusable(feat_y, y):
-    return (not y.requires_grad) and all((not f.requires_grad) and f.dtype == torch.float32 and f.shape[1] % 4 == 0 and f.shape[1] <= 512
+    ys = y if isinstance(y, (tuple, list)) else (y,)
+    return (not any(t.requires_grad for t in ys)) and all((not f.requires_grad) and f.dtype == torch.float32 and f.shape[1] % 4 == 0 and f.shape[1] <= 512
                                          for f in feat_y)
 
 
@@ -104,15 +130,16 @@ class _LpipsTail(torch.autograd.Function):
         from ... import _lib
         xs = [a.contiguous(memory_format=torch.channels_last) for a in args[:k]]
         ys = [a.contiguous(memory_format=torch.channels_last) for a in args[k:2 * k]]
-        lins = [a.contiguous() for a in args[2 * k:]]
+        lins = [a.contiguous() for a in args[2 * k:3 * k]]
+        sw = args[3 * k] if len(args) > 3 * k else None            # per-sample weights of the sum over the batch
         out = torch.zeros((), device=xs[0].device)
         lib = _lib.load()
         for fx, fy, w in zip(xs, ys, lins):
             n, c, h, wd = fx.shape
             assert fy.shape[1:] == fx.shape[1:] and fy.shape[0] in (1, n)
-            _lib.check(lib.spi_lpips_tap_forward(_lib.ptr(fx), _lib.ptr(fy), _lib.ptr(w), n, h * wd, c, fy.shape[0], _lib.ptr(out), _lib.stream()))
-        ctx.k = k
-        ctx.save_for_backward(*xs, *ys, *lins)
+            _lib.check(lib.spi_lpips_tap_forward(_lib.ptr(fx), _lib.ptr(fy), _lib.ptr(w), n, h * wd, c, fy.shape[0], _lib.ptr(out), _lib.ptr(sw), _lib.stream()))
+        ctx.k, ctx.has_sw = k, sw is not None
+        ctx.save_for_backward(*xs, *ys, *lins, *([sw] if sw is not None else []))
         return out
 
     @staticmethod
@@ -120,7 +147,8 @@ class _LpipsTail(torch.autograd.Function):
         from ... import _lib
         k = ctx.k
         saved = ctx.saved_tensors
-        xs, ys, lins = saved[:k], saved[k:2 * k], saved[2 * k:]
+        xs, ys, lins = saved[:k], saved[k:2 * k], saved[2 * k:3 * k]
+        sw = saved[3 * k] if ctx.has_sw else None
         gout = gout.contiguous().float()
         lib = _lib.load()
         grads = []
@@ -131,6 +159,6 @@ class _LpipsTail(torch.autograd.Function):
             n, c, h, wd = fx.shape
             dx = torch.empty_like(fx)
             _lib.check(lib.spi_lpips_tap_backward(_lib.ptr(fx), _lib.ptr(fy), _lib.ptr(w), n, h * wd, c, fy.shape[0], _lib.ptr(gout), _lib.ptr(dx),
-                                                  _lib.stream()))
+                                                  _lib.ptr(sw), _lib.stream()))
             grads.append(dx)
-        return (None, *grads, *([None] * (2 * k)))
+        return (None, *grads, *([None] * (2 * k + (1 if ctx.has_sw else 0))))

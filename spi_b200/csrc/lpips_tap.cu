@@ -14,7 +14,7 @@ constexpr int LT_MAXG = 4;      // float4 groups per lane: C <= 512
 template <int NG, bool BWD>
 __global__ void __launch_bounds__(256) lpips_tap_kernel(const float* __restrict__ x, const float* __restrict__ yn, const float* __restrict__ lin,
                                                         int n, int hw, int C, int ny, float inv_hw, const float* __restrict__ gout,
-                                                        float* __restrict__ out, float* __restrict__ dx) {
+                                                        float* __restrict__ out, float* __restrict__ dx, const float* __restrict__ sample_w) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int groups = C >> 2;
     float4 wl[NG];
@@ -23,10 +23,12 @@ __global__ void __launch_bounds__(256) lpips_tap_kernel(const float* __restrict_
         const int gi = lane + 32 * g;
         wl[g] = gi < groups ? *reinterpret_cast<const float4*>(lin + 4 * gi) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    const float go = BWD ? gout[0] * inv_hw : 0.f;
+    const float go0 = BWD ? gout[0] * inv_hw : 0.f;
     const long long pixels = (long long)n * hw;
     float part = 0.f;
     for (long long p = (long long)blockIdx.x * 8 + warp; p < pixels; p += (long long)gridDim.x * 8) {
+        const float sw = sample_w ? __ldg(sample_w + p / hw) : 1.f;           // per-sample weight of the sum over n (NULL: 1)
+        const float go = go0 * sw;
         const float4* xr = reinterpret_cast<const float4*>(x + p * C);
         const long long py = ny == n ? p : p % hw;
         const float4* yr = reinterpret_cast<const float4*>(yn + py * C);
@@ -54,7 +56,7 @@ __global__ void __launch_bounds__(256) lpips_tap_kernel(const float* __restrict_
                 s += q[g].x * xv[g].x + q[g].y * xv[g].y + q[g].z * xv[g].z + q[g].w * xv[g].w;
             }
         }
-        if (!BWD) part += d;
+        if (!BWD) part += d * sw;
         else {
             s = warp_sum(s);
             // d tap / d x_k = q_k / (n + eps) - (sum_c q_c x_c) x_k / (n (n + eps)^2); an all-zero feature vector gets a zero gradient
@@ -84,15 +86,15 @@ __global__ void __launch_bounds__(256) lpips_tap_kernel(const float* __restrict_
 
 template <bool BWD>
 int launch_tap(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, const float* gout, float* out, float* dx,
-               cudaStream_t stream) {
+               const float* sample_w, cudaStream_t stream) {
     const long long pixels = (long long)n * hw;
     long long want = (pixels + 7) / 8, cap = (long long)spi_num_sms() * 8;
     const int grid = (int)(want < cap ? want : cap);
     const float inv_hw = 1.f / (float)hw;
     const int ng = (c + 127) / 128;
-    if (ng <= 1) lpips_tap_kernel<1, BWD><<<grid, 256, 0, stream>>>(x, yn, lin, n, hw, c, ny, inv_hw, gout, out, dx);
-    else if (ng <= 2) lpips_tap_kernel<2, BWD><<<grid, 256, 0, stream>>>(x, yn, lin, n, hw, c, ny, inv_hw, gout, out, dx);
-    else lpips_tap_kernel<4, BWD><<<grid, 256, 0, stream>>>(x, yn, lin, n, hw, c, ny, inv_hw, gout, out, dx);
+    if (ng <= 1) lpips_tap_kernel<1, BWD><<<grid, 256, 0, stream>>>(x, yn, lin, n, hw, c, ny, inv_hw, gout, out, dx, sample_w);
+    else if (ng <= 2) lpips_tap_kernel<2, BWD><<<grid, 256, 0, stream>>>(x, yn, lin, n, hw, c, ny, inv_hw, gout, out, dx, sample_w);
+    else lpips_tap_kernel<4, BWD><<<grid, 256, 0, stream>>>(x, yn, lin, n, hw, c, ny, inv_hw, gout, out, dx, sample_w);
     SPI_COUNT_LAUNCH(1);
     SPI_LAUNCH_CHECK("lpips_tap");
     return SPI_OK;
@@ -108,18 +110,19 @@ int check_tap(const float* x, const float* yn, const float* lin, int n, int hw, 
 
 }  // namespace
 
-/* out[0] += sum_n mean_hw sum_c lin_c (x_c / (|x| + 1e-10) - yn_c)^2   (out is accumulated: the caller zeroes it once per LPIPS call) */
+/* out[0] += sum_n sw_n mean_hw sum_c lin_c (x_c / (|x| + 1e-10) - yn_c)^2   (out is accumulated: the caller zeroes it once per LPIPS call;
+ * sample_weight [n] or NULL = all ones: lets several (image, target) pairs with different loss weights share one pass of the trunk) */
 extern "C" int spi_lpips_tap_forward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, float* out,
-                                     cudaStream_t stream) {
+                                     const float* sample_weight, cudaStream_t stream) {
     if (int rc = check_tap(x, yn, lin, n, hw, c, ny)) return rc;
     SPI_CHECK_ARG(out, "lpips_tap_forward: null output");
-    return launch_tap<false>(x, yn, lin, n, hw, c, ny, nullptr, out, nullptr, stream);
+    return launch_tap<false>(x, yn, lin, n, hw, c, ny, nullptr, out, nullptr, sample_weight, stream);
 }
 
 /* dx = gout[0] * d tap / d x   (written) */
 extern "C" int spi_lpips_tap_backward(const float* x, const float* yn, const float* lin, int n, int hw, int c, int ny, const float* gout,
-                                      float* dx, cudaStream_t stream) {
+                                      float* dx, const float* sample_weight, cudaStream_t stream) {
     if (int rc = check_tap(x, yn, lin, n, hw, c, ny)) return rc;
     SPI_CHECK_ARG(gout && dx && (((uintptr_t)dx) & 15) == 0, "lpips_tap_backward: null / misaligned pointer");
-    return launch_tap<true>(x, yn, lin, n, hw, c, ny, gout, nullptr, dx, stream);
+    return launch_tap<true>(x, yn, lin, n, hw, c, ny, gout, nullptr, dx, sample_weight, stream);
 }

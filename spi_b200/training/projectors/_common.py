@@ -77,6 +77,7 @@ class LatentProjector:
             camera_m = cal_mirror_c(camera=c)
             self.target_camera = torch.cat([c, camera_m], dim=0)
             self.weight_m = cal_camera_weight(camera_m)[0]
+            self._pair_weights = torch.stack([torch.ones((), device=device), self.weight_m.reshape(()).to(device=device, dtype=torch.float32)])
         if kind == 'sg':
             with torch.no_grad():
                 self.target_features = vgg16(area_256((target + 1) * (255 / 2)), resize_images=False, return_lpips=True)
@@ -105,7 +106,11 @@ class LatentProjector:
             ws2 = ws.expand(2, -1, -1) if global_config.share_backbone else ws.repeat(2, 1, 1)
             out = G.synthesis(ws2, self.target_camera, noise_mode='const')
             img = out['image']
-            dist = self.lpips_func(img[:1], self.target) + self.lpips_func(img[1:], self.target_m) * self.weight_m
+            if hasattr(self.lpips_func, 'weighted_pairs'):
+                # lpips(img, target) + weight_m * lpips(img_m, target_m) (mirror_projector.py:100-104) with one pass of the VGG trunk
+                dist = self.lpips_func.weighted_pairs(img, (self.target, self.target_m), self._pair_weights)
+            else:
+                dist = self.lpips_func(img[:1], self.target) + self.lpips_func(img[1:], self.target_m) * self.weight_m
         elif self.kind == 'sgw+':
             img = G.synthesis(ws, self.c, noise_mode='const')['image']
             dist = self.lpips_func(img, self.target)

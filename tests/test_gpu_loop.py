@@ -67,6 +67,29 @@ def test_lpips_gradient_vs_oracle(lpips_mod, nets):
     assert rel_l2(xg.grad, xo.grad) < 0.1      # white-noise input + TF32 contraction: heavy cancellation in d(LPIPS)/dx
 
 
+def test_lpips_weighted_pairs_equals_separate_calls(lpips_mod):
+    """The mirror projector's lpips(img, target) + w_m * lpips(img_m, target_m) evaluated with one pass of the VGG trunk over both views
+    (`LPIPS.weighted_pairs`) against the two separate calls: value and gradient, registered (cached) and unregistered targets."""
+    gen = torch.Generator().manual_seed(4)
+    x = (torch.rand(2, 3, 512, 512, generator=gen) * 2 - 1).cuda()
+    t0 = weights.target_image().cuda()
+    t1 = torch.flip(t0, dims=[3]).contiguous()
+    w = torch.tensor([1.0, 0.37], device='cuda')
+    for registered in (False, True):
+        if registered:
+            lpips_mod.register_target(t0)
+            lpips_mod.register_target(t1)
+        xa = x.clone().requires_grad_(True)
+        la = lpips_mod.weighted_pairs(xa, (t0, t1), w)
+        la.backward()
+        xb = x.clone().requires_grad_(True)
+        lb = lpips_mod(xb[:1], t0) + lpips_mod(xb[1:], t1) * w[1]
+        lb.backward()
+        assert abs(float(la) / float(lb) - 1) < 1e-4
+        assert rel_l2(xa.grad, xb.grad) < 0.1       # white-noise input + TF32 trunk at batch 2 vs batch 1 (other tile shapes / split counts): same class as above
+    lpips_mod.release_targets()
+
+
 def make_coach(kind, gen_sd, lpips_mod, cx_mod):
     from spi_b200.configs import hyperparameters, paths_config
     paths_config.EG3D_PATH = 'synthetic:0'
