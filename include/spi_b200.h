@@ -23,7 +23,7 @@ extern "C" {
 const char* spi_last_error(void);
 unsigned long long spi_launch_count(void);   /* kernels launched by this library since the last reset */
 void spi_reset_launch_count(void);
-int spi_abi_version(void);
+int spi_abi_version(void);                   /* 3 for this header; bumped whenever a signature below changes */
 
 /* ---- L1 operators: replace the pybind plugins built by eg3d/torch_utils/custom_ops.py:61 ------------- */
 

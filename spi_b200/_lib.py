@@ -76,6 +76,7 @@ _SIGS = {
     'spi_conv1x1_rgb': [c_int] + [c_void_p] * 3 + [c_ll] + [c_int] * 4 + [c_void_p],
 }
 
+ABI_VERSION = 3            # include/spi_b200.h: spi_abi_version()
 EXPORTS = sorted(list(_SIGS) + ['spi_last_error', 'spi_launch_count', 'spi_reset_launch_count', 'spi_abi_version'])
 
 
@@ -97,6 +98,9 @@ def load():
         lib.spi_last_error.restype = ctypes.c_char_p
         lib.spi_launch_count.restype = ctypes.c_ulonglong
         lib.spi_abi_version.restype = c_int
+        if lib.spi_abi_version() != ABI_VERSION:
+            raise RuntimeError(f'{_LIB_PATH} has ABI version {lib.spi_abi_version()}, this package binds version {ABI_VERSION}: rebuild it '
+                               '(`python -m spi_b200.build`)')
         _lib = lib
     return _lib
 

@@ -15,7 +15,7 @@ void spi_set_error(const char* fmt, ...) {
 extern "C" const char* spi_last_error() { return g_err; }
 extern "C" unsigned long long spi_launch_count() { return g_spi_launches; }
 extern "C" void spi_reset_launch_count() { g_spi_launches = 0; }
-extern "C" int spi_abi_version() { return 2; }
+extern "C" int spi_abi_version() { return 3; }       // 3: spi_lpips_tap_* take per-sample weights; grouped (style / modulation bank) entry points
 
 // Device flag shared by the tcgen05 kernels (conv_tc05.cu, raymarch_tc.cuh): set when a bounded mbarrier wait timed out.
 int* spi_tc_err_flag() {

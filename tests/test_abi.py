@@ -49,3 +49,12 @@ def test_product_never_imports_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), f
+
+
+def test_library_reports_the_abi_version_the_bindings_expect():
+    """A stale libspi_b200.so (older signatures) must fail at load, not misread arguments: the loader compares spi_abi_version()."""
+    from spi_b200 import _lib
+    lib = _lib.load()
+    assert lib.spi_abi_version() == _lib.ABI_VERSION == 3
+    header = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'spi_b200.h')).read()
+    assert 'spi_abi_version(void);' in header and '3 for this header' in header
